@@ -1,0 +1,728 @@
+"""CPU oracle for the IRON surface-rendering hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file restates, in plain PyTorch-CPU fp32 and as stateless functions over
+explicit parameter dictionaries, the algorithm of the reference's hot path
+(SURVEY.md section 8a).  It is NOT part of the product: only `tests/`,
+`__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
+`bench.py` may import it.  The product (`iron_b200/`) never does.
+
+Parity status: PINNED.  `oracle/make_golden.py` imports the real reference
+modules from /root/reference in the build container, runs them on seeded
+inputs and writes `tests/golden/*.npz`; `tests/test_oracle_golden.py` checks
+every function here against those files (masks exactly, floats to ~1e-6).
+
+Every function cites the reference lines it follows (paths relative to
+/root/reference).  Arithmetic is fp32; the oracle uses torch.autograd for
+derivatives exactly where the reference does, and additionally carries the
+closed-form input-gradient / double-backward of Appendix A so the
+CUDA kernels' formulas can be checked on CPU.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+Tensor = torch.Tensor
+Params = Dict[str, Tensor]
+
+SQRT2 = float(np.sqrt(2))
+
+# --------------------------------------------------------------------------
+# positional encoding                     models/embedder.py:11-36, 39-54
+# --------------------------------------------------------------------------
+
+
+def posenc(x: Tensor, n_freqs: int) -> Tensor:
+    """[x, sin(2^0 x), cos(2^0 x), ..., sin(2^(L-1) x), cos(2^(L-1) x)].
+
+    models/embedder.py:15-36 with include_input=True, log_sampling=True
+    (freq_bands = 2 ** linspace(0, L-1, L), :23).
+    """
+    if n_freqs <= 0:
+        return x
+    bands = 2.0 ** torch.linspace(0.0, n_freqs - 1, n_freqs)
+    out = [x]
+    for f in bands:
+        out.append(torch.sin(x * f))
+        out.append(torch.cos(x * f))
+    return torch.cat(out, dim=-1)
+
+
+def posenc_dim(n_freqs: int, d: int = 3) -> int:
+    return d * (1 + 2 * n_freqs) if n_freqs > 0 else d
+
+
+# --------------------------------------------------------------------------
+# weight-normalised linear layers         models/fields.py:75-76
+# --------------------------------------------------------------------------
+
+
+def wn_weight(p: Params, l: int) -> Tensor:
+    """Effective weight of old-style nn.utils.weight_norm(dim=0): W = v * (g / ||v||_row).
+    torch._weight_norm is the primitive nn.utils.weight_norm itself calls; using it (rather than
+    spelling the formula) keeps the oracle bit-identical to the reference -- a 1-ulp change of W
+    already moves ~0.5 % of silhouette rays by ~5e-5 inside the convergence band."""
+    return torch._weight_norm(p[f"lin{l}.weight_v"], p[f"lin{l}.weight_g"], 0)
+
+
+def wn_linear(p: Params, l: int, x: Tensor) -> Tensor:
+    return torch.nn.functional.linear(x, wn_weight(p, l), p[f"lin{l}.bias"])
+
+
+def n_lin(p: Params) -> int:
+    n = 0
+    while f"lin{n}.weight_v" in p:
+        n += 1
+    return n
+
+
+# --------------------------------------------------------------------------
+# parameter construction (mirrors the RNG consumption of the reference ctors)
+# --------------------------------------------------------------------------
+
+
+def _fresh_linear(n_in: int, n_out: int) -> Tuple[Tensor, Tensor]:
+    lin = torch.nn.Linear(n_in, n_out)
+    return lin.weight.data, lin.bias.data
+
+
+def make_sdf_params(
+    d_hidden: int = 256,
+    n_layers: int = 8,
+    d_out: int = 257,
+    skip_in: Sequence[int] = (4,),
+    multires: int = 6,
+    bias: float = 0.5,
+    d_in: int = 3,
+) -> Params:
+    """IDR geometric init, models/fields.py:26-78 (inside_outside=False).
+
+    Uses torch's global RNG in the same order as the reference constructor
+    (one nn.Linear per layer, then the init overrides), so the same
+    torch.manual_seed gives the same weights.
+    """
+    e = posenc_dim(multires, d_in)
+    dims = [e] + [d_hidden] * n_layers + [d_out]
+    L = len(dims)
+    p: Params = {}
+    for l in range(L - 1):
+        out_dim = dims[l + 1] - dims[0] if (l + 1) in skip_in else dims[l + 1]
+        w, b = _fresh_linear(dims[l], out_dim)
+        if l == L - 2:  # fields.py:48-55
+            torch.nn.init.normal_(w, mean=np.sqrt(np.pi) / np.sqrt(dims[l]), std=0.0001)
+            torch.nn.init.constant_(b, -bias)
+        elif multires > 0 and l == 0:  # :63-66
+            torch.nn.init.constant_(b, 0.0)
+            torch.nn.init.constant_(w[:, 3:], 0.0)
+            torch.nn.init.normal_(w[:, :3], 0.0, np.sqrt(2) / np.sqrt(out_dim))
+        elif multires > 0 and l in skip_in:  # :67-70
+            torch.nn.init.constant_(b, 0.0)
+            torch.nn.init.normal_(w, 0.0, np.sqrt(2) / np.sqrt(out_dim))
+            torch.nn.init.constant_(w[:, -(dims[0] - 3):], 0.0)
+        else:  # :71-73
+            torch.nn.init.constant_(b, 0.0)
+            torch.nn.init.normal_(w, 0.0, np.sqrt(2) / np.sqrt(out_dim))
+        # weight_norm(dim=0): g = ||w||_row, v = w     (:75-76)
+        p[f"lin{l}.bias"] = b.clone()
+        p[f"lin{l}.weight_g"] = w.norm(dim=1, keepdim=True).clone()
+        p[f"lin{l}.weight_v"] = w.clone()
+    return p
+
+
+# kwargs of the three material nets of the 'ggx' config, models/network_conf.py:72-120
+MATERIAL_NETS = {
+    "diffuse_albedo_network": dict(d_in=9, d_out=3, multires=0, multires_view=4, mode="idr",
+                                   squeeze_out=True, output_bias=0.0, output_scale=1.0),
+    "specular_albedo_network": dict(d_in=6, d_out=3, multires=6, multires_view=-1, mode="no_view_dir",
+                                    squeeze_out=False, output_bias=0.4, output_scale=0.1),
+    "specular_roughness_network": dict(d_in=6, d_out=1, multires=6, multires_view=-1, mode="no_view_dir",
+                                       squeeze_out=False, output_bias=0.1, output_scale=0.1),
+}
+
+
+def material_in_dim(cfg: dict, d_feature: int = 256) -> int:
+    """models/fields.py:163-175."""
+    d = cfg["d_in"] + d_feature
+    if cfg["multires"] > 0:
+        d += posenc_dim(cfg["multires"]) - 3
+    if cfg["multires_view"] > 0:
+        d += posenc_dim(cfg["multires_view"]) - 3
+    return d
+
+
+def make_material_params(cfg: dict, d_feature: int = 256, d_hidden: int = 256, n_layers: int = 4) -> Params:
+    """Default nn.Linear init + weight_norm, models/fields.py:163-195 (no skip)."""
+    dims = [material_in_dim(cfg, d_feature)] + [d_hidden] * n_layers + [cfg["d_out"]]
+    p: Params = {}
+    for l in range(len(dims) - 1):
+        w, b = _fresh_linear(dims[l], dims[l + 1])
+        p[f"lin{l}.bias"] = b.clone()
+        p[f"lin{l}.weight_g"] = w.norm(dim=1, keepdim=True).clone()
+        p[f"lin{l}.weight_v"] = w.clone()
+    return p
+
+
+def make_material_dict(d_feature: int = 256) -> Dict[str, Params]:
+    """The three nets in the order the reference dict literal builds them
+    (models/network_conf.py:50-120: color_network first -- its RNG draw is
+    reproduced and discarded -- then diffuse, specular x2 (duplicate key), roughness)."""
+    color_cfg = dict(d_in=9, d_out=3, multires=0, multires_view=4)
+    make_material_params(color_cfg, d_feature)  # color_network: consumes RNG, unused by 'ggx' render_fn
+    out = {"diffuse_albedo_network": make_material_params(MATERIAL_NETS["diffuse_albedo_network"], d_feature)}
+    make_material_params(MATERIAL_NETS["specular_albedo_network"], d_feature)  # first (overwritten) duplicate
+    out["specular_albedo_network"] = make_material_params(MATERIAL_NETS["specular_albedo_network"], d_feature)
+    out["specular_roughness_network"] = make_material_params(MATERIAL_NETS["specular_roughness_network"], d_feature)
+    return out
+
+
+# --------------------------------------------------------------------------
+# SDF MLP                                   models/fields.py:82-137
+# --------------------------------------------------------------------------
+
+
+def sdf_forward(p: Params, x: Tensor, scale: float = 1.0, multires: int = 6,
+                skip_in: Sequence[int] = (4,), beta: float = 100.0) -> Tensor:
+    """models/fields.py:82-98.  Returns [..., d_out]; column 0 is the SDF."""
+    L = n_lin(p)
+    e = posenc(x * scale, multires)
+    h = e
+    for l in range(L):
+        if l in skip_in:
+            h = torch.cat([h, e], dim=-1) / SQRT2
+        h = wn_linear(p, l, h)
+        if l < L - 1:
+            h = torch.nn.functional.softplus(h, beta=beta)
+    return torch.cat([h[..., :1] / scale, h[..., 1:]], dim=-1)
+
+
+def sdf_gradient(p: Params, x: Tensor, **kw) -> Tensor:
+    """models/fields.py:106-118 (graph kept)."""
+    x.requires_grad_(True)
+    y = sdf_forward(p, x, **kw)[..., :1]
+    return torch.autograd.grad(y, x, torch.ones_like(y), create_graph=True, retain_graph=True)[0]
+
+
+def sdf_get_all(p: Params, x: Tensor, is_training: bool = True, **kw) -> Tuple[Tensor, Tensor, Tensor]:
+    """models/fields.py:120-137."""
+    with torch.enable_grad():
+        x.requires_grad_(True)
+        out = sdf_forward(p, x, **kw)
+        y, feat = out[..., :1], out[..., 1:]
+        g = torch.autograd.grad(y, x, torch.ones_like(y), create_graph=is_training,
+                                retain_graph=is_training)[0]
+    if not is_training:
+        return y.detach(), feat.detach(), g.detach()
+    return y, feat, g
+
+
+# ---- closed form: what the CUDA kernels compute ----
+
+
+def _sp(z, beta):
+    return torch.nn.functional.softplus(z, beta=beta)
+
+
+def _sp1(z, beta):  # sp'(z) = sigmoid(beta z), 1 beyond the threshold (beta*z > 20)
+    return torch.where(z * beta > 20.0, torch.ones_like(z), torch.sigmoid(beta * z))
+
+
+def _sp2(z, beta):  # sp''(z) = beta * s * (1 - s), 0 beyond the threshold
+    s = torch.sigmoid(beta * z)
+    return torch.where(z * beta > 20.0, torch.zeros_like(z), beta * s * (1.0 - s))
+
+
+def posenc_jt(xs: Tensor, pvec: Tensor, n_freqs: int) -> Tensor:
+    """J_e(x')^T p for the encoding e(x') (Appendix A 'Je^T p')."""
+    out = pvec[..., 0:3].clone()
+    for k in range(n_freqs):
+        f = 2.0 ** k
+        ps = pvec[..., 3 + 6 * k: 6 + 6 * k]
+        pc = pvec[..., 6 + 6 * k: 9 + 6 * k]
+        out = out + f * (torch.cos(xs * f) * ps - torch.sin(xs * f) * pc)
+    return out
+
+
+def posenc_j(xs: Tensor, nbar: Tensor, n_freqs: int) -> Tensor:
+    """J_e(x') nbar : 3-vector -> E-vector."""
+    out = [nbar]
+    for k in range(n_freqs):
+        f = 2.0 ** k
+        out.append(f * torch.cos(xs * f) * nbar)
+        out.append(-f * torch.sin(xs * f) * nbar)
+    return torch.cat(out, dim=-1)
+
+
+def sdf_get_all_closed_form(p: Params, x: Tensor, scale: float = 1.0, multires: int = 6,
+                            skip_in: Sequence[int] = (4,), beta: float = 100.0):
+    """Forward + analytic d sdf / d x without autograd.  Returns (y, feat, n, saved)."""
+    L = n_lin(p)
+    W = [wn_weight(p, l) for l in range(L)]
+    b = [p[f"lin{l}.bias"] for l in range(L)]
+    xs = x * scale
+    e = posenc(xs, multires)
+    E = e.shape[-1]
+    u, z = [], []
+    a = e
+    for l in range(L):
+        ul = torch.cat([a, e], dim=-1) / SQRT2 if l in skip_in else a
+        zl = ul @ W[l].t() + b[l]
+        u.append(ul)
+        z.append(zl)
+        a = _sp(zl, beta) if l < L - 1 else zl
+    y = z[-1][..., :1] / scale
+    feat = z[-1][..., 1:]
+    # reverse chain for q = d y / d (layer input)
+    q = (W[L - 1][0:1, :] / scale).expand(x.shape[0], -1)  # q_{L-1}: grad wrt u_{L-1}
+    pacc = torch.zeros(x.shape[0], E, dtype=x.dtype)
+    r: List[Optional[Tensor]] = [None] * L
+    qa: List[Optional[Tensor]] = [None] * L
+    for l in range(L - 2, -1, -1):
+        if (l + 1) in skip_in:
+            nh = u[l + 1].shape[-1] - E
+            qal = q[..., :nh] / SQRT2
+            pacc = pacc + q[..., nh:] / SQRT2
+        else:
+            qal = q
+        qa[l] = qal
+        r[l] = _sp1(z[l], beta) * qal
+        q = r[l] @ W[l]
+    pacc = pacc + q
+    n = scale * posenc_jt(xs, pacc, multires)
+    saved = dict(W=W, u=u, z=z, r=r, qa=qa, xs=xs, E=E)
+    return y, feat, n, saved
+
+
+def sdf_get_all_backward_closed_form(p: Params, saved, ybar: Tensor, fbar: Tensor, nbar: Tensor,
+                                     scale: float = 1.0, multires: int = 6,
+                                     skip_in: Sequence[int] = (4,), beta: float = 100.0) -> Params:
+    """Gradients of <ybar,y> + <fbar,feat> + <nbar,n> w.r.t. weight_g / weight_v / bias
+    (Appendix A parts A, B and the weight-norm chain)."""
+    L = n_lin(p)
+    W, u, z, r, qa, xs, E = (saved[k] for k in ("W", "u", "z", "r", "qa", "xs", "E"))
+    dW = [torch.zeros_like(w) for w in W]
+    db = [torch.zeros_like(p[f"lin{l}.bias"]) for l in range(L)]
+    # ---- part B: through n ----
+    pbar = scale * posenc_j(xs, nbar, multires)  # E-vector
+    qbar = pbar
+    zbarB: List[Optional[Tensor]] = [None] * L
+    for l in range(L - 1):
+        rbar = qbar @ W[l].t()
+        dW[l] += r[l].t() @ qbar
+        zbarB[l] = _sp2(z[l], beta) * qa[l] * rbar
+        qabar = _sp1(z[l], beta) * rbar
+        if (l + 1) in skip_in:
+            qbar = torch.cat([qabar / SQRT2, pbar / SQRT2], dim=-1)
+        else:
+            qbar = qabar
+    dW[L - 1][0, :] += qbar.sum(0) / scale
+    # ---- part A: ordinary backprop ----
+    delta = torch.cat([ybar / scale, fbar], dim=-1)
+    for l in range(L - 1, -1, -1):
+        dW[l] += delta.t() @ u[l]
+        db[l] += delta.sum(0)
+        if l == 0:
+            break
+        ubar = delta @ W[l]
+        if l in skip_in:
+            abar = ubar[..., : u[l].shape[-1] - E] / SQRT2
+        else:
+            abar = ubar
+        delta = _sp1(z[l - 1], beta) * abar + zbarB[l - 1]
+    # ---- weight norm ----
+    grads: Params = {}
+    for l in range(L):
+        v = p[f"lin{l}.weight_v"]
+        g = p[f"lin{l}.weight_g"]
+        nv = v.norm(dim=1, keepdim=True)
+        vh = v / nv
+        dg = (dW[l] * vh).sum(dim=1, keepdim=True)
+        grads[f"lin{l}.weight_g"] = dg
+        grads[f"lin{l}.weight_v"] = (g / nv) * (dW[l] - dg * vh)
+        grads[f"lin{l}.bias"] = db[l]
+    return grads
+
+
+# --------------------------------------------------------------------------
+# material MLPs                   models/fields.py:203-239, rendering_func.py:5-16
+# --------------------------------------------------------------------------
+
+
+def material_forward(p: Params, cfg: dict, points: Tensor, normals: Tensor,
+                     view_dirs: Optional[Tensor], feats: Tensor) -> Tensor:
+    """models/fields.py:203-239 (modes 'idr' and 'no_view_dir'; no skip)."""
+    pts = posenc(points, cfg["multires"]) if cfg["multires"] > 0 else points
+    if cfg["mode"] == "idr":
+        vd = posenc(view_dirs, cfg["multires_view"]) if cfg["multires_view"] > 0 else view_dirs
+        h = torch.cat([pts, vd, normals, feats], dim=-1)
+    elif cfg["mode"] == "no_view_dir":
+        h = torch.cat([pts, normals, feats], dim=-1)
+    else:
+        raise ValueError(cfg["mode"])
+    L = n_lin(p)
+    for l in range(L):
+        h = wn_linear(p, l, h)
+        if l < L - 1:
+            h = torch.relu(h)
+    h = cfg["output_scale"] * (h + cfg["output_bias"])
+    if cfg["squeeze_out"]:
+        h = torch.sigmoid(h)  # squeeze_out_scale = 1.0
+    return h
+
+
+def get_materials(nets: Dict[str, Params], points: Tensor, normals: Tensor, feats: Tensor,
+                  is_metal: bool = False) -> Dict[str, Tensor]:
+    """models/rendering_func.py:5-16."""
+    kd = material_forward(nets["diffuse_albedo_network"], MATERIAL_NETS["diffuse_albedo_network"],
+                          points, normals, -normals, feats).abs()
+    ks = material_forward(nets["specular_albedo_network"], MATERIAL_NETS["specular_albedo_network"],
+                          points, normals, None, feats).abs()
+    if not is_metal:
+        ks = torch.mean(ks, dim=-1, keepdim=True).expand_as(ks)
+    al = material_forward(nets["specular_roughness_network"], MATERIAL_NETS["specular_roughness_network"],
+                          points, normals, None, feats).abs() + 0.01
+    return {"diffuse_albedo": kd, "specular_albedo": ks, "specular_roughness": al}
+
+
+# --------------------------------------------------------------------------
+# GGX colocated shading                     models/renderer_ggx.py:12-16, 82-146
+# --------------------------------------------------------------------------
+
+_TABLES = None
+
+
+def ggx_tables() -> Tuple[Tensor, Tensor]:
+    """MTS_TRANS[5000], MTS_DIFF_TRANS[50] (models/renderer_ggx.py:65-74); the repo ships the
+    same numbers as iron_b200/data/ggx_tables.npz (float32)."""
+    global _TABLES
+    if _TABLES is None:
+        import os
+        f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "iron_b200", "data",
+                                 "ggx_tables.npz"))
+        _TABLES = (torch.from_numpy(f["ext_rtrans"].copy()), torch.from_numpy(f["int_diff_rtrans"].copy()))
+    return _TABLES
+
+
+def ggx_shade(light: Tensor, distance: Tensor, normal: Tensor, viewdir: Tensor,
+              kd: Tensor, ks: Tensor, alpha: Tensor) -> Dict[str, Tensor]:
+    """models/renderer_ggx.py:82-146.  Table lookups are floor-indexed (no gradient)."""
+    trans, diff_trans = ggx_tables()
+    L = light / (distance * distance + 1e-10)
+    c = torch.sum(viewdir * normal, dim=-1, keepdim=True)
+    c = torch.clamp(c, min=0.00001, max=0.99999)
+    eta = 1.48958738
+    inv_eta2 = 1.0 / (eta * eta)
+    alpha = torch.clamp(alpha, min=0.0001)
+    c2 = c * c
+    root = c2 + (1.0 - c2) / (alpha * alpha + 1e-10)
+    D = 1.0 / (np.pi * alpha * alpha * root * root + 1e-10)
+    F = 0.03867
+    # smithG1, :12-16
+    sin_t = torch.sqrt(1.0 - c * c)
+    tan_t = sin_t / (c + 1e-10)
+    rt = alpha * tan_t
+    G1 = 2.0 / (1.0 + torch.hypot(rt, torch.ones_like(rt)))
+    G = G1 ** 2
+    spec = L * ks * F * D * G / (4.0 * c + 1e-10)
+    wc = c ** 0.25
+    wa = ((alpha - 0) / (4 - 0)) ** 0.25
+    tx = torch.floor(wc * 100).long()
+    ty = torch.floor(wa * 50).long()
+    idx = torch.clamp(ty * 100 + tx, min=0, max=4999)
+    T12 = torch.clamp(trans[idx], min=0.0, max=1.0)
+    idy = torch.clamp(ty, min=0, max=49)
+    Fdr = torch.clamp(1.0 - diff_trans[idy], min=0.0, max=1.0)
+    diff = L * (kd / (1.0 - Fdr + 1e-10) / np.pi) * c * T12 * T12 * inv_eta2
+    return {"diffuse_rgb": diff, "specular_rgb": spec, "rgb": diff + spec}
+
+
+# --------------------------------------------------------------------------
+# camera + unit-sphere clip                 models/raytracer.py:223-237, 240-364
+# --------------------------------------------------------------------------
+
+FIXTURE_K = [811.9282694049824, 0.0, 256.0, 0.0, 0.0, 811.9282694049824, 256.0, 0.0,
+             0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 1.0]
+FIXTURE_W2C = [0.998867339183008, 0.0, -0.04758191582374219, 1.5416074755814572e-17,
+               -0.013163727354886733, -0.9609695958324571, -0.27634064516051604, 1.1553154537250536e-16,
+               -0.045724774418075535, 0.27665400030652737, -0.959881143224937, 2.0,
+               0.0, 0.0, 0.0, 1.0]
+
+
+class OCamera:
+    """Pinhole camera, models/raytracer.py:240-364 (rays, crop, resize only)."""
+
+    def __init__(self, W: int, H: int, K: Tensor, W2C: Tensor):
+        self.W, self.H, self.K, self.W2C = W, H, K, W2C
+        self.K_inv = torch.inverse(K)
+        self.C2W = torch.inverse(W2C)
+
+    @staticmethod
+    def fixture() -> "OCamera":
+        """tests/data_singleview/cam_dict_norm.json["12.png"] (512x512, f=811.93, distance 2)."""
+        K = torch.tensor(FIXTURE_K, dtype=torch.float64).reshape(4, 4).float()
+        W2C = torch.tensor(FIXTURE_W2C, dtype=torch.float64).reshape(4, 4).float()
+        return OCamera(512, 512, K, W2C)
+
+    def pixel_uv(self) -> Tensor:  # :300-303
+        u, v = np.meshgrid(np.arange(self.W), np.arange(self.H))
+        return torch.from_numpy(np.stack((u, v), axis=-1).astype(np.float32)) + 0.5
+
+    def rays(self, uv: Tensor):  # :254-286
+        sh = list(uv.shape[:-1])
+        uv1 = torch.cat((uv.reshape(-1, 2), torch.ones(uv.numel() // 2, 1)), dim=-1)
+        d = torch.matmul(torch.matmul(uv1, self.K_inv[:3, :3].t()), self.C2W[:3, :3].t()).reshape(sh + [3])
+        dn = d.norm(dim=-1)
+        d = d / dn.unsqueeze(-1)
+        o = self.C2W[:3, 3].unsqueeze(0).expand(uv1.shape[0], -1).reshape(sh + [3])
+        return o, d, dn
+
+    def crop(self, w: int, h: int, ul: Tuple[int, int]) -> "OCamera":  # :327-351 (explicit ul_corner)
+        K = self.K.clone()
+        K[0, 2] -= ul[0]
+        K[1, 2] -= ul[1]
+        return OCamera(w, h, K, self.W2C.clone())
+
+    def resize(self, factor: float) -> "OCamera":  # :353-358
+        h, w = int(self.H * factor), int(self.W * factor)
+        K = self.K.clone()
+        K[0, :3] *= w / self.W
+        K[1, :3] *= h / self.H
+        return OCamera(w, h, K, self.W2C.clone())
+
+
+def intersect_sphere(o: Tensor, d: Tensor, r: float = 1.0):
+    """models/raytracer.py:223-237."""
+    d1 = -torch.sum(d * o, dim=-1) / torch.sum(d * d, dim=-1)
+    pmid = o + d1.unsqueeze(-1) * d
+    tmp = r * r - torch.sum(pmid * pmid, dim=-1)
+    hit = tmp > 0.0
+    d2 = torch.sqrt(torch.clamp(tmp, min=0.0)) / torch.norm(d, dim=-1)
+    return hit, torch.clamp(d1 - d2, min=0.0), d1 + d2
+
+
+# --------------------------------------------------------------------------
+# tracer                                     models/raytracer.py:45-220
+# --------------------------------------------------------------------------
+
+
+class TraceStats:
+    def __init__(self):
+        self.evals_sphere = 0
+        self.evals_sampler = 0
+        self.evals_bisect = 0
+        self.k_max = 0
+        self.n_sampler_rays = 0
+        self.n_root_rays = 0
+
+    @property
+    def evals(self):
+        return self.evals_sphere + self.evals_sampler + self.evals_bisect
+
+
+def sphere_trace(sdf: Callable[[Tensor], Tensor], o, d, t_min, t_max, work, thr=5e-5, iters=16,
+                 stats: Optional[TraceStats] = None):
+    """models/raytracer.py:105-140."""
+    unf = work.clone()
+    t = t_min.clone()
+    x = o + d * t.unsqueeze(-1)
+    f = sdf(x)
+    if stats:
+        stats.evals_sphere += x.shape[0]
+    k = 0
+    while True:
+        unf = unf & (f.abs() > thr) & (t < t_max)
+        if k == iters or unf.sum() == 0:
+            break
+        k += 1
+        step = f[unf]
+        t[unf] += step
+        x[unf] += d[unf] * step.unsqueeze(-1)
+        f[unf] = sdf(x[unf])
+        if stats:
+            stats.evals_sphere += int(unf.sum())
+    conv = work & ~unf & (f.abs() <= thr) & (t < t_max)
+    return conv, unf, x, f, t
+
+
+def bisect(sdf, f_lo, f_hi, t_lo, t_hi, o, d, thr=5e-5, stats: Optional[TraceStats] = None):
+    """models/raytracer.py:199-220: every ray of the call is halved until no ray is working."""
+    work = (f_lo > 0) & (f_hi < 0)
+    t_mid = (t_lo + t_hi) / 2.0
+    k = 0
+    while work.any():
+        f_mid = sdf(o + d * t_mid.unsqueeze(-1))
+        if stats:
+            stats.evals_bisect += t_mid.shape[0]
+        pos = f_mid > 0
+        neg = f_mid <= 0
+        t_lo = torch.where(pos, t_mid, t_lo)
+        t_hi = torch.where(neg, t_mid, t_hi)
+        t_mid = (t_lo + t_hi) / 2.0
+        work = work & ((t_hi - t_lo) > 2 * thr)
+        k += 1
+    x = o + d * t_mid.unsqueeze(-1)
+    f = sdf(x)
+    if stats:
+        stats.evals_bisect += t_mid.shape[0]
+        stats.k_max = max(stats.k_max, k)
+    return x, t_mid, f
+
+
+def dense_sample(sdf, o, d, t_min, t_max, thr=5e-5, n_steps=128, max_num_pts=200000,
+                 stats: Optional[TraceStats] = None):
+    """models/raytracer.py:142-197."""
+    lin = torch.linspace(0, 1, steps=n_steps).float().view(1, n_steps)
+    ts = t_min.unsqueeze(-1) + lin * (t_max.unsqueeze(-1) - t_min.unsqueeze(-1))
+    pts = o.unsqueeze(-2) + d.unsqueeze(-2) * ts.unsqueeze(-1)
+    vals = torch.cat([sdf(c) for c in torch.split(pts.reshape(-1, 3), max_num_pts, dim=0)], dim=0)
+    vals = vals.reshape(-1, n_steps)
+    if stats:
+        stats.evals_sampler += vals.numel()
+        stats.n_sampler_rays += vals.shape[0]
+    out_x = torch.zeros_like(d)
+    out_f = torch.zeros_like(t_min)
+    out_t = torch.zeros_like(t_min)
+    score = torch.sign(vals) * torch.arange(n_steps, 0, -1).float().reshape(1, n_steps)
+    mval, midx = torch.min(score, dim=-1)
+    root = (mval < 0.0) & (midx >= 1)
+    if root.sum() > 0:
+        j = midx[root].unsqueeze(-1)
+        t_lo = torch.gather(ts[root], -1, j - 1).squeeze(-1)
+        f_lo = torch.gather(vals[root], -1, j - 1).squeeze(-1)
+        t_hi = torch.gather(ts[root], -1, j).squeeze(-1)
+        f_hi = torch.gather(vals[root], -1, j).squeeze(-1)
+        if stats:
+            stats.n_root_rays += int(root.sum())
+        px, pt, pf = bisect(sdf, f_lo, f_hi, t_lo, t_hi, o[root], d[root], thr, stats)
+        out_x[root] = px
+        out_f[root] = pf
+        out_t[root] = pt
+    return root, out_x, out_f, out_t
+
+
+@torch.no_grad()
+def trace_rays(sdf, o, d, t_min, t_max, work, thr=5e-5, iters=16, n_steps=128, max_num_pts=200000,
+               stats: Optional[TraceStats] = None) -> Dict[str, Tensor]:
+    """RayTracer.forward, models/raytracer.py:45-86."""
+    conv, unf, x, f, t = sphere_trace(sdf, o, d, t_min, t_max, work, thr, iters, stats)
+    if unf.sum() > 0:
+        outside = (f[unf] > 0.0).float()
+        s_min = outside * t[unf] + (1.0 - outside) * t_min[unf]
+        s_max = outside * t_max[unf] + (1.0 - outside) * t[unf]
+        s_conv, s_x, s_f, s_t = dense_sample(sdf, o[unf], d[unf], s_min, s_max, thr, n_steps, max_num_pts, stats)
+        conv[unf] = s_conv
+        x[unf] = s_x
+        f[unf] = s_f
+        t[unf] = s_t
+    return {"convergent_mask": conv, "points": x, "sdf": f, "distance": t}
+
+
+@torch.no_grad()
+def trace_pixels(p: Params, cam: OCamera, uv: Tensor, max_num_rays: int = 200000,
+                 stats: Optional[TraceStats] = None, **sdf_kw) -> Dict[str, Tensor]:
+    """raytrace_pixels, models/raytracer.py:367-409 (mask=None); one tracer call per ray chunk."""
+    sh = list(uv.shape[:-1])
+    o, d, dn = cam.rays(uv)
+    sdf = lambda x: sdf_forward(p, x, **sdf_kw)[..., 0]
+    parts: Dict[str, List[Tensor]] = {}
+    for oc, dc, dnc in zip(torch.split(o.reshape(-1, 3), max_num_rays), torch.split(d.reshape(-1, 3), max_num_rays),
+                           torch.split(dn.reshape(-1), max_num_rays)):
+        hit, t0, t1 = intersect_sphere(oc, dc, 1.0)
+        res = trace_rays(sdf, oc, dc, t0, t1, hit, stats=stats)
+        res["depth"] = res["distance"] / dnc
+        for k, v in res.items():
+            parts.setdefault(k, []).append(v)
+    out = {}
+    for k, v in parts.items():
+        v = torch.cat(v, dim=0).reshape(sh + [-1])
+        out[k] = v[..., 0] if v.shape[-1] == 1 else v
+    out.update({"uv": uv, "ray_o": o, "ray_d": d, "ray_d_norm": dn})
+    return out
+
+
+# --------------------------------------------------------------------------
+# shading of hit points            models/raytracer.py:17-24, 593-662; render_surface.py:117-156
+# --------------------------------------------------------------------------
+
+
+def reparam_points(x, grads, dirs, f):
+    """IDR implicit differentiation, models/raytracer.py:17-24."""
+    dot = torch.clamp((grads * dirs).sum(dim=-1, keepdim=True), min=1e-4)
+    return x - dirs / dot * (f - f.detach())
+
+
+def shade_hits(sdf_p: Params, nets: Dict[str, Params], light: Tensor, res: Dict[str, Tensor],
+               is_training: bool = True, max_num_pts: int = 320000, **sdf_kw) -> Dict[str, Tensor]:
+    """render_normal_and_color (models/raytracer.py:593-662) with the 'ggx' render_fn
+    (render_surface.py:117-156) inlined.  Returns dense image-shaped buffers."""
+    sh = list(res["convergent_mask"].shape)
+    outs: Dict[str, List[Tensor]] = {}
+    P = res["points"].reshape(-1, 3)
+    D = res["ray_d"].reshape(-1, 3)
+    O = res["ray_o"].reshape(-1, 3)
+    Mk = res["convergent_mask"].reshape(-1)
+    for pc, dc, oc, mk in zip(torch.split(P, max_num_pts), torch.split(D, max_num_pts),
+                              torch.split(O, max_num_pts), torch.split(Mk, max_num_pts)):
+        n = mk.shape[0]
+        buf = {k: torch.zeros(n, 3) for k in ("color", "diffuse_color", "specular_color", "diffuse_albedo",
+                                              "specular_albedo", "normal")}
+        buf["specular_roughness"] = torch.zeros(n)
+        if mk.any():
+            x, dd, oo = pc[mk], dc[mk], oc[mk]
+            f, feat, g = sdf_get_all(sdf_p, x, is_training=is_training, **sdf_kw)
+            if is_training:
+                x = reparam_points(x, g.detach(), -dd.detach(), f)
+            with torch.set_grad_enabled(is_training):
+                nrm = g / (g.norm(dim=-1, keepdim=True) + 1e-10)
+                mats = get_materials(nets, x, nrm, feat)
+                sh_out = ggx_shade(light, (x - oo).norm(dim=-1, keepdim=True), nrm, -dd,
+                                   mats["diffuse_albedo"], mats["specular_albedo"], mats["specular_roughness"])
+                buf["color"][mk] = sh_out["rgb"]
+                buf["diffuse_color"][mk] = sh_out["diffuse_rgb"]
+                buf["specular_color"][mk] = sh_out["specular_rgb"]
+                buf["diffuse_albedo"][mk] = mats["diffuse_albedo"]
+                buf["specular_albedo"][mk] = mats["specular_albedo"]
+                buf["specular_roughness"][mk] = mats["specular_roughness"].squeeze(-1)
+                buf["normal"][mk] = nrm
+        for k, v in buf.items():
+            outs.setdefault(k, []).append(v)
+    out = {}
+    for k, v in outs.items():
+        v = torch.cat(v, dim=0)
+        out[k] = v.reshape(sh + [3]) if v.dim() == 2 else v.reshape(sh)
+    return out
+
+
+# --------------------------------------------------------------------------
+# one stage-2 step (the unit bench.py counts)       render_surface.py:533-653, BASELINE.md section 3
+# --------------------------------------------------------------------------
+
+
+def stage2_step(sdf_p: Params, nets: Dict[str, Params], light: Tensor, cam: OCamera, target: Tensor,
+                eik_points: Tensor, eik_weight: float = 0.1, stats: Optional[TraceStats] = None,
+                max_num_rays: int = 50000, **sdf_kw):
+    """trace -> shade(is_training) -> L2 image loss + eik_weight * eikonal(random pts + hit normals)
+    -> backward.  fill_holes / edge sampling / SSIM / pyramid are outside the section-8 scope (rows f-1..f-4).
+
+    The `normal` buffer holds the *normalised* normal (render_surface.py:146), so the hit-normal eikonal
+    term is ~0 exactly as in the reference (render_surface.py:601-603).
+    Gradients are left in `.grad` of every tensor in sdf_p / nets / light that requires grad.
+    """
+    res = trace_pixels(sdf_p, cam, cam.pixel_uv(), max_num_rays=max_num_rays, stats=stats, **sdf_kw)
+    shaded = shade_hits(sdf_p, nets, light, res, is_training=True, **sdf_kw)
+    mask = res["convergent_mask"]
+    eg = sdf_gradient(sdf_p, eik_points, **sdf_kw).view(-1, 3)
+    eik_cnt = eg.shape[0]
+    eik = ((eg.norm(dim=-1) - 1) ** 2).sum()
+    img = torch.zeros(())
+    if mask.any():
+        img = ((shaded["color"] - target) ** 2).sum() / float(mask.numel())
+        hn = shaded["normal"][mask]
+        eik_cnt += hn.shape[0]
+        eik = eik + ((hn.norm(dim=-1) - 1) ** 2).sum()
+    loss = img + eik / eik_cnt * eik_weight
+    loss.backward()
+    res.update(shaded)
+    return loss.detach(), res

@@ -1,0 +1,200 @@
+"""Pins oracle/iron_oracle.py against vectors produced by the real reference modules
+(oracle/make_golden.py -> tests/golden/*.npz).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import iron_oracle as O
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a).copy())
+
+
+def close(a, b, atol, rtol=0.0):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    err = np.abs(a - b)
+    tol = atol + rtol * np.abs(b)
+    assert (err <= tol).all(), f"max err {err.max():.3e} (tol {atol:.1e}+{rtol:.1e}*|b|), worst at {np.argmax(err - tol)}"
+
+
+def sdf_params_from(g, prefix):
+    return {k[len(prefix):]: T(v) for k, v in g.items() if k.startswith(prefix)}
+
+
+def test_ggx_forward_backward(golden):
+    g = golden("ggx")
+    leaves = [T(g[k]).requires_grad_(True) for k in ("light", "dist", "normal", "kd", "ks", "alpha")]
+    out = O.ggx_shade(leaves[0], leaves[1], leaves[2], T(g["viewdir"]), leaves[3], leaves[4], leaves[5])
+    for k in ("diffuse_rgb", "specular_rgb", "rgb"):
+        close(out[k].detach().numpy(), g[k], 0.0, 1e-6)
+    w = T(g["wout"])
+    loss = (out["diffuse_rgb"] * w[0]).sum() + (out["specular_rgb"] * w[1]).sum() + (out["rgb"] * w[2]).sum()
+    gr = torch.autograd.grad(loss, leaves)
+    for got, k in zip(gr, ("g_light", "g_dist", "g_normal", "g_kd", "g_ks", "g_alpha")):
+        close(got.numpy(), g[k], 1e-6 * np.abs(g[k]).max(), 1e-5)
+
+
+def test_sdf_small_forward_getall(golden):
+    g = golden("sdf_small")
+    p = sdf_params_from(g, "w.")
+    x = T(g["x"])
+    close(O.sdf_forward(p, x).numpy(), g["fwd"], 1e-6, 1e-6)
+    y, f, n = O.sdf_get_all(p, x.clone(), is_training=False)
+    close(y.numpy(), g["y"], 1e-6)
+    close(f.numpy(), g["feat"], 1e-6, 1e-6)
+    close(n.numpy(), g["grad"], 1e-5, 1e-5)
+
+
+def test_sdf_small_double_backward_autograd(golden):
+    g = golden("sdf_small")
+    p = {k: v.requires_grad_(True) for k, v in sdf_params_from(g, "w.").items()}
+    y, f, n = O.sdf_get_all(p, T(g["x"]), is_training=True)
+    loss = (y * T(g["up_y"])).sum() + (f * T(g["up_feat"])).sum() + (n * T(g["up_grad"])).sum()
+    names = sorted(p)
+    gr = torch.autograd.grad(loss, [p[k] for k in names])
+    for k, got in zip(names, gr):
+        ref = g["g." + k]
+        close(got.numpy(), ref, 2e-5 * max(1.0, np.abs(ref).max()), 1e-4)
+
+
+def test_sdf_small_closed_form_matches_reference(golden):
+    """Appendix-A closed form (what the CUDA kernels implement) vs the reference's autograd, in fp64."""
+    g = golden("sdf_small")
+    p = {k: v.double() for k, v in sdf_params_from(g, "w.").items()}
+    x = T(g["x"]).double()
+    y, f, n, saved = O.sdf_get_all_closed_form(p, x)
+    close(y.numpy(), g["y"], 2e-6)
+    close(f.numpy(), g["feat"], 2e-6, 1e-6)
+    close(n.numpy(), g["grad"], 1e-5, 1e-5)
+    grads = O.sdf_get_all_backward_closed_form(p, saved, T(g["up_y"]).double(), T(g["up_feat"]).double(),
+                                               T(g["up_grad"]).double())
+    for k, got in grads.items():
+        ref = g["g." + k]
+        close(got.numpy(), ref, 3e-5 * max(1.0, np.abs(ref).max()), 2e-4)
+    # and against the oracle's own autograd in fp64: must agree to rounding
+    pa = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    ya, fa, na = O.sdf_get_all(pa, x.clone(), is_training=True)
+    loss = (ya * T(g["up_y"])).sum() + (fa * T(g["up_feat"])).sum() + (na * T(g["up_grad"])).sum()
+    names = sorted(pa)
+    for k, ga in zip(names, torch.autograd.grad(loss, [pa[k] for k in names])):
+        close(grads[k].numpy(), ga.numpy(), 1e-9 * max(1.0, ga.abs().max().item()), 1e-9)
+
+
+@pytest.mark.parametrize("H", [256, 512])
+def test_seeded_init_and_forward(golden, H):
+    g = golden("sdf_seeded")
+    torch.manual_seed(0)
+    p = O.make_sdf_params(d_hidden=H)
+    for k, v in p.items():
+        s = g[f"h{H}.sum.{k}"]
+        assert abs(v.double().sum().item() - s[0]) <= 1e-9 * max(1, abs(s[0])), k
+        assert abs(v.double().abs().sum().item() - s[1]) <= 1e-9 * max(1, abs(s[1])), k
+    x = T(g[f"h{H}.x"])
+    close(O.sdf_forward(p, x).numpy(), g[f"h{H}.fwd"], 2e-6, 1e-6)
+    _, _, n = O.sdf_get_all(p, x.clone(), is_training=False)
+    close(n.numpy(), g[f"h{H}.grad"], 5e-6, 1e-6)
+
+
+def test_materials(golden):
+    g = golden("materials")
+    torch.manual_seed(0)
+    nets = O.make_material_dict()
+    for nm, p in nets.items():
+        for k, v in p.items():
+            s = g[f"sum.{nm}.{k}"]
+            assert abs(v.double().sum().item() - s[0]) <= 1e-9 * max(1, abs(s[0])), (nm, k)
+            v.requires_grad_(True)
+    leaves = [T(g[k]).requires_grad_(True) for k in ("points", "normals", "feats")]
+    mats = O.get_materials(nets, *leaves)
+    for k in mats:
+        close(mats[k].detach().numpy(), g["out." + k], 1e-6, 1e-6)
+    loss = sum((mats[k] * T(g["up." + k])).sum() for k in mats)
+    plist = [(f"{nm}.{k}", v) for nm, p in nets.items() for k, v in p.items()]
+    gr = torch.autograd.grad(loss, leaves + [v for _, v in plist])
+    for got, k in zip(gr[:3], ("g_points", "g_normals", "g_feats")):
+        close(got.numpy(), g[k], 1e-6 * max(1.0, np.abs(g[k]).max()), 1e-5)
+    for (k, _), got in zip(plist, gr[3:]):
+        s = g["gsum." + k]
+        assert abs(got.double().pow(2).sum().sqrt().item() - s[2]) <= 1e-5 * max(1e-6, s[2]), k
+        if "g." + k in g:
+            close(got.numpy(), g["g." + k], 1e-6 * max(1.0, np.abs(g["g." + k]).max()), 1e-5)
+
+
+def _trace_net():
+    torch.manual_seed(0)
+    p = O.make_sdf_params(d_hidden=256)
+    gen = torch.Generator().manual_seed(1)
+    for l in range(1, 8):
+        v = p[f"lin{l}.weight_v"]
+        v.add_(torch.randn(v.shape, generator=gen) * 0.005)
+    return p
+
+
+def _cmp_trace(res, g, tag, depth=True):
+    m_ref = g[f"{tag}.convergent_mask"].astype(bool)
+    m = res["convergent_mask"].numpy().astype(bool)
+    assert (m == m_ref).all(), f"{tag}: {(m != m_ref).sum()} mask mismatches of {m.size}"
+    for k in ("points", "sdf", "distance") + (("depth",) if depth else ()):
+        a, b = res[k].numpy()[m], g[f"{tag}.{k}"][m_ref]
+        close(a, b, 2e-6)
+
+
+@pytest.mark.parametrize("tag", ["centre", "edge"])
+def test_trace_crops(golden, tag):
+    g = golden("trace_h256")
+    p = _trace_net()
+    ul = tuple(int(v) for v in g[f"{tag}.ul"])
+    cam = O.OCamera.fixture().crop(64, 64, ul)
+    o, d, dn = cam.rays(cam.pixel_uv())
+    close(d.numpy(), g[f"{tag}.ray_d"], 1e-7)
+    close(dn.numpy(), g[f"{tag}.ray_d_norm"], 1e-6)
+    close(o.numpy(), g[f"{tag}.ray_o"], 1e-7)
+    st = O.TraceStats()
+    res = O.trace_pixels(p, cam, cam.pixel_uv(), stats=st)
+    _cmp_trace(res, g, tag)
+    assert st.evals > 4096
+
+
+def test_trace_coarse_chunked_and_bundle(golden):
+    g = golden("trace_h256")
+    p = _trace_net()
+    cam = O.OCamera.fixture().resize(0.125)
+    res = O.trace_pixels(p, cam, cam.pixel_uv(), max_num_rays=1500)
+    _cmp_trace(res, g, "coarse")
+    o, d = T(g["bundle.ray_o"]), T(g["bundle.ray_d"])
+    hit, t0, t1 = O.intersect_sphere(o, d, 1.0)
+    assert (hit.numpy() == g["bundle.hit"]).all()
+    close(t0.numpy(), g["bundle.t0"], 1e-7)
+    close(t1.numpy(), g["bundle.t1"], 1e-7)
+    res = O.trace_rays(lambda q: O.sdf_forward(p, q)[..., 0], o, d, t0, t1, hit)
+    _cmp_trace(res, g, "bundle", depth=False)
+
+
+def test_full_step(golden):
+    g = golden("step_h256")
+    p = _trace_net()
+    torch.manual_seed(0)
+    nets = O.make_material_dict()
+    light = torch.tensor(32.0, requires_grad=True)
+    for d in [p] + list(nets.values()):
+        for v in d.values():
+            v.requires_grad_(True)
+    cam = O.OCamera.fixture().crop(32, 32, tuple(int(v) for v in g["ul"]))
+    loss, res = O.stage2_step(p, nets, light, cam, T(g["target"]), T(g["eik_points"]))
+    assert (res["convergent_mask"].numpy() == g["mask"]).all()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    for k in ("color", "diffuse_color", "specular_color", "diffuse_albedo", "specular_albedo", "specular_roughness",
+              "normal"):
+        close(res[k].detach().numpy(), g["res." + k], 2e-6, 1e-5)
+    allp = [("sdf." + k, v) for k, v in p.items()]
+    for nm, d in nets.items():
+        allp += [(f"{nm}.{k}", v) for k, v in d.items()]
+    allp.append(("point_light_network.light", light))
+    for k, v in allp:
+        s = g["gsum." + k]
+        nrm = v.grad.double().pow(2).sum().sqrt().item()
+        assert abs(nrm - s[2]) <= 1e-3 * max(s[2], 1e-12), (k, nrm, s[2])
+        if "g." + k in g:
+            ref = g["g." + k]
+            close(v.grad.numpy(), ref, 1e-4 * np.abs(ref).max(), 1e-3)
