@@ -1,0 +1,175 @@
+/*
+ * iron_b200 C ABI -- the drop-in boundary of the B200-native surface-rendering hot path.
+ *
+ * The reference (arthurlirui/IRON) has no FFI layer: its boundary is the Python module API
+ * (SURVEY.md section 8b).  These entry points are what a binding for that API calls; the Python
+ * modules in iron_b200/ (same class names / signatures as the reference) are the first such binding
+ * (ctypes).  Every function:
+ *   - takes raw DEVICE pointers (fp32 unless stated), element counts, and a CUDA stream handle
+ *     (cudaStream_t passed as void*; NULL = legacy default stream),
+ *   - allocates nothing: workspaces are sized by the *_workspace_bytes functions and passed in,
+ *   - keeps no global state besides the last error string,
+ *   - returns 0 on success, a negative IRONB_E* code for argument errors, or the positive
+ *     cudaError_t of a failed launch.  There is no CPU fallback anywhere.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   ironb_ggx_fwd / ironb_ggx_bwd        GGXColocatedRenderer.forward        models/renderer_ggx.py:82-146 (+ autograd)
+ *   ironb_mlp_fold / ironb_mlp_fold_bwd  nn.utils.weight_norm on every layer  models/fields.py:75-76, 194-195
+ *   ironb_sdf_getall_fwd / _bwd          SDFNetwork.forward/sdf/gradient/get_all  models/fields.py:82-137
+ *                                        (+ the double backward autograd runs through them)
+ *   ironb_matnet_fwd / _bwd              RenderingNetwork.forward             models/fields.py:203-239 (+ autograd)
+ *   ironb_camera_rays                    Camera.get_rays + intersect_sphere   models/raytracer.py:254-286, 223-237
+ *   ironb_trace                          RayTracer.forward (sphere_tracing, ray_sampler, rootfind)
+ *                                                                             models/raytracer.py:45-220
+ *   ironb_shade_prep / _bwd              reparam_points + normal/distance glue of render_fn
+ *                                                                             models/raytracer.py:17-24, render_surface.py:127-133
+ */
+#ifndef IRON_B200_H
+#define IRON_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IRONB_MAX_LIN 12
+
+#define IRONB_OK 0
+#define IRONB_EINVAL (-1)   /* bad argument (null pointer, negative size, unsupported shape) */
+#define IRONB_ENOSUP (-2)   /* configuration outside what the kernels were built for */
+
+/* Geometry of one weight-normalised MLP and where its folded weights live inside one packed fp32
+ * device buffer.  Built by ironb_sdf_layout / ironb_matnet_layout, then treated as read-only. */
+typedef struct ironb_mlp_layout {
+  int32_t n_lin;                   /* number of linear layers: 9 for the SDF net, 5 for a material net */
+  int32_t kind;                    /* 0 = SDF net (softplus, PE input, skip), 1 = material net (ReLU) */
+  int32_t d_in;                    /* raw coordinate dim (3) */
+  int32_t multires;                /* PE frequencies of the SDF input (6); 0 = none */
+  int32_t pe_dim;                  /* E = d_in*(1+2*multires) (39) */
+  int32_t skip_layer;              /* layer whose input is cat(h, PE)/sqrt(2); -1 = none   fields.py:88-89 */
+  int32_t d_hidden;
+  int32_t d_out;                   /* 257 for the SDF net */
+  float scale;                     /* SDFNetwork.scale   fields.py:83,98 */
+  float beta;                      /* Softplus beta (100)  fields.py:80 */
+  int32_t in_dim[IRONB_MAX_LIN];   /* true fan-in  K_l */
+  int32_t out_dim[IRONB_MAX_LIN];  /* true fan-out N_l (H-E for the layer before the skip) */
+  int32_t in_pad[IRONB_MAX_LIN];   /* K_l rounded up to 8 (zero filled) */
+  int32_t out_pad[IRONB_MAX_LIN];  /* for l < n_lin-1: in_pad[l+1]; last layer: N rounded up to 8 */
+  int64_t off_w[IRONB_MAX_LIN];    /* W_l  [out_pad][in_pad] row-major, float offset into the packed buffer */
+  int64_t off_wt[IRONB_MAX_LIN];   /* W_l^T [in_pad][out_pad] */
+  int64_t off_b[IRONB_MAX_LIN];    /* b_l  [out_pad] */
+  int64_t packed_floats;           /* total size of the packed buffer, in floats */
+} ironb_mlp_layout;
+
+const char* ironb_last_error(void);
+int ironb_version(void);
+
+/* ---------------------------------------------------------------- layouts (host only) */
+int ironb_sdf_layout(int d_in, int d_out, int d_hidden, int n_layers, int skip_layer, int multires,
+                     float scale, float beta, ironb_mlp_layout* out);
+int ironb_matnet_layout(int in_dim0, int d_out, int d_hidden, int n_layers, ironb_mlp_layout* out);
+
+/* ---------------------------------------------------------------- weight norm
+ * W = v * (g / ||v||_row)  (old-style nn.utils.weight_norm, dim=0).  v/g/b: arrays of n_lin device
+ * pointers (v[l]: [out,in] row-major, g[l]: [out] or NULL = no weight norm, b[l]: [out]). */
+int ironb_mlp_fold(const ironb_mlp_layout* lay, const float* const* v, const float* const* g,
+                   const float* const* b, float* packed, void* stream);
+/* dpacked has the layout of `packed` and holds dL/dW at off_w and dL/db at off_b.
+ * Writes dv[l] ([out,in]), dg[l] ([out], may be NULL when g[l] is NULL), db[l] ([out]). */
+int ironb_mlp_fold_bwd(const ironb_mlp_layout* lay, const float* const* v, const float* const* g,
+                       const float* dpacked, float* const* dv, float* const* dg, float* const* db,
+                       void* stream);
+
+/* ---------------------------------------------------------------- SDF network
+ * Forward over M points x[M,3].  Outputs (any may be NULL): y[M] (sdf), feat[M,d_out-1], grad[M,3]
+ * (= d y / d x, closed form of autograd.grad in SDFNetwork.gradient/get_all).
+ * save != 0 keeps per-layer state in `ws` for ironb_sdf_getall_bwd. */
+int64_t ironb_sdf_getall_workspace_bytes(const ironb_mlp_layout* lay, int64_t M, int want_grad, int save);
+int ironb_sdf_getall_fwd(const ironb_mlp_layout* lay, const float* packed, const float* x, int64_t M,
+                         float* y, float* feat, float* grad, int save, void* ws, int64_t ws_bytes,
+                         void* stream);
+/* Gradients of <ybar,y> + <fbar,feat> + <nbar,grad> (each upstream may be NULL) w.r.t. the folded
+ * weights/biases, ACCUMULATED into dpacked (caller zeroes it).  This is the double backward of
+ * fields.py:106-137 in closed form. `ws` is the saved forward workspace and
+ * is clobbered. */
+int ironb_sdf_getall_bwd(const ironb_mlp_layout* lay, const float* packed, const float* x, int64_t M,
+                         const float* ybar, const float* fbar, const float* nbar, void* ws,
+                         int64_t ws_bytes, float* dpacked, void* stream);
+
+/* ---------------------------------------------------------------- material networks (RenderingNetwork)
+ * mode 0 = 'idr'         input = cat(PE_p(points), PE_v(view_dirs), normals, feats)
+ * mode 1 = 'no_view_dir' input = cat(PE_p(points), normals, feats)
+ * mode 2 = 'no_normal'   input = cat(PE_p(points), PE_v(view_dirs), feats)
+ * mode 3 = 'points_only' input = cat(PE_p(points), feats)                       fields.py:209-222
+ * out = out_scale * (lin_last(..) + out_bias); squeeze != 0 applies squeeze_scale*sigmoid   fields.py:232-238 */
+typedef struct ironb_matnet_cfg {
+  int32_t mode;
+  int32_t multires;        /* PE of points, 0 = raw */
+  int32_t multires_view;   /* PE of view dirs, 0 = raw */
+  int32_t d_feature;
+  int32_t squeeze;
+  float out_bias, out_scale, squeeze_scale;
+} ironb_matnet_cfg;
+
+int ironb_matnet_in_dim(const ironb_matnet_cfg* cfg);
+int64_t ironb_matnet_workspace_bytes(const ironb_mlp_layout* lay, int64_t M);
+int ironb_matnet_fwd(const ironb_mlp_layout* lay, const ironb_matnet_cfg* cfg, const float* packed,
+                     const float* points, const float* normals, const float* view_dirs,
+                     const float* feats, int64_t M, float* out, void* ws, int64_t ws_bytes, void* stream);
+/* d_points/d_normals/d_view/d_feats may be NULL; written (not accumulated). dpacked accumulated. */
+int ironb_matnet_bwd(const ironb_mlp_layout* lay, const ironb_matnet_cfg* cfg, const float* packed,
+                     int64_t M, const float* out, const float* gout, void* ws, int64_t ws_bytes,
+                     float* dpacked, float* d_points, float* d_normals, float* d_view, float* d_feats,
+                     void* stream);
+
+/* ---------------------------------------------------------------- GGX colocated shading
+ * light: device scalar.  dist[M], normal[M,3], viewdir[M,3], kd[M,3], ks[M,3], alpha[M].
+ * trans[5000], diff_trans[50]: the Mitsuba rough-plastic tables (renderer_ggx.py:65-74). */
+int ironb_ggx_fwd(const float* light, const float* dist, const float* normal, const float* viewdir,
+                  const float* kd, const float* ks, const float* alpha, const float* trans,
+                  const float* diff_trans, int64_t M, float* diffuse_rgb, float* specular_rgb,
+                  float* rgb, void* stream);
+/* Upstream grads g_diffuse/g_specular/g_rgb [M,3] may each be NULL.  d_light is ACCUMULATED
+ * (atomicAdd; caller zeroes), the others are written.  d_viewdir may be NULL. */
+int ironb_ggx_bwd(const float* light, const float* dist, const float* normal, const float* viewdir,
+                  const float* kd, const float* ks, const float* alpha, const float* trans,
+                  const float* diff_trans, int64_t M, const float* g_diffuse, const float* g_specular,
+                  const float* g_rgb, float* d_light, float* d_dist, float* d_normal, float* d_viewdir,
+                  float* d_kd, float* d_ks, float* d_alpha, void* stream);
+
+/* ---------------------------------------------------------------- camera rays + unit-sphere clip
+ * uv[N,2] pixel coordinates; Kinv3[9], R_c2w[9] row-major 3x3 blocks of K^-1 and C2W; origin[3].
+ * All on the device.  Outputs ray_o[N,3], ray_d[N,3], ray_d_norm[N]; if min_dis != NULL also the
+ * sphere clip (hit[N] u8, min_dis[N], max_dis[N]) for radius r. */
+int ironb_camera_rays(const float* uv, int64_t N, const float* Kinv3, const float* R_c2w,
+                      const float* origin, float r, float* ray_o, float* ray_d, float* ray_d_norm,
+                      uint8_t* hit, float* min_dis, float* max_dis, void* stream);
+int ironb_intersect_sphere(const float* ray_o, const float* ray_d, int64_t N, float r, uint8_t* hit,
+                           float* min_dis, float* max_dis, void* stream);
+
+/* ---------------------------------------------------------------- tracer
+ * One call == one RayTracer.forward (the bisection count is coupled across the rays of a call,
+ * raytracer.py:204-214).  linspace: the n_steps sample positions (torch.linspace(0,1,n_steps)).
+ * Outputs: conv[N] u8, points[N,3], sdf[N], dist[N].  stats (device, int64[8], may be NULL):
+ * [0] evals sphere tracing, [1] evals sampler, [2] evals bisection, [3] sampler rays, [4] root rays,
+ * [5] k_max, [6] tile evaluations. */
+int64_t ironb_trace_workspace_bytes(const ironb_mlp_layout* lay, int64_t N);
+int ironb_trace(const ironb_mlp_layout* lay, const float* packed, const float* ray_o,
+                const float* ray_d, const float* min_dis, const float* max_dis,
+                const uint8_t* work_mask, int64_t N, float sdf_threshold, int sphere_tracing_iters,
+                int n_steps, const float* linspace, uint8_t* conv, float* points, float* sdf,
+                float* dist, int64_t* stats, void* ws, int64_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- hit-point glue (fused elementwise)
+ * Stable compaction of the hit mask: idx[0..count) = ascending ray ids with mask != 0. count: device int32. */
+int ironb_compact_mask(const uint8_t* mask, int64_t N, int32_t* idx, int32_t* count, void* stream);
+/* Gather rows: dst[i,:] = src[idx[i],:]  (width floats per row). */
+int ironb_gather_rows(const float* src, const int32_t* idx, int64_t M, int width, float* dst, void* stream);
+/* Scatter rows into a zero-initialised dense buffer: dst[idx[i],:] = src[i,:]. */
+int ironb_scatter_rows(const float* src, const int32_t* idx, int64_t M, int width, float* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRON_B200_H */

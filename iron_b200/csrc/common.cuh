@@ -1,0 +1,61 @@
+// Shared helpers for the iron_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/iron_b200.h"
+
+namespace ironb {
+
+void set_error(const char* fmt, ...);
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define IRONB_REQUIRE(cond, ...)            \
+  do {                                      \
+    if (!(cond)) {                          \
+      ::ironb::set_error(__VA_ARGS__);      \
+      return IRONB_EINVAL;                  \
+    }                                       \
+  } while (0)
+
+#define IRONB_CHECK_LAUNCH(what)                                               \
+  do {                                                                         \
+    cudaError_t e__ = cudaGetLastError();                                      \
+    if (e__ != cudaSuccess) {                                                  \
+      ::ironb::set_error("%s: %s", what, cudaGetErrorString(e__));             \
+      return (int)e__;                                                         \
+    }                                                                          \
+  } while (0)
+
+#define IRONB_CUDA(call)                                                       \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      ::ironb::set_error("%s: %s", #call, cudaGetErrorString(e__));            \
+      return (int)e__;                                                         \
+    }                                                                          \
+  } while (0)
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+int num_sms();
+
+// ---- the two scalar activations of the SDF net, written exactly as torch evaluates them ----
+// nn.Softplus(beta): x*beta > 20 ? x : log1p(exp(x*beta))/beta        (models/fields.py:80)
+__device__ __forceinline__ float softplus_beta(float z, float beta) {
+  float bz = z * beta;
+  return bz > 20.f ? z : __fdiv_rn(log1pf(expf(bz)), beta);
+}
+// d/dz softplus = sigmoid(beta z); 1 beyond the threshold (autograd of the thresholded branch)
+__device__ __forceinline__ float softplus_d1(float z, float beta) {
+  float bz = z * beta;
+  return bz > 20.f ? 1.f : __fdiv_rn(1.f, 1.f + expf(-bz));
+}
+
+#define IRONB_SQRT2F 1.41421356237309515f  // float(np.sqrt(2)); the reference DIVIDES by it (fields.py:89)
+
+}  // namespace ironb

@@ -1,0 +1,453 @@
+// SDFNetwork forward, analytic input gradient, and the double backward, layer at a time.
+//
+// Restates models/fields.py:82-137 (+ models/embedder.py:11-36) as explicit linear algebra (SURVEY.md
+// appendix A):   a_0 = e(x*s);  u_l = a_l  (or cat(a_l, e)/sqrt2 at the skip layer);  z_l = W_l u_l + b_l;
+// a_{l+1} = softplus_beta(z_l);  y = z_last[0]/s, feature = z_last[1:].
+//   grad = dy/dx:  q_last = W_last[0,:]/s;  r_l = sp'(z_l) * qa_{l+1};  q_l = W_l^T r_l;  n = s * Je^T p.
+//   backward of (y, feature, grad) w.r.t. W, b: part B (through grad, ascending l) then part A (ordinary
+//   back-propagation, descending l), with  zbarB_l = sp''(z_l) qa_{l+1} rbar_l = beta (1 - sp'(z_l)) r_l rbar_l.
+// Every product is one fp32 tile GEMM (gemm.cuh) with the elementwise work fused into its epilogue.
+#include "gemm.cuh"
+
+namespace ironb {
+namespace {
+
+// ------------------------------------------------------------------ positional encoding
+// e = [x', sin(2^0 x'), cos(2^0 x'), ..., sin(2^(L-1) x'), cos(2^(L-1) x')], x' = x*scale; pad columns = 0.
+__global__ void __launch_bounds__(256) pe_kernel(const float* __restrict__ x, int64_t M, int multires, float scale,
+                                                 int Epad, float* __restrict__ e) {
+  int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float xs[3] = {x[m * 3] * scale, x[m * 3 + 1] * scale, x[m * 3 + 2] * scale};
+  float* o = e + m * Epad;
+  o[0] = xs[0]; o[1] = xs[1]; o[2] = xs[2];
+  int w = 3;
+  float f = 1.f;
+  for (int k = 0; k < multires; ++k) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s, co;
+      sincosf(xs[c] * f, &s, &co);     // accurate path: arguments reach 32 rad
+      o[w + c] = s;
+      o[w + 3 + c] = co;
+    }
+    w += 6;
+    f *= 2.f;
+  }
+  for (; w < Epad; ++w) o[w] = 0.f;
+}
+
+// ------------------------------------------------------------------ epilogues
+struct EpiFwdHidden {
+  const float* bias;   // [Npad]
+  float* Z;            // [M][ld] or null
+  float* Unext;        // [M][ld]
+  float* R;            // [M][ld] or null: r = sp'(z) * qrow[n]  (only for the layer before the last)
+  const float* qrow;   // W_last[0,:] (divided by scale via qscale)
+  const float* e;      // PE buffer (pre-skip layer only)
+  int ld, n_true, pre_skip, Epad, E;
+  float beta, qscale;
+  __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[4]) const {
+    float zz[4], uu[4], rr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + j;
+      if (n < n_true) {
+        float z = acc[j] + __ldg(bias + n);
+        float a = softplus_beta(z, beta);
+        if (pre_skip) a = __fdiv_rn(a, IRONB_SQRT2F);
+        zz[j] = z; uu[j] = a;
+        rr[j] = R ? softplus_d1(z, beta) * (__ldg(qrow + n) * qscale) : 0.f;
+      } else {
+        zz[j] = 0.f; rr[j] = 0.f;
+        int c = n - n_true;
+        uu[j] = (pre_skip && c < E) ? __fdiv_rn(__ldg(e + (int64_t)m * Epad + c), IRONB_SQRT2F) : 0.f;
+      }
+    }
+    int64_t o = (int64_t)m * ld + n0;
+    if (Z) *reinterpret_cast<float4*>(Z + o) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+    *reinterpret_cast<float4*>(Unext + o) = make_float4(uu[0], uu[1], uu[2], uu[3]);
+    if (R) *reinterpret_cast<float4*>(R + o) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+  }
+};
+
+struct EpiFwdLast {
+  const float* bias;
+  float* y;      // [M] or null
+  float* feat;   // [M][d_out-1] or null
+  int d_out;
+  float inv_scale;
+  __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[4]) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + j;
+      if (n >= d_out) continue;
+      float z = acc[j] + __ldg(bias + n);
+      if (n == 0) { if (y) y[m] = z * inv_scale; }
+      else if (feat) feat[(int64_t)m * (d_out - 1) + (n - 1)] = z;
+    }
+  }
+};
+
+// reverse chain: acc = q_l[m][k] (gradient of y w.r.t. u_l).  For l >= 1 it becomes r_{l-1}; for l == 0 it
+// is added into the PE-gradient accumulator P.
+struct EpiQ {
+  const float* Zprev;  // Z_{l-1} [M][ld]       (l >= 1)
+  float* Rprev;        // R_{l-1} [M][ld]       (l >= 1)
+  float* P;            // [M][Epad]
+  int ld, n_true_prev, is_skip, is_first, Epad, E;
+  float beta;
+  __device__ __forceinline__ void operator()(int m, int k0, const float (&acc)[4]) const {
+    if (is_first) {
+      float4* p = reinterpret_cast<float4*>(P + (int64_t)m * Epad + k0);
+      float4 v = *p;
+      v.x += acc[0]; v.y += acc[1]; v.z += acc[2]; v.w += acc[3];
+      *p = v;
+      return;
+    }
+    float rr[4];
+    int64_t o = (int64_t)m * ld + k0;
+    float4 z4 = *reinterpret_cast<const float4*>(Zprev + o);
+    const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int k = k0 + j;
+      if (k < n_true_prev) {
+        float qa = is_skip ? __fdiv_rn(acc[j], IRONB_SQRT2F) : acc[j];
+        rr[j] = softplus_d1(zz[j], beta) * qa;
+      } else {
+        rr[j] = 0.f;
+        int c = k - n_true_prev;
+        if (is_skip && c < E) P[(int64_t)m * Epad + c] = __fdiv_rn(acc[j], IRONB_SQRT2F);
+      }
+    }
+    *reinterpret_cast<float4*>(Rprev + o) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+  }
+};
+
+// part B: acc = rbar_l[m][n].  Overwrites R_l with zbarB_l and emits qbar_{l+1}.
+struct EpiB {
+  const float* Z;    // Z_l
+  float* R;          // in: r_l, out: zbarB_l
+  float* QBnext;     // [M][ld]
+  const float* PB;   // pbar [M][Epad]
+  int ld, n_true, pre_skip, Epad, E;
+  float beta;
+  __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[4]) const {
+    int64_t o = (int64_t)m * ld + n0;
+    float4 z4 = *reinterpret_cast<const float4*>(Z + o);
+    float4 r4 = *reinterpret_cast<const float4*>(R + o);
+    const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+    const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+    float zb[4], qb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + j;
+      if (n < n_true) {
+        float s1 = softplus_d1(zz[j], beta);
+        bool lin = zz[j] * beta > 20.f;
+        zb[j] = lin ? 0.f : beta * (1.f - s1) * rr[j] * acc[j];
+        float qa = s1 * acc[j];
+        qb[j] = pre_skip ? __fdiv_rn(qa, IRONB_SQRT2F) : qa;
+      } else {
+        zb[j] = 0.f;
+        int c = n - n_true;
+        qb[j] = (pre_skip && c < E) ? __fdiv_rn(__ldg(PB + (int64_t)m * Epad + c), IRONB_SQRT2F) : 0.f;
+      }
+    }
+    *reinterpret_cast<float4*>(R + o) = make_float4(zb[0], zb[1], zb[2], zb[3]);
+    *reinterpret_cast<float4*>(QBnext + o) = make_float4(qb[0], qb[1], qb[2], qb[3]);
+  }
+};
+
+// part A: acc = ubar_l[m][k];  delta_{l-1} = sp'(z_{l-1}) * abar + zbarB_{l-1}
+struct EpiA {
+  const float* Zprev;
+  const float* ZBprev;  // or null
+  float* Dprev;         // [M][ld]
+  int ld, n_true_prev, is_skip;
+  float beta;
+  __device__ __forceinline__ void operator()(int m, int k0, const float (&acc)[4]) const {
+    int64_t o = (int64_t)m * ld + k0;
+    float4 z4 = *reinterpret_cast<const float4*>(Zprev + o);
+    const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+    float zb[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ZBprev) {
+      float4 b4 = *reinterpret_cast<const float4*>(ZBprev + o);
+      zb[0] = b4.x; zb[1] = b4.y; zb[2] = b4.z; zb[3] = b4.w;
+    }
+    float dd[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int k = k0 + j;
+      if (k < n_true_prev) {
+        float ab = is_skip ? __fdiv_rn(acc[j], IRONB_SQRT2F) : acc[j];
+        dd[j] = softplus_d1(zz[j], beta) * ab + zb[j];
+      } else {
+        dd[j] = 0.f;
+      }
+    }
+    *reinterpret_cast<float4*>(Dprev + o) = make_float4(dd[0], dd[1], dd[2], dd[3]);
+  }
+};
+
+// n = s * Je^T p    (Je^T p = p[0:3] + sum_k 2^k (cos_k * p_sin,k - sin_k * p_cos,k))
+__global__ void __launch_bounds__(256) normal_kernel(const float* __restrict__ e, const float* __restrict__ P,
+                                                     int64_t M, int multires, int Epad, float scale,
+                                                     float* __restrict__ grad) {
+  int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float* em = e + m * Epad;
+  const float* pm = P + m * Epad;
+  float out[3] = {pm[0], pm[1], pm[2]};
+  float f = 1.f;
+  int w = 3;
+  for (int k = 0; k < multires; ++k) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[c] += f * (em[w + 3 + c] * pm[w + c] - em[w + c] * pm[w + 3 + c]);
+    w += 6;
+    f *= 2.f;
+  }
+  grad[m * 3] = out[0] * scale; grad[m * 3 + 1] = out[1] * scale; grad[m * 3 + 2] = out[2] * scale;
+}
+
+// pbar = s * Je nbar  -> written into the P buffer (which doubles as qbar_0)
+__global__ void __launch_bounds__(256) pbar_kernel(const float* __restrict__ e, const float* __restrict__ nbar,
+                                                   int64_t M, int multires, int Epad, float scale,
+                                                   float* __restrict__ P) {
+  int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float* em = e + m * Epad;
+  float* pm = P + m * Epad;
+  float nb[3] = {nbar[m * 3] * scale, nbar[m * 3 + 1] * scale, nbar[m * 3 + 2] * scale};
+  pm[0] = nb[0]; pm[1] = nb[1]; pm[2] = nb[2];
+  float f = 1.f;
+  int w = 3;
+  for (int k = 0; k < multires; ++k) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      pm[w + c] = f * em[w + 3 + c] * nb[c];
+      pm[w + 3 + c] = -f * em[w + c] * nb[c];
+    }
+    w += 6;
+    f *= 2.f;
+  }
+  for (; w < Epad; ++w) pm[w] = 0.f;
+}
+
+// delta_last = [ybar/s, fbar, 0...]
+__global__ void __launch_bounds__(256) dlast_kernel(const float* __restrict__ ybar, const float* __restrict__ fbar,
+                                                    int64_t M, int d_out, int ld, float inv_scale,
+                                                    float* __restrict__ D) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M * ld) return;
+  int64_t m = i / ld;
+  int n = (int)(i - m * ld);
+  float v = 0.f;
+  if (n == 0) v = ybar ? ybar[m] * inv_scale : 0.f;
+  else if (n < d_out) v = fbar ? fbar[m * (d_out - 1) + n - 1] : 0.f;
+  D[i] = v;
+}
+
+struct SdfWs {
+  float* e; float* P;
+  float* U[IRONB_MAX_LIN];   // U[0] == e
+  float* Z[IRONB_MAX_LIN];
+  float* R[IRONB_MAX_LIN];
+  float* QB[2]; float* D[2];
+  int64_t floats;
+};
+
+int max_pad(const ironb_mlp_layout* L) {
+  int mx = 0;
+  for (int l = 0; l < L->n_lin; ++l) { mx = max(mx, L->in_pad[l]); mx = max(mx, L->out_pad[l]); }
+  return mx;
+}
+
+// Carve the workspace.  full == false: only the PE buffer and two ping-pong activation buffers.
+SdfWs carve(const ironb_mlp_layout* L, int64_t M, bool full, float* base) {
+  SdfWs w;
+  memset(&w, 0, sizeof(w));
+  int64_t off = 0;
+  auto take = [&](int64_t cols) { float* p = base ? base + off : nullptr; off += (M * cols + 63) / 64 * 64; return p; };
+  const int last = L->n_lin - 1;
+  const int mp = max_pad(L);
+  w.e = take(L->in_pad[0]);
+  w.U[0] = w.e;
+  if (!full) {
+    float* a = take(mp); float* b = take(mp);
+    for (int l = 1; l <= last; ++l) w.U[l] = (l & 1) ? a : b;
+  } else {
+    w.P = take(L->in_pad[0]);
+    for (int l = 1; l <= last; ++l) w.U[l] = take(L->in_pad[l]);
+    for (int l = 0; l < last; ++l) w.Z[l] = take(L->out_pad[l]);
+    for (int l = 0; l < last; ++l) w.R[l] = take(L->out_pad[l]);
+    w.QB[0] = take(mp); w.QB[1] = take(mp);
+    w.D[0] = take(mp); w.D[1] = take(mp);
+  }
+  w.floats = off;
+  return w;
+}
+
+}  // namespace
+}  // namespace ironb
+
+using namespace ironb;
+
+extern "C" int64_t ironb_sdf_getall_workspace_bytes(const ironb_mlp_layout* lay, int64_t M, int want_grad, int save) {
+  if (!lay || M < 0) return -1;
+  SdfWs w = carve(lay, M, want_grad || save, nullptr);
+  return w.floats * (int64_t)sizeof(float);
+}
+
+extern "C" int ironb_sdf_getall_fwd(const ironb_mlp_layout* lay, const float* packed, const float* x, int64_t M,
+                                    float* y, float* feat, float* grad, int save, void* ws, int64_t ws_bytes,
+                                    void* stream) {
+  IRONB_REQUIRE(lay && lay->kind == 0, "sdf_getall_fwd: layout is not an SDF layout");
+  IRONB_REQUIRE(M >= 0 && M < (1ll << 31), "sdf_getall_fwd: M out of range");
+  if (M == 0) return IRONB_OK;
+  IRONB_REQUIRE(packed && x && ws, "sdf_getall_fwd: null pointer");
+  const bool full = (grad != nullptr) || save;
+  SdfWs w = carve(lay, M, full, reinterpret_cast<float*>(ws));
+  IRONB_REQUIRE(ws_bytes >= w.floats * (int64_t)sizeof(float), "sdf_getall_fwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int last = lay->n_lin - 1;
+  const int Epad = lay->in_pad[0], E = lay->pe_dim;
+  const int mblocks = (int)ceil_div64(M, 256);
+
+  pe_kernel<<<mblocks, 256, 0, st>>>(x, M, lay->multires, lay->scale, Epad, w.e);
+  IRONB_CHECK_LAUNCH("pe_kernel");
+
+  for (int l = 0; l < last; ++l) {
+    EpiFwdHidden ep;
+    ep.bias = packed + lay->off_b[l];
+    ep.Z = full ? w.Z[l] : nullptr;
+    ep.Unext = w.U[l + 1];
+    ep.R = (grad != nullptr && l == last - 1) ? w.R[l] : nullptr;
+    ep.qrow = packed + lay->off_w[last];     // row 0 of W_last
+    ep.e = w.e;
+    ep.ld = lay->out_pad[l];
+    ep.n_true = lay->out_dim[l];
+    ep.pre_skip = (l + 1 == lay->skip_layer);
+    ep.Epad = Epad; ep.E = E;
+    ep.beta = lay->beta;
+    ep.qscale = 1.f / lay->scale;
+    int rc = launch_gemm_nt(w.U[l], lay->in_pad[l], packed + lay->off_w[l], lay->in_pad[l], (int)M,
+                            lay->out_pad[l], lay->in_pad[l], ep, st, "sdf fwd hidden gemm");
+    if (rc) return rc;
+  }
+  if (y != nullptr || feat != nullptr) {
+    EpiFwdLast ep{packed + lay->off_b[last], y, feat, lay->d_out, 1.f / lay->scale};
+    int rc = launch_gemm_nt(w.U[last], lay->in_pad[last], packed + lay->off_w[last], lay->in_pad[last], (int)M,
+                            lay->out_pad[last], lay->in_pad[last], ep, st, "sdf fwd last gemm");
+    if (rc) return rc;
+  }
+  if (grad != nullptr) {
+    IRONB_CUDA(cudaMemsetAsync(w.P, 0, (size_t)M * Epad * sizeof(float), st));
+    for (int l = last - 1; l >= 0; --l) {
+      EpiQ ep;
+      ep.Zprev = l >= 1 ? w.Z[l - 1] : nullptr;
+      ep.Rprev = l >= 1 ? w.R[l - 1] : nullptr;
+      ep.P = w.P;
+      ep.ld = lay->in_pad[l];
+      ep.n_true_prev = l >= 1 ? lay->out_dim[l - 1] : 0;
+      ep.is_skip = (l == lay->skip_layer);
+      ep.is_first = (l == 0);
+      ep.Epad = Epad; ep.E = E;
+      ep.beta = lay->beta;
+      int rc = launch_gemm_nt(w.R[l], lay->out_pad[l], packed + lay->off_wt[l], lay->out_pad[l], (int)M,
+                              lay->in_pad[l], lay->out_pad[l], ep, st, "sdf grad gemm");
+      if (rc) return rc;
+    }
+    normal_kernel<<<mblocks, 256, 0, st>>>(w.e, w.P, M, lay->multires, Epad, lay->scale, grad);
+    IRONB_CHECK_LAUNCH("normal_kernel");
+  }
+  return IRONB_OK;
+}
+
+extern "C" int ironb_sdf_getall_bwd(const ironb_mlp_layout* lay, const float* packed, const float* x, int64_t M,
+                                    const float* ybar, const float* fbar, const float* nbar, void* ws,
+                                    int64_t ws_bytes, float* dpacked, void* stream) {
+  (void)x;
+  IRONB_REQUIRE(lay && lay->kind == 0, "sdf_getall_bwd: layout is not an SDF layout");
+  IRONB_REQUIRE(M >= 0 && M < (1ll << 31), "sdf_getall_bwd: M out of range");
+  if (M == 0) return IRONB_OK;
+  IRONB_REQUIRE(packed && ws && dpacked, "sdf_getall_bwd: null pointer");
+  SdfWs w = carve(lay, M, true, reinterpret_cast<float*>(ws));
+  IRONB_REQUIRE(ws_bytes >= w.floats * (int64_t)sizeof(float), "sdf_getall_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int last = lay->n_lin - 1;
+  const int Epad = lay->in_pad[0], E = lay->pe_dim;
+  const int mblocks = (int)ceil_div64(M, 256);
+  const float inv_s = 1.f / lay->scale;
+  const bool has_n = nbar != nullptr;
+  const bool has_yf = (ybar != nullptr) || (fbar != nullptr);
+  if (!has_n && !has_yf) return IRONB_OK;
+
+  // ---- part B: through grad ----
+  if (has_n) {
+    pbar_kernel<<<mblocks, 256, 0, st>>>(w.e, nbar, M, lay->multires, Epad, lay->scale, w.P);
+    IRONB_CHECK_LAUNCH("pbar_kernel");
+    const float* qb = w.P;
+    for (int l = 0; l < last; ++l) {
+      // dW_l += r_l^T qbar_l
+      int rc = launch_gemm_tn(w.R[l], lay->out_pad[l], qb, lay->in_pad[l], (int)M, lay->out_pad[l], lay->in_pad[l],
+                              dpacked + lay->off_w[l], lay->in_pad[l], st, "sdf bwd B wgrad");
+      if (rc) return rc;
+      EpiB ep;
+      ep.Z = w.Z[l]; ep.R = w.R[l];
+      ep.QBnext = w.QB[(l + 1) & 1];
+      ep.PB = w.P;
+      ep.ld = lay->out_pad[l];
+      ep.n_true = lay->out_dim[l];
+      ep.pre_skip = (l + 1 == lay->skip_layer);
+      ep.Epad = Epad; ep.E = E;
+      ep.beta = lay->beta;
+      rc = launch_gemm_nt(qb, lay->in_pad[l], packed + lay->off_w[l], lay->in_pad[l], (int)M, lay->out_pad[l],
+                          lay->in_pad[l], ep, st, "sdf bwd B gemm");
+      if (rc) return rc;
+      qb = w.QB[(l + 1) & 1];
+    }
+    // dW_last[0,:] += sum_m qbar_last / s
+    int rc = launch_colsum(qb, lay->in_pad[last], (int)M, lay->in_dim[last], inv_s, dpacked + lay->off_w[last], st,
+                           "sdf bwd B colsum");
+    if (rc) return rc;
+  }
+
+  // ---- part A: ordinary back-propagation ----
+  int lstart = last;
+  const float* D = nullptr;
+  if (has_yf) {
+    int64_t tot = M * lay->out_pad[last];
+    dlast_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(ybar, fbar, M, lay->d_out, lay->out_pad[last], inv_s,
+                                                                w.D[last & 1]);
+    IRONB_CHECK_LAUNCH("dlast_kernel");
+    D = w.D[last & 1];
+  } else {
+    // delta_last == 0: start one layer down, where delta equals zbarB (which sits in the R buffer)
+    lstart = last - 1;
+    D = w.R[lstart];
+  }
+  for (int l = lstart; l >= 0; --l) {
+    int rc = launch_gemm_tn(D, lay->out_pad[l], w.U[l], lay->in_pad[l], (int)M, lay->out_pad[l], lay->in_pad[l],
+                            dpacked + lay->off_w[l], lay->in_pad[l], st, "sdf bwd A wgrad");
+    if (rc) return rc;
+    rc = launch_colsum(D, lay->out_pad[l], (int)M, lay->out_dim[l], 1.f, dpacked + lay->off_b[l], st,
+                       "sdf bwd A bias");
+    if (rc) return rc;
+    if (l == 0) break;
+    EpiA ep;
+    ep.Zprev = w.Z[l - 1];
+    ep.ZBprev = has_n ? w.R[l - 1] : nullptr;
+    ep.Dprev = w.D[(l - 1) & 1];
+    ep.ld = lay->in_pad[l];
+    ep.n_true_prev = lay->out_dim[l - 1];
+    ep.is_skip = (l == lay->skip_layer);
+    ep.beta = lay->beta;
+    rc = launch_gemm_nt(D, lay->out_pad[l], packed + lay->off_wt[l], lay->out_pad[l], (int)M, lay->in_pad[l],
+                        lay->out_pad[l], ep, st, "sdf bwd A gemm");
+    if (rc) return rc;
+    D = w.D[(l - 1) & 1];
+  }
+  return IRONB_OK;
+}

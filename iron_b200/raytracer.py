@@ -1,0 +1,336 @@
+"""RayTracer / Camera / raytrace_* / render_* with the reference's signatures (models/raytracer.py), driving
+the persistent sm_100a tracer (ironb_trace) and the fused get_all / shading kernels.
+
+What differs from the reference, by design:
+  * `RayTracer.forward` takes the same opaque `sdf` callable, but the fused tracer needs the network's
+    weights, so the callable is resolved to its owning `SDFNetwork` (the module itself, a bound method, an
+    `sdf_network` attribute, or a closure / global the lambda captured).  `raytrace_pixels`, which receives
+    the module, is the primary entry.  A callable that cannot be resolved raises TypeError (no fallback).
+  * no host round trip per marching iteration; hit points are compacted on the device (stable, ascending
+    pixel order, like boolean-mask indexing) with ONE size read-back per shading chunk.
+  * `fill_holes` / `detect_edges` (kornia morphology + Sobel + edge walk, models/raytracer.py:554-585) are
+    rows f-1 / f-4 of SURVEY.md section 8 ("next"), not built yet: passing True raises NotImplementedError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .fields import SDFNetwork
+
+
+def reparam_points(nondiff_points, nondiff_grads, nondiff_trgt_dirs, diff_sdf_vals):
+    """IDR implicit differentiation (models/raytracer.py:17-24): value == points, d points/d theta = -v/(grad.v) d f/d theta."""
+    dot = (nondiff_grads * nondiff_trgt_dirs).sum(dim=-1, keepdim=True)
+    dot = torch.clamp(dot, min=1e-4)
+    return nondiff_points - nondiff_trgt_dirs / dot * (diff_sdf_vals - diff_sdf_vals.detach())
+
+
+def _resolve_sdf_network(sdf) -> SDFNetwork:
+    if isinstance(sdf, SDFNetwork):
+        return sdf
+    for attr in ("sdf_network", "__self__"):
+        v = getattr(sdf, attr, None)
+        if isinstance(v, SDFNetwork):
+            return v
+    for cell in getattr(sdf, "__closure__", None) or ():
+        try:
+            v = cell.cell_contents
+        except ValueError:
+            continue
+        if isinstance(v, SDFNetwork):
+            return v
+    code, glob = getattr(sdf, "__code__", None), getattr(sdf, "__globals__", None)
+    if code is not None and glob is not None:
+        for name in code.co_names:
+            if isinstance(glob.get(name), SDFNetwork):
+                return glob[name]
+    raise TypeError("iron_b200.RayTracer: the fused tracer needs the SDFNetwork behind the `sdf` callable; pass the "
+                    "module, its bound .sdf method, or a lambda that captures it (no eager fallback exists)")
+
+
+class RayTracer(nn.Module):
+    def __init__(self, sdf_threshold=5.0e-5, sphere_tracing_iters=16, n_steps=128, max_num_pts=200000):
+        super().__init__()
+        self.sdf_threshold = sdf_threshold
+        self.sphere_tracing_iters = sphere_tracing_iters
+        self.n_steps = n_steps
+        self.max_num_pts = max_num_pts   # kept for signature parity; the fused sampler never materialises n_steps x rays
+        self._linspace = {}
+        self.collect_stats = False
+        self.last_stats = None
+
+    def _lin(self, dev):
+        key = (str(dev), self.n_steps)
+        if key not in self._linspace:
+            # the reference's sample positions ARE torch.linspace(0, 1, n_steps) (models/raytracer.py:144-147)
+            self._linspace[key] = torch.linspace(0, 1, steps=self.n_steps).float().to(dev).contiguous()
+        return self._linspace[key]
+
+    @torch.no_grad()
+    def forward(self, sdf, ray_o, ray_d, min_dis, max_dis, work_mask):
+        """-> {"convergent_mask": bool[N], "points": [N,3], "sdf": [N], "distance": [N]}  (models/raytracer.py:45-86)"""
+        net = _resolve_sdf_network(sdf)
+        net._check_device(ray_o)
+        dev = ray_o.device
+        sh = list(ray_o.shape[:-1])
+        o = _lib.f32c(ray_o.reshape(-1, 3))
+        d = _lib.f32c(ray_d.reshape(-1, 3))
+        tmin = _lib.f32c(min_dis.reshape(-1))
+        tmax = _lib.f32c(max_dis.reshape(-1))
+        wm = work_mask.reshape(-1).to(torch.uint8).contiguous()
+        N = o.shape[0]
+        conv = torch.zeros(N, dtype=torch.uint8, device=dev)
+        points = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        sdf_out = torch.empty(N, dtype=torch.float32, device=dev)
+        dist = torch.empty(N, dtype=torch.float32, device=dev)
+        stats = torch.zeros(8, dtype=torch.int64, device=dev) if self.collect_stats else None
+        lib = _lib.load()
+        packed = net.folded()
+        lay = net.layout
+        with torch.cuda.device(dev):
+            nbytes = lib.ironb_trace_workspace_bytes(C.byref(lay), N)
+            ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+            _lib.check(lib.ironb_trace(C.byref(lay), _lib.ptr(packed), _lib.ptr(o), _lib.ptr(d), _lib.ptr(tmin),
+                                       _lib.ptr(tmax), _lib.ptr(wm), N, float(self.sdf_threshold),
+                                       int(self.sphere_tracing_iters), int(self.n_steps), _lib.ptr(self._lin(dev)),
+                                       _lib.ptr(conv), _lib.ptr(points), _lib.ptr(sdf_out), _lib.ptr(dist),
+                                       _lib.ptr(stats), _lib.ptr(ws), ws.numel(), _lib.stream()), "trace")
+        if stats is not None:
+            self.last_stats = stats if self.last_stats is None else self.last_stats + stats
+        return {
+            "convergent_mask": conv.bool().reshape(sh),
+            "points": points.reshape(sh + [3]),
+            "sdf": sdf_out.reshape(sh),
+            "distance": dist.reshape(sh),
+        }
+
+
+@torch.no_grad()
+def intersect_sphere(ray_o, ray_d, r):
+    """Unit-sphere entry / exit distances (models/raytracer.py:223-237) -> (mask, min_dis, max_dis)."""
+    dev = ray_o.device
+    sh = list(ray_o.shape[:-1])
+    o = _lib.f32c(ray_o.reshape(-1, 3))
+    d = _lib.f32c(ray_d.reshape(-1, 3))
+    N = o.shape[0]
+    hit = torch.empty(N, dtype=torch.uint8, device=dev)
+    tmin = torch.empty(N, dtype=torch.float32, device=dev)
+    tmax = torch.empty(N, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().ironb_intersect_sphere(_lib.ptr(o), _lib.ptr(d), N, float(r), _lib.ptr(hit), _lib.ptr(tmin),
+                                                      _lib.ptr(tmax), _lib.stream()), "intersect_sphere")
+    return hit.bool().reshape(sh), tmin.reshape(sh), tmax.reshape(sh)
+
+
+class Camera(object):
+    """Pinhole camera (models/raytracer.py:240-364)."""
+
+    def __init__(self, W, H, K, W2C):
+        self.W = W
+        self.H = H
+        self.K = K
+        self.W2C = W2C
+        self.K_inv = torch.inverse(K)
+        self.C2W = torch.inverse(W2C)
+        self.device = self.K.device
+        self._kinv3 = self.K_inv[:3, :3].float().contiguous()
+        self._rot = self.C2W[:3, :3].float().contiguous()
+        self._org = self.C2W[:3, 3].float().contiguous()
+
+    def _rays(self, uv, clip_radius=None):
+        if not self.K.is_cuda:
+            raise RuntimeError("iron_b200.Camera.get_rays runs on CUDA only: build the camera from CUDA tensors")
+        dev = self.device
+        sh = list(uv.shape[:-1])
+        uvf = _lib.f32c(uv.reshape(-1, 2).to(dev))
+        N = uvf.shape[0]
+        ray_o = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        ray_d = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        nrm = torch.empty(N, dtype=torch.float32, device=dev)
+        hit = tmin = tmax = None
+        if clip_radius is not None:
+            hit = torch.empty(N, dtype=torch.uint8, device=dev)
+            tmin = torch.empty(N, dtype=torch.float32, device=dev)
+            tmax = torch.empty(N, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().ironb_camera_rays(_lib.ptr(uvf), N, _lib.ptr(self._kinv3), _lib.ptr(self._rot),
+                                                     _lib.ptr(self._org), float(clip_radius or 1.0), _lib.ptr(ray_o),
+                                                     _lib.ptr(ray_d), _lib.ptr(nrm), _lib.ptr(hit), _lib.ptr(tmin),
+                                                     _lib.ptr(tmax), _lib.stream()), "camera_rays")
+        out = (ray_o.reshape(sh + [3]), ray_d.reshape(sh + [3]), nrm.reshape(sh))
+        if clip_radius is not None:
+            out = out + (hit.reshape(sh), tmin.reshape(sh), tmax.reshape(sh))
+        return out
+
+    def get_rays(self, uv):
+        """uv [...,2] -> ray_o [...,3], ray_d [...,3] (unit), ray_d_norm [...]  (:254-286)"""
+        return self._rays(uv)
+
+    def get_camera_origin(self, prefix_shape=None):
+        ray_o = self.C2W[:3, 3]
+        if prefix_shape is not None:
+            prefix_shape = list(prefix_shape)
+            ray_o = ray_o.view([1] * len(prefix_shape) + [3]).expand(prefix_shape + [3])
+        return ray_o
+
+    def get_uv(self):
+        u, v = np.meshgrid(np.arange(self.W), np.arange(self.H))
+        return torch.from_numpy(np.stack((u, v), axis=-1).astype(np.float32)).to(self.device) + 0.5
+
+    def project(self, points):
+        sh = list(points.shape[:-1])
+        p = points.reshape(-1, 3)
+        p = torch.cat([p, torch.ones_like(p[:, :1])], dim=1)
+        uv = torch.matmul(torch.matmul(p, self.W2C.transpose(1, 0)), self.K.transpose(1, 0))
+        uv = uv[:, :2] / uv[:, 2:3]
+        return uv.view(sh + [2])
+
+    def crop_region(self, trgt_W, trgt_H, center_crop=False, ul_corner=None, image=None, mask=None):
+        """Returns (camera, image, mask) like the fork's 3-tuple (:327-351)."""
+        K = self.K.clone()
+        if ul_corner is not None:
+            ul_col, ul_row = ul_corner
+        elif center_crop:
+            ul_col = self.W // 2 - trgt_W // 2 - np.random.randint(0, 256)
+            ul_row = self.H // 2 - trgt_H // 2 - np.random.randint(0, 256)
+        else:
+            ul_col = np.random.randint(0, self.W - trgt_W)
+            ul_row = np.random.randint(0, self.H - trgt_H)
+        K[0, 2] -= ul_col
+        K[1, 2] -= ul_row
+        camera = Camera(trgt_W, trgt_H, K, self.W2C.clone())
+        if image is not None:
+            assert image.shape[0] == self.H and image.shape[1] == self.W, "image size does not match specified size"
+            image = image[ul_row:ul_row + trgt_H, ul_col:ul_col + trgt_W]
+        if mask is not None:
+            assert mask.shape[0] == self.H and mask.shape[1] == self.W, "mask size does not match specified size"
+            mask = mask[ul_row:ul_row + trgt_H, ul_col:ul_col + trgt_W]
+        return camera, image, mask
+
+    def resize(self, factor, image=None):
+        trgt_H, trgt_W = int(self.H * factor), int(self.W * factor)
+        K = self.K.clone()
+        K[0, :3] *= trgt_W / self.W
+        K[1, :3] *= trgt_H / self.H
+        camera = Camera(trgt_W, trgt_H, K, self.W2C.clone())
+        if image is not None:
+            image = torch.nn.functional.interpolate(image.permute(2, 0, 1)[None], size=(trgt_H, trgt_W), mode="area")[0]
+            image = image.permute(1, 2, 0)
+        return camera, image
+
+
+@torch.no_grad()
+def raytrace_pixels(sdf_network, raytracer, uv, camera, mask=None, max_num_rays=200000):
+    """models/raytracer.py:367-409.  One tracer call per <= max_num_rays chunk (the bisection count couples
+    the rays of a call, so the chunking is part of the reference's result)."""
+    dots_sh = list(uv.shape[:-1])
+    ray_o, ray_d, ray_d_norm, hit, tmin, tmax = camera._rays(uv, clip_radius=1.0)
+    work = hit.bool() if mask is None else (hit.bool() & mask.bool())
+    N = int(np.prod(dots_sh)) if dots_sh else 1
+    parts = {}
+    fo, fd, fn = ray_o.view(-1, 3), ray_d.view(-1, 3), ray_d_norm.view(-1)
+    fw, fa, fb = work.view(-1), tmin.view(-1), tmax.view(-1)
+    for s in range(0, N, max_num_rays):
+        e = min(N, s + max_num_rays)
+        res = raytracer(sdf_network, fo[s:e], fd[s:e], fa[s:e], fb[s:e], fw[s:e])
+        res["depth"] = res["distance"] / fn[s:e]
+        for k, v in res.items():
+            parts.setdefault(k, []).append(v)
+    out = {}
+    for k, v in parts.items():
+        v = (v[0] if len(v) == 1 else torch.cat(v, dim=0)).reshape(dots_sh + [-1])
+        out[k] = v[..., 0] if v.shape[-1] == 1 else v
+    out.update({"uv": uv, "ray_o": ray_o, "ray_d": ray_d, "ray_d_norm": ray_d_norm})
+    return out
+
+
+@torch.no_grad()
+def raytrace_camera(camera, sdf_network, raytracer, max_num_rays=200000, fill_holes=False, detect_edges=False):
+    """models/raytracer.py:542-590 without hole filling / edge detection."""
+    if fill_holes or detect_edges:
+        raise NotImplementedError("fill_holes / detect_edges are 'next' rows of the scope table (SURVEY.md 8f), not built")
+    results = raytrace_pixels(sdf_network, raytracer, camera.get_uv(), camera, max_num_rays=max_num_rays)
+    results["depth"] = results["depth"] * results["convergent_mask"].float()
+    return results
+
+
+def compact_hits(mask_flat: torch.Tensor):
+    """Stable device-side compaction of a bool/uint8 mask -> (int64 indices [M], M).  One host read (M)."""
+    dev = mask_flat.device
+    N = mask_flat.numel()
+    m8 = mask_flat.to(torch.uint8).contiguous()
+    idx = torch.empty(N + (N + 1023) // 1024 + 1, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().ironb_compact_mask(_lib.ptr(m8), N, _lib.ptr(idx), _lib.ptr(cnt), _lib.stream()),
+                   "compact_mask")
+    M = int(cnt.item())
+    return idx[:M], M
+
+
+def gather_rows(src: torch.Tensor, idx32: torch.Tensor) -> torch.Tensor:
+    src = _lib.f32c(src)
+    M, w = idx32.shape[0], src.shape[-1]
+    dst = torch.empty(M, w, dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.load().ironb_gather_rows(_lib.ptr(src), _lib.ptr(idx32.contiguous()), M, w, _lib.ptr(dst),
+                                                 _lib.stream()), "gather_rows")
+    return dst
+
+
+def render_normal_and_color(results, sdf_network, color_network_dict, render_fn, is_training=False, max_num_pts=320000):
+    """models/raytracer.py:593-662: shade the hit points chunk by chunk and merge into image-shaped buffers."""
+    dots_sh = list(results["convergent_mask"].shape)
+    P = results["points"].view(-1, 3)
+    D = results["ray_d"].reshape(-1, 3)
+    O = results["ray_o"].reshape(-1, 3)
+    Mk = results["convergent_mask"].view(-1)
+    N = Mk.shape[0]
+    merged = None
+    for s in range(0, N, max_num_pts):
+        e = min(N, s + max_num_pts)
+        mask_split = Mk[s:e]
+        idx, M = compact_hits(mask_split)
+        dev = P.device
+        if M > 0:
+            points_split = gather_rows(P[s:e], idx)
+            ray_d_split = gather_rows(D[s:e], idx)
+            ray_o_split = gather_rows(O[s:e], idx)
+            sdf_split, feature_split, normal_split = sdf_network.get_all(points_split, is_training=is_training)
+            if is_training:
+                points_split = reparam_points(points_split, normal_split.detach(), -ray_d_split.detach(), sdf_split)
+        else:
+            z = lambda: torch.zeros(0, dtype=torch.float32, device=dev)
+            points_split, ray_d_split, ray_o_split, normal_split, feature_split = z(), z(), z(), z(), z()
+        mask_arg = mask_split.clone()
+        mask_arg._ironb_idx = idx.long()   # lets iron_b200.render_fn scatter without another nonzero()/sync
+        with torch.set_grad_enabled(is_training):
+            rr = render_fn(mask_arg, color_network_dict, ray_o_split, ray_d_split, points_split, normal_split,
+                           feature_split)
+        if merged is None:
+            merged = {k: [v] for k, v in rr.items()} if rr is not None else {}
+        else:
+            for k in rr.keys():
+                merged[k].append(rr[k])
+    for k in list(merged.keys()):
+        tmp = (merged[k][0] if len(merged[k]) == 1 else torch.cat(merged[k], dim=0)).reshape(dots_sh + [-1])
+        if tmp.shape[-1] == 1:
+            tmp = tmp.squeeze(-1)
+        merged[k] = tmp
+    results.update(merged)
+
+
+def render_camera(camera, sdf_network, raytracer, color_network_dict, render_fn, fill_holes=False, handle_edges=True,
+                  is_training=False):
+    """models/raytracer.py:778-814.  handle_edges=True (the reference default) needs the edge-sampling row,
+    which is not built: pass handle_edges=False."""
+    results = raytrace_camera(camera, sdf_network, raytracer, max_num_rays=50000, fill_holes=fill_holes,
+                              detect_edges=handle_edges)
+    render_normal_and_color(results, sdf_network, color_network_dict, render_fn, is_training=is_training,
+                            max_num_pts=320000)
+    return results

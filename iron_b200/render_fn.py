@@ -1,0 +1,46 @@
+"""The 'ggx' render_fn of the stage-2 driver (render_surface.py:117-156): normalise the SDF gradient, query the
+three material networks, shade with the colocated-flash GGX model and scatter the hit results into dense,
+zero-filled buffers.  `make_render_fn(renderer)` returns the callback `render_normal_and_color` expects."""
+import torch
+
+from .rendering_func import get_materials
+
+
+def _scatter(dense_shape, idx, src, width):
+    n = 1
+    for s in dense_shape:
+        n *= s
+    if width == 1:
+        out = torch.zeros(n, dtype=torch.float32, device=src.device).index_copy(0, idx, src.reshape(-1))
+        return out.reshape(dense_shape)
+    out = torch.zeros(n, width, dtype=torch.float32, device=src.device).index_copy(0, idx, src)
+    return out.reshape(list(dense_shape) + [width])
+
+
+def make_render_fn(renderer, is_metal=False):
+    def render_fn(interior_mask, color_network_dict, ray_o, ray_d, points, normals, features):
+        dots_sh = list(interior_mask.shape)
+        dev = interior_mask.device
+        idx = getattr(interior_mask, "_ironb_idx", None)
+        if idx is None:
+            idx = torch.nonzero(interior_mask.reshape(-1), as_tuple=False).reshape(-1)
+        z3 = lambda: torch.zeros(dots_sh + [3], dtype=torch.float32, device=dev)
+        if idx.numel() == 0:
+            return {"color": z3(), "diffuse_color": z3(), "specular_color": z3(), "diffuse_albedo": z3(),
+                    "specular_albedo": z3(), "specular_roughness": z3()[..., 0].clone(), "normal": z3()}
+        normals = normals / (normals.norm(dim=-1, keepdim=True) + 1e-10)
+        params = get_materials(network_dict=color_network_dict, points=points, normals=normals, features=features,
+                               is_metal=is_metal)
+        res = renderer(color_network_dict["point_light_network"](), (points - ray_o).norm(dim=-1, keepdim=True),
+                       normals, -ray_d, params=params)
+        return {
+            "color": _scatter(dots_sh, idx, res["rgb"], 3),
+            "diffuse_color": _scatter(dots_sh, idx, res["diffuse_rgb"], 3),
+            "specular_color": _scatter(dots_sh, idx, res["specular_rgb"], 3),
+            "diffuse_albedo": _scatter(dots_sh, idx, params["diffuse_albedo"], 3),
+            "specular_albedo": _scatter(dots_sh, idx, params["specular_albedo"].contiguous(), 3),
+            "specular_roughness": _scatter(dots_sh, idx, params["specular_roughness"], 1),
+            "normal": _scatter(dots_sh, idx, normals, 3),
+        }
+
+    return render_fn

@@ -1,0 +1,72 @@
+"""Material networks + get_materials: CUDA forward/backward vs the golden vectors of the reference modules."""
+import numpy as np
+import pytest
+import torch
+
+from util import T, TOL_GRAD_REL, assert_close, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+NETS = ("diffuse_albedo_network", "specular_albedo_network", "specular_roughness_network")
+
+
+def test_materials_golden(golden):
+    import iron_b200
+    g = golden("materials")
+    torch.manual_seed(0)
+    nets = iron_b200.init_rendering_network_dict("ggx")
+    for nm in NETS:   # same seed + same construction order as the reference => same weights
+        for k, v in nets[nm].state_dict().items():
+            ref = g[f"sum.{nm}.{k}"]
+            got = np.array([v.double().sum().item(), v.double().abs().sum().item()])
+            assert np.allclose(got, ref, rtol=1e-6, atol=1e-6), (nm, k, got, ref)
+    leaves = [T(g[k]).to(DEV).requires_grad_(True) for k in ("points", "normals", "feats")]
+    mats = iron_b200.get_materials(nets, leaves[0], leaves[1], leaves[2])
+    for k in ("diffuse_albedo", "specular_albedo", "specular_roughness"):
+        assert_close(mats[k].detach().cpu().numpy(), g["out." + k], 2e-6, 2e-5, what=k)
+    loss = sum((mats[k] * T(g["up." + k]).to(DEV)).sum() for k in mats)
+    loss.backward()
+    for leaf, k in zip(leaves, ("g_points", "g_normals", "g_feats")):
+        assert_close(leaf.grad.cpu().numpy(), g[k], 1e-5 * np.abs(g[k]).max(), 1e-3, what=k)
+    for nm in NETS:
+        for k, p in nets[nm].named_parameters():
+            gr = p.grad.double().cpu()
+            ref = g[f"gsum.{nm}.{k}"]
+            got = np.array([gr.sum().item(), gr.abs().sum().item(), gr.pow(2).sum().sqrt().item()])
+            assert abs(got[2] - ref[2]) <= TOL_GRAD_REL * ref[2] + 1e-9, (nm, k, got, ref)
+            assert abs(got[1] - ref[1]) <= TOL_GRAD_REL * ref[1] + 1e-9, (nm, k, got, ref)
+            if f"g.{nm}.{k}" in g:
+                assert rel_l2(gr.numpy(), g[f"g.{nm}.{k}"]) < TOL_GRAD_REL, (nm, k)
+
+
+def test_rendering_network_modes_vs_oracle():
+    """no_view_dir and idr nets on a ragged batch vs the oracle's material_forward + autograd."""
+    import iron_b200
+    from oracle import iron_oracle as O
+    from util import oracle_params
+    for nm, M in (("diffuse_albedo_network", 777), ("specular_roughness_network", 130)):
+        cfg = O.MATERIAL_NETS[nm]
+        torch.manual_seed(4)
+        net = iron_b200.RenderingNetwork(d_feature=256, mode=cfg["mode"], d_in=cfg["d_in"], d_out=cfg["d_out"], d_hidden=256,
+                                         n_layers=4, multires=cfg["multires"], multires_view=cfg["multires_view"],
+                                         squeeze_out=cfg["squeeze_out"], output_bias=cfg["output_bias"],
+                                         output_scale=cfg["output_scale"])
+        p = {k: v.requires_grad_(True) for k, v in oracle_params(net).items()}
+        net = net.to(DEV)
+        gen = torch.Generator().manual_seed(8)
+        pts = (torch.rand(M, 3, generator=gen) - 0.5).requires_grad_(True)
+        nrm = torch.nn.functional.normalize(torch.randn(M, 3, generator=gen), dim=-1).requires_grad_(True)
+        fts = (torch.randn(M, 256, generator=gen) * 0.3).requires_grad_(True)
+        up = torch.randn(M, cfg["d_out"], generator=gen)
+        ref = O.material_forward(p, cfg, pts, nrm, -nrm if cfg["mode"] == "idr" else None, fts)
+        names = sorted(p)
+        rg = torch.autograd.grad((ref * up).sum(), [pts, nrm, fts] + [p[k] for k in names])
+        c = [t.detach().clone().to(DEV).requires_grad_(True) for t in (pts, nrm, fts)]
+        out = net(c[0], c[1], -c[1] if cfg["mode"] == "idr" else None, c[2])
+        (out * up.to(DEV)).sum().backward()
+        assert_close(out.detach().cpu().numpy(), ref.detach().numpy(), 2e-6, 2e-5, what=nm + " out")
+        for a, b, k in zip(c, rg[:3], ("points", "normals", "feats")):
+            assert_close(a.grad.cpu().numpy(), b.numpy(), 1e-5 * float(b.abs().max()), 1e-3, what=f"{nm} d_{k}")
+        for k, r in zip(names, rg[3:]):
+            got = dict(net.named_parameters())[k].grad.cpu().numpy()
+            assert rel_l2(got, r.numpy()) < TOL_GRAD_REL, (nm, k, rel_l2(got, r.numpy()))

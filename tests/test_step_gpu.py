@@ -1,0 +1,85 @@
+"""One full stage-2 step (trace -> get_all -> reparam -> materials -> GGX -> loss -> backward) on the CUDA path vs
+the golden step produced by the reference modules (32x32 silhouette crop, H=256)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import iron_oracle as O
+from util import T, TOL_GRAD_REL, TOL_NORMAL, TOL_RGB, assert_close, perturb, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def build():
+    import iron_b200
+    torch.manual_seed(0)
+    nets = iron_b200.init_rendering_network_dict("ggx")       # same RNG order as make_golden section 4
+    torch.manual_seed(0)
+    sdf = iron_b200.SDFNetwork(d_in=3, d_out=257, d_hidden=256, n_layers=8, skip_in=[4], multires=6, bias=0.5,
+                               scale=1.0, geometric_init=True, weight_norm=True)
+    perturb(sdf, 0.005, seed=1)
+    sdf = sdf.to(DEV)
+    nets["point_light_network"].set_light(32.0)
+    K = torch.tensor(O.FIXTURE_K, dtype=torch.float64).reshape(4, 4).float().to(DEV)
+    W2C = torch.tensor(O.FIXTURE_W2C, dtype=torch.float64).reshape(4, 4).float().to(DEV)
+    cam512 = iron_b200.Camera(512, 512, K, W2C)
+    return iron_b200, sdf, nets, cam512
+
+
+def test_step_golden(golden):
+    g = golden("step_h256")
+    ib, sdf, nets, cam512 = build()
+    # the material nets were built after a color_network + under the same seed as the reference: check one pin
+    cam, _, _ = cam512.crop_region(32, 32, ul_corner=tuple(int(v) for v in g["ul"]))
+    rend = ib.GGXColocatedRenderer(use_cuda=True)
+    loss, res = ib.stage2_step(sdf, nets, ib.RayTracer(), ib.make_render_fn(rend), cam, T(g["target"]).to(DEV),
+                               T(g["eik_points"]).to(DEV), eik_weight=0.1)
+    m = res["convergent_mask"].cpu().numpy()
+    mr = g["mask"]
+    assert (m == mr).mean() >= 0.998, f"hit mask agreement {(m == mr).mean():.4f} on {m.size} rays"
+    both = m & mr
+    # BASELINE tolerances per output, on common hits: normal 1e-4, RGB 1e-3, depth 1e-4 (quantile, see test_trace_gpu)
+    assert_close(res["normal"].detach().cpu().numpy()[both], g["res.normal"][both], TOL_NORMAL, what="normal", frac=0.995)
+    for k in ("color", "diffuse_color", "specular_color"):
+        assert_close(res[k].detach().cpu().numpy()[both], g["res." + k][both], TOL_RGB, 1e-3, what=k, frac=0.995)
+    for k in ("diffuse_albedo", "specular_albedo", "specular_roughness"):
+        assert_close(res[k].detach().cpu().numpy()[both], g["res." + k][both], 1e-4, 1e-4, what=k, frac=0.995)
+    assert_close(res["distance"].cpu().numpy()[both], g["res.distance"][both], 1e-4, what="distance", frac=0.995)
+    same_mask = bool((m == mr).all())
+    assert abs(float(loss) - float(g["loss"])) <= (1e-3 if same_mask else 2e-2) * abs(float(g["loss"])), (float(loss), float(g["loss"]))
+    # parameter gradients: 1e-3 relative (L2 norm of every tensor) when the hit sets are identical; a ray that
+    # flips adds/removes a whole pixel's contribution, so the bound is loosened to 5 % in that case and reported
+    tol = TOL_GRAD_REL if same_mask else 5e-2
+    named = [("sdf." + k, p) for k, p in sdf.named_parameters()]
+    for nm in ("diffuse_albedo_network", "specular_albedo_network", "specular_roughness_network", "point_light_network"):
+        named += [(nm + "." + k, p) for k, p in nets[nm].named_parameters()]
+    worst = 0.0
+    for k, p in named:
+        assert p.grad is not None, k
+        gr = p.grad.double().cpu()
+        ref = g["gsum." + k]
+        nrm_err = abs(gr.pow(2).sum().sqrt().item() - ref[2]) / max(ref[2], 1e-12)
+        worst = max(worst, nrm_err)
+        assert nrm_err <= tol, (k, gr.pow(2).sum().sqrt().item(), ref[2], "same_mask", same_mask)
+        if "g." + k in g:
+            r = rel_l2(gr.numpy(), g["g." + k])
+            worst = max(worst, r)
+            assert r <= tol * 2, (k, r, "same_mask", same_mask)
+    print(f"step parity: same_mask={same_mask} worst relative gradient error {worst:.2e}")
+
+
+def test_render_camera_inference(golden):
+    """is_training=False path: detached outputs, no autograd graph, same images."""
+    g = golden("step_h256")
+    ib, sdf, nets, cam512 = build()
+    cam, _, _ = cam512.crop_region(32, 32, ul_corner=tuple(int(v) for v in g["ul"]))
+    rend = ib.GGXColocatedRenderer(use_cuda=True)
+    res = ib.render_camera(cam, sdf, ib.RayTracer(), nets, ib.make_render_fn(rend), fill_holes=False, handle_edges=False,
+                           is_training=False)
+    assert not res["color"].requires_grad
+    m, mr = res["convergent_mask"].cpu().numpy(), g["mask"]
+    both = m & mr
+    assert_close(res["color"].cpu().numpy()[both], g["res.color"][both], TOL_RGB, 1e-3, what="color", frac=0.995)
+    assert res["color"].shape == (32, 32, 3) and res["specular_roughness"].shape == (32, 32)
+    assert float(res["color"][~res["convergent_mask"]].abs().max()) == 0.0
