@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- traced+shaded rays/s (fwd+bwd) of the IRON stage-2 hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--hidden 512] [--patch 64]
+
+Workload (BASELINE.json configs[1]): one stage-2 training step on a 64x64 crop (4096 rays) of the 512x512
+colocated-flash fixture view, 8x512 SDF MLP (PE L=6, skip@4, softplus beta=100), three 4x256 material MLPs, GGX
+shading, L2 image loss + eikonal, backward (incl. the double backward through the SDF net); synthetic
+random-init networks (seed 0) and a synthetic target.  One "step" = trace -> shade -> loss -> backward
+[-> gradient allreduce when N > 1].  Rays shard across ranks with replicated weights (weak scaling: every rank
+traces its own 4096-ray crop); the only collective is the per-step NCCL allreduce of the flat gradient buffer.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed (CUDA events per step, L2 flushed between steps);
+`e2e` runs the same step through the public API from pinned HOST buffers with the H2D/D2H copies in the timed
+region; `roofline` is the dominant kernel (the persistent tracer's SDF-MLP tiles); `cpu_baseline` is the CPU
+oracle (a PyTorch-CPU restatement of the reference path) timed on this box's host cores.
+`--impl reference` times that CPU oracle alone (the reference is pure Python and cannot travel to the GPU box;
+the oracle is pinned to it by tests/golden/*).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "traced+shaded rays/sec fwd+bwd (8x512 SDF MLP, GGX)"
+UNIT = "rays/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def crop_corner(rank: int, patch: int):
+    """Per-rank 64x64 crop of the 512x512 view: rank 0 = the canonical centre crop, others tile around it."""
+    offs = [(0, 0), (1, 0), (-1, 0), (0, 1), (0, -1), (1, 1), (-1, -1), (1, -1)]
+    dx, dy = offs[rank % 8]
+    c = 256 - patch // 2
+    return (c + dx * patch, c + dy * patch)
+
+
+# ------------------------------------------------------------------------------------------ CPU oracle arm
+def oracle_setup(hidden: int, patch: int, rank: int = 0):
+    import torch
+    from oracle import iron_oracle as O
+    torch.manual_seed(0)
+    mats = O.make_material_dict()
+    torch.manual_seed(0)
+    sdf = O.make_sdf_params(d_hidden=hidden)
+    for d in [sdf] + list(mats.values()):
+        for v in d.values():
+            v.requires_grad_(True)
+    light = torch.tensor(32.0, requires_grad=True)
+    cam = O.OCamera.fixture().crop(patch, patch, crop_corner(rank, patch))
+    target = torch.rand(patch, patch, 3, generator=torch.Generator().manual_seed(11)) * 0.5
+    eik = torch.empty(patch * patch // 2, 3).uniform_(-1.0, 1.0, generator=torch.Generator().manual_seed(12))
+    return O, sdf, mats, light, cam, target, eik
+
+
+def oracle_step(state):
+    import torch
+    O, sdf, mats, light, cam, target, eik = state
+    for d in [sdf] + list(mats.values()):
+        for v in d.values():
+            v.grad = None
+    light.grad = None
+    t0 = time.perf_counter()
+    O.stage2_step(sdf, mats, light, cam, target, eik.clone())
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(hidden: int, patch: int, budget_s: float = 20.0):
+    """The CPU oracle on this box's host cores, bounded to ~budget_s of CPU work: the same step on the same
+    weights, on the largest centred sub-crop whose estimated time fits."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # calibrate on a 16x16 crop, then pick the sample size
+    st = oracle_setup(hidden, 16)
+    t16 = oracle_step(st)
+    t16 = min(t16, oracle_step(st))
+    per_ray = t16 / 256.0
+    size = patch
+    while size > 16 and per_ray * size * size * 2 > budget_s:
+        size //= 2
+    st = oracle_setup(hidden, size)
+    oracle_step(st)                      # warm-up
+    ts = [oracle_step(st)]
+    if sum(ts) * 2 < budget_s:
+        ts.append(oracle_step(st))
+    t = statistics.median(ts)
+    return {"value": size * size / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{size}x{size} centre crop ({size * size} rays) of the same view/weights, {len(ts)} timed step(s) "
+                      f"after 1 warm-up, torch CPU fp32 {torch.get_num_threads()} threads, {t:.2f} s/step"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python/PyTorch and
+    /root/reference does not exist on the GPU box, so this times oracle/iron_oracle.py (pinned to the reference by
+    tests/golden) with all host threads, on the same config."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    st = oracle_setup(args.hidden, 16)
+    t16 = min(oracle_step(st), oracle_step(st))
+    per_ray = t16 / 256.0
+    size = args.patch
+    total = args.steps + args.warmup
+    while size > 16 and per_ray * size * size * total > 200.0:
+        size //= 2
+    st = oracle_setup(args.hidden, size)
+    for _ in range(args.warmup):
+        oracle_step(st)
+    ts = [oracle_step(st) for _ in range(args.steps)]
+    t = sum(ts) / len(ts)
+    v = size * size / t
+    sample = (f"{size}x{size} centre crop ({size * size} rays/step) of the configs[1] view, oracle port of the reference "
+              f"path, torch CPU fp32, {cores} threads")
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": workload_config(args, size),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, patch):
+    return {"workload": f"BASELINE configs[1]: IRON stage-2 step, {patch}x{patch} crop ({patch * patch} rays/GPU) of the 512x512 "
+                        f"colocated-flash fixture view, trace+shade+loss+backward",
+            "sdf_mlp": f"8x{args.hidden}, PE L=6, skip@4, softplus(100), weight-norm", "material_mlps": "3 x (4x256, ReLU)",
+            "rays_per_gpu": patch * patch, "eikonal_points": patch * patch // 2, "parallelism": f"dp{args.gpus} (rays sharded, weights replicated)",
+            "l2": "256 MiB flush between steps, outside the per-step CUDA-event pairs",
+            "init": "seed-0 geometric init, light=32"}
+
+
+# ------------------------------------------------------------------------------------------ CUDA arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import iron_b200 as ib
+    from iron_b200 import _lib
+    from oracle import iron_oracle as O   # fixture constants only (camera K / W2C); nothing is computed with it here
+    lib = _lib.load()
+
+    H, S = args.hidden, args.patch
+    torch.manual_seed(0)
+    nets = ib.init_rendering_network_dict("ggx")
+    torch.manual_seed(0)
+    sdf = ib.SDFNetwork(d_in=3, d_out=257, d_hidden=H, n_layers=8, skip_in=[4], multires=6, bias=0.5, scale=1.0,
+                        geometric_init=True, weight_norm=True).to(dev)
+    nets["point_light_network"].set_light(32.0)
+    nets = {k: v.to(dev) for k, v in nets.items()}
+    rend = ib.GGXColocatedRenderer(use_cuda=True)
+    render_fn = ib.make_render_fn(rend)
+    tracer = ib.RayTracer()
+    tracer.collect_stats = True
+    K_h = torch.tensor(O.FIXTURE_K, dtype=torch.float64).reshape(4, 4).float().pin_memory()
+    W2C_h = torch.tensor(O.FIXTURE_W2C, dtype=torch.float64).reshape(4, 4).float().pin_memory()
+    ul = crop_corner(rank, S)
+    target_h = (torch.rand(S, S, 3, generator=torch.Generator().manual_seed(11 + rank)) * 0.5).pin_memory()
+    eik_h = torch.empty(S * S // 2, 3).uniform_(-1.0, 1.0, generator=torch.Generator().manual_seed(12 + rank)).pin_memory()
+
+    def make_cam(Kd, Wd):
+        cam512 = ib.Camera(512, 512, Kd, Wd)
+        return cam512.crop_region(S, S, ul_corner=ul)[0]
+
+    cam = make_cam(K_h.to(dev), W2C_h.to(dev))
+    target, eik = target_h.to(dev), eik_h.to(dev)
+    params = [p for p in sdf.parameters()]
+    for nm in ("diffuse_albedo_network", "specular_albedo_network", "specular_roughness_network", "point_light_network"):
+        params += list(nets[nm].parameters())
+    n_params = sum(p.numel() for p in params)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    trace_ms = []
+
+    def step(cam_, target_, eik_, time_trace=False):
+        for p in params:
+            p.grad = None
+        if time_trace:   # time the dominant kernel (the tracer's four phase launches) on the launching stream
+            orig = tracer.forward
+            evs = []
+
+            def timed(*a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = orig(*a, **k)
+                e1.record()
+                evs.append((e0, e1))
+                return r
+            tracer.forward = timed
+        loss, res = ib.stage2_step(sdf, nets, tracer, render_fn, cam_, target_, eik_)
+        if time_trace:
+            tracer.forward = orig
+            trace_ms.append(evs)
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            flat.div_(world)
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+                off += p.numel()
+        return loss, res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        step(cam, target, eik)
+    barrier()
+
+    # ---- timed: K steps, per-step CUDA events, L2 flushed between steps
+    sampler = ClockSampler(local) if rank == 0 else None
+    tracer.last_stats = None
+    l0 = lib.ironb_launch_count()
+    evs = []
+    hits = 0
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss, res = step(cam, target, eik, time_trace=True)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = lib.ironb_launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    my_ms = sum(step_ms)
+    tr_ms = [sum(a.elapsed_time(b) for a, b in ev) for ev in trace_ms]
+    stats = tracer.last_stats.cpu().tolist()
+    hits = int(res["convergent_mask"].sum().item())
+    t = torch.tensor([my_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    rays_total = S * S * world * args.steps
+    value = rays_total / (total_ms * 1e-3)
+
+    # ---- e2e: same step through the public API from pinned host buffers (H2D + D2H inside the timed region)
+    barrier()
+    e2e_steps = args.steps
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        Kd, Wd = K_h.to(dev, non_blocking=True), W2C_h.to(dev, non_blocking=True)
+        tg, ek = target_h.to(dev, non_blocking=True), eik_h.to(dev, non_blocking=True)
+        loss, _ = step(make_cam(Kd, Wd), tg, ek)
+        loss_host = float(loss.item())          # D2H of the step's result
+    barrier()
+    e2e_t = time.perf_counter() - t0
+    te = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = S * S * world * e2e_steps / float(te.item())
+    h2d = K_h.numel() * 4 + W2C_h.numel() * 4 + target_h.numel() * 4 + eik_h.numel() * 4
+    d2h = 4 + 4   # loss + the hit count the shading chunk reads back
+
+    if rank == 0:
+        pk = peaks()
+        evals = stats[0] + stats[1] + stats[2]                       # SDF evaluations the tracer executed, all K steps
+        flop_per_eval = 2.0 * (7 * H * H + H)                       # sdf-only evaluation
+        tr_total_ms = sum(tr_ms)
+        achieved = evals * flop_per_eval / (tr_total_ms * 1e-3) / 1e12 if tr_total_ms > 0 else 0.0
+        peak = pk["bf16_tflops_sustained"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, S),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(te.item()) * 1e3 / e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "trace_kernel<NJ,TM,phase 0..3> (persistent tracer: fused PE + 8 SDF-MLP layers per tile)",
+                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "mode": "fp32 FFMA (SIMT) with fp32 accumulate; peak = bf16 dense tensor, sustained, of " + pk["source"],
+                         "flop_per_eval": flop_per_eval, "evals_per_step": evals / args.steps,
+                         "kernel_ms_per_step": tr_total_ms / args.steps,
+                         "kernel_share_of_step": tr_total_ms / my_ms if my_ms else None},
+            "tracer": {"evals_sphere": stats[0] / args.steps, "evals_sampler": stats[1] / args.steps,
+                       "evals_bisect": stats[2] / args.steps, "sampler_rays": stats[3] / args.steps,
+                       "root_rays": stats[4] / args.steps, "k_max": stats[5], "hits": hits, "rays": S * S},
+            "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps, "grad_params": n_params,
+            "loss": loss_host,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(H, S)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--hidden", type=int, default=512)
+    ap.add_argument("--patch", type=int, default=64)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,8 @@ typedef struct ironb_mlp_layout {
 
 const char* ironb_last_error(void);
 int ironb_version(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t ironb_launch_count(void);
 
 /* ---------------------------------------------------------------- layouts (host only) */
 int ironb_sdf_layout(int d_in, int d_out, int d_hidden, int n_layers, int skip_layer, int multires,

@@ -42,6 +42,7 @@ _PP = C.POINTER(C.c_void_p)
 _PROTOS = {
     "ironb_last_error": (C.c_char_p, []),
     "ironb_version": (_INT, []),
+    "ironb_launch_count": (_I64, []),
     "ironb_sdf_layout": (_INT, [_INT, _INT, _INT, _INT, _INT, _INT, _F, _F, _LAY]),
     "ironb_matnet_layout": (_INT, [_INT, _INT, _INT, _INT, _LAY]),
     "ironb_mlp_fold": (_INT, [_LAY, _PP, _PP, _PP, _P, _P]),

@@ -10,6 +10,7 @@
 namespace ironb {
 
 void set_error(const char* fmt, ...);
+void note_launch();   // bumps the process-wide kernel-launch counter (ironb_launch_count)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -24,6 +25,7 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 #define IRONB_CHECK_LAUNCH(what)                                               \
   do {                                                                         \
     cudaError_t e__ = cudaGetLastError();                                      \
+    ::ironb::note_launch();                                                    \
     if (e__ != cudaSuccess) {                                                  \
       ::ironb::set_error("%s: %s", what, cudaGetErrorString(e__));             \
       return (int)e__;                                                         \

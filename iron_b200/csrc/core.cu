@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace ironb {
@@ -14,6 +16,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int num_sms() {
   static int cached[64] = {0};
@@ -49,6 +54,7 @@ using namespace ironb;
 
 extern "C" const char* ironb_last_error(void) { return g_err; }
 extern "C" int ironb_version(void) { return 100; }
+extern "C" int64_t ironb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // Layer shapes of SDFNetwork.__init__ (models/fields.py:26-45): dims = [E] + [H]*n_layers + [d_out];
 // the layer feeding the skip layer emits H - E features.

@@ -235,7 +235,15 @@ __global__ void __launch_bounds__(TPB, 1) trace_kernel(TraceNet net, TraceArgs A
   // one-time init
   for (int i = tid; i < TM; i += TPB) { S.ray[i] = -1; S.x[0][i] = S.x[1][i] = S.x[2][i] = 0.f; }
   if (tid < G) S.g_ray[tid] = -1;
-  if (tid == 0) { S.exhausted = 0; S.kmax = (MODE == 3) ? A.counters[5] : 0; }
+  if (tid == 0) {
+    S.exhausted = 0;
+    S.kmax = (MODE == 3) ? A.counters[5] : 0;
+    if (MODE == 3 && blockIdx.x == 0 && A.stats) {   // lists are final here: publish their sizes
+      atomicAdd(A.stats + 3, (unsigned long long)A.counters[1]);
+      atomicAdd(A.stats + 4, (unsigned long long)A.counters[3]);
+      atomicMax(A.stats + 5, (unsigned long long)A.counters[5]);
+    }
+  }
   for (int i = tid; i < SM::EPAD_MAX * TMS; i += TPB) ebuf[i] = 0.f;
   __syncthreads();
 

@@ -107,7 +107,7 @@ def test_trace_inputs_not_mutated_and_stats(golden, net256):
     p = oracle_params(net256)
     ro = O.trace_rays(lambda x: O.sdf_forward(p, x)[..., 0], o.cpu(), d.cpu(), t0.cpu(), t1.cpu(), hit.cpu(), stats=stats)
     assert abs(int(st[0]) - stats.evals_sphere) <= 0.002 * stats.evals_sphere + 8, (st, stats.evals_sphere)
-    assert int(st[3]) == 0 or True
+    assert abs(int(st[3]) - stats.n_sampler_rays) <= 2 and abs(int(st[4]) - stats.n_root_rays) <= 2, (st, stats.n_sampler_rays, stats.n_root_rays)
     assert int(st[1]) <= stats.evals_sampler, (int(st[1]), stats.evals_sampler)
     assert int(st[5]) == stats.k_max, (int(st[5]), stats.k_max)
     assert (res["convergent_mask"].cpu() == ro["convergent_mask"]).float().mean() >= 0.999
@@ -137,10 +137,10 @@ def test_trace_h512_vs_oracle():
                                geometric_init=True, weight_norm=True)
     p = oracle_params(net)
     net = net.to(DEV)
-    cam = O.OCamera.fixture().crop(48, 48, (300, 232))
+    cam = O.OCamera.fixture().crop(48, 48, (350, 232))
     uv = cam.pixel_uv()
     ref = O.trace_pixels(p, cam, uv)
-    cam_g, _, _ = fixture_camera().crop_region(48, 48, ul_corner=(300, 232))
+    cam_g, _, _ = fixture_camera().crop_region(48, 48, ul_corner=(350, 232))
     res = iron_b200.raytrace_pixels(net, iron_b200.RayTracer(), cam_g.get_uv(), cam_g)
     m, mr = res["convergent_mask"].cpu().numpy(), ref["convergent_mask"].numpy()
     assert 0 < mr.sum() < mr.size, "crop should straddle the silhouette"
