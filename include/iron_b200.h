@@ -67,6 +67,14 @@ int ironb_version(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t ironb_launch_count(void);
 
+/* GEMM arithmetic of the differentiable part (get_all forward / double backward, material MLPs):
+ * 1 = tcgen05 3xTF32 split (tensor cores, fp32-grade accuracy; the default), 0 = fp32 FFMA tiles.
+ * Returns the previous mode.  The environment variable IRONB_GEMM=simt selects 0 at start-up. */
+int ironb_set_gemm_mode(int mode);
+/* C[M][ldc] = A[M][lda] * B[N][ldb]^T (fp32, K-major operands, N/K/ld multiples of 4): unit-test entry of both GEMMs. */
+int ironb_gemm_nt(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float* C, int ldc,
+                  int mode, void* stream);
+
 /* ---------------------------------------------------------------- layouts (host only) */
 int ironb_sdf_layout(int d_in, int d_out, int d_hidden, int n_layers, int skip_layer, int multires,
                      float scale, float beta, ironb_mlp_layout* out);

@@ -1,0 +1,85 @@
+// Host side of the tcgen05 GEMM: TMA tensor-map encoding through the driver entry point, the GEMM mode switch,
+// and a plain C = A * B^T entry used by the unit tests of both GEMM implementations.
+#include <stdlib.h>
+
+#include <atomic>
+
+#include "gemm.cuh"
+#include "gemm_tc.cuh"
+
+namespace ironb {
+namespace tc {
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("tcgen05 gemm: cuTensorMapEncodeTiled is unavailable"); return IRONB_ENOSUP; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) || (ld & 3) || K <= 0 || rows <= 0) {
+    set_error("tcgen05 gemm: operand must be 16-byte aligned with a row pitch that is a multiple of 4 floats");
+    return IRONB_EINVAL;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, 128u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("tcgen05 gemm: cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld); return IRONB_EINVAL; }
+  return IRONB_OK;
+}
+
+static std::atomic<int> g_mode{-1};
+bool tc_enabled() {
+  int m = g_mode.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = getenv("IRONB_GEMM");
+    m = (e && (e[0] == 's' || e[0] == 'S' || e[0] == '0')) ? 0 : 1;   // IRONB_GEMM=simt selects the FFMA GEMM
+    g_mode.store(m, std::memory_order_relaxed);
+  }
+  return m == 1;
+}
+int set_mode(int mode) {
+  int prev = tc_enabled() ? 1 : 0;
+  g_mode.store(mode ? 1 : 0, std::memory_order_relaxed);
+  return prev;
+}
+
+}  // namespace tc
+
+namespace {
+struct EpiStore {
+  float* C;
+  int ldc;
+  __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[4]) const {
+    *reinterpret_cast<float4*>(C + (int64_t)m * ldc + n0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+};
+}  // namespace
+}  // namespace ironb
+
+using namespace ironb;
+
+extern "C" int ironb_set_gemm_mode(int mode) { return tc::set_mode(mode); }
+
+extern "C" int ironb_gemm_nt(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float* C, int ldc,
+                             int mode, void* stream) {
+  IRONB_REQUIRE(A && B && C, "gemm_nt: null pointer");
+  IRONB_REQUIRE((N & 3) == 0 && (K & 3) == 0 && (ldc & 3) == 0, "gemm_nt: N, K, ldc must be multiples of 4");
+  EpiStore ep{C, ldc};
+  if (mode == 1) return tc::launch_gemm_nt_tc(A, lda, B, ldb, M, N, K, ep, as_stream(stream), "gemm_nt (tcgen05)");
+  return launch_gemm_nt(A, lda, B, ldb, M, N, K, ep, as_stream(stream), "gemm_nt (simt)");
+}

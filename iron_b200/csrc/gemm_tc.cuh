@@ -1,0 +1,283 @@
+// tcgen05 (5th-gen tensor core) tile GEMM with fp32-grade accuracy:  C[m][n] = epi( sum_k A[m][k] * B[n][k] )
+//
+//   * A [M][lda] and B [N][ldb] are fp32, K-major, and stay ONE fp32 copy in global memory / L2.
+//   * TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) stages 128 x 32 fp32 boxes of A and B into a 3-stage
+//     shared-memory ring (mbarrier complete_tx).
+//   * four "splitter" warps rewrite each staged tile in place as hi = tf32_rn(x) and write lo = tf32_rn(x - hi)
+//     next to it (same swizzled offsets, so no address math), then fence to the async proxy.
+//   * one thread issues, per 8-wide k-step, THREE tcgen05.mma.kind::tf32 (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi): the
+//     3xTF32 split whose products are exact and whose sum is accumulated in fp32 in TMEM (128 lanes x 128 cols).
+//     tcgen05.commit releases the ring slot back to the TMA producer and finally publishes the accumulator.
+//   * the splitter warps then become the epilogue: tcgen05.ld 32x32b.x32 (TMEM -> registers), and the same
+//     epilogue functors as the SIMT GEMM (bias / softplus / skip concat / backward elementwise) write the result.
+//
+// Why split in shared memory instead of pre-splitting in HBM: 3xTF32 operands are 8 B per element; at 128 x 128
+// tiles that is ~84 B/clk/SM of L2 traffic, above the measured L2 slice throughput, while one fp32 copy is 42 B/clk.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace ironb {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;            // 16 KiB: one operand tile (128 rows x 128 B)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // [A_hi][B_hi][A_lo][B_lo]
+constexpr int HI_BYTES = 2 * TILE_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers + tmem ptr*/;
+constexpr int NTHREADS = 192;                      // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-5 split + epilogue
+constexpr uint32_t TMEM_COLS = 512;               // three 128-column accumulators (even k-steps, odd k-steps, lo-terms)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);          // start address
+  d |= (uint64_t)1 << 16;                               // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+  return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+template <class Epi>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N, int K,
+                  Epi epi) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                       // SWIZZLE_128B tiles need 1024 B alignment
+  unsigned char* base_ptr = smem_raw + (base - raw);
+  const uint32_t bars = base + STAGES * STAGE_BYTES;                  // full[3] conv[3] empty[3] acc[1] | tmem ptr
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto conv = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  const uint32_t acc_bar = bars + 8u * (3 * STAGES);
+  const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nk = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full(s), 1);
+      mbar_init(conv(s), 128);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: 128 columns x 128 lanes of fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(empty(s), ph ^ 1);
+        mbar_arrive_expect_tx(full(s), HI_BYTES);
+        const uint32_t st = base + s * STAGE_BYTES;
+        tma_load_2d(st, &mapA, it * BK, m0, full(s));
+        tma_load_2d(st + TILE_BYTES, &mapB, it * BK, n0, full(s));
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(conv(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = base + s * STAGE_BYTES;
+        const uint64_t a_hi = make_desc(st), b_hi = make_desc(st + TILE_BYTES);
+        const uint64_t a_lo = make_desc(st + 2 * TILE_BYTES), b_lo = make_desc(st + 3 * TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < BK / 8; ++kk) {
+          const uint64_t adv = (uint64_t)(kk * 2);          // 8 tf32 = 32 B = 2 x 16 B along the swizzled row
+          const int g = it * (BK / 8) + kk;                 // global k-step
+          // The tensor core accumulates into TMEM with truncation, so every accumulation step costs up to 1 ulp
+          // of the running sum, always towards zero.  Keep the chains short and the small terms apart:
+          // hi*hi alternates between two accumulators, the two lo cross terms go to a third; the epilogue adds
+          // the three in fp32 round-to-nearest.
+          tc_mma_tf32(tmem + ((g & 1) ? 128u : 0u), a_hi + adv, b_hi + adv, IDESC, g >= 2 ? 1u : 0u);
+          tc_mma_tf32(tmem + 256u, a_lo + adv, b_hi + adv, IDESC, g >= 1 ? 1u : 0u);
+          tc_mma_tf32(tmem + 256u, a_hi + adv, b_lo + adv, IDESC, 1u);
+        }
+        tc_commit(empty(s));          // slot free once these MMAs have read it
+      }
+      tc_commit(acc_bar);             // accumulator complete
+    }
+  } else {
+    // ================= splitter, then epilogue (warps 2..5) =================
+    const int t = threadIdx.x - 64;   // 0..127
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(full(s), ph);
+      float4* hi = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES);
+      float4* lo = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES + HI_BYTES);
+#pragma unroll 4
+      for (int j = 0; j < HI_BYTES / 16 / 128; ++j) {
+        const int c = t + j * 128;
+        float4 v = hi[c];
+        float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        float4 l = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+        hi[c] = h;
+        lo[c] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      mbar_arrive(conv(s));
+    }
+    // epilogue: TMEM lane = tile row (warp%4 selects the 32-lane quarter), column = tile column
+    mbar_wait(acc_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32], r1[32], r2[32];
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      tmem_ld32(taddr, r);
+      tmem_ld32(taddr + 128u, r1);
+      tmem_ld32(taddr + 256u, r2);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        r[i] = __float_as_uint(__fadd_rn(__fadd_rn(__uint_as_float(r[i]), __uint_as_float(r1[i])), __uint_as_float(r2[i])));
+      if (m < M) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int n = n0 + c0 + g * 4;
+          if (n < N) {
+            const float v[4] = {__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]), __uint_as_float(r[g * 4 + 2]),
+                                __uint_as_float(r[g * 4 + 3])};
+            epi(m, n, v);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn();
+// rows x K fp32 matrix with row pitch ld floats -> 2-D map with a (BK x 128) SWIZZLE_128B box, zero fill out of bounds
+int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld);
+bool tc_enabled();
+
+template <class Epi>
+int launch_gemm_nt_tc(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const Epi& epi, cudaStream_t st,
+                      const char* what) {
+  if (M <= 0 || N <= 0) return IRONB_OK;
+  CUtensorMap mA, mB;
+  int rc = make_map(&mA, A, M, K, lda);
+  if (rc) return rc;
+  rc = make_map(&mB, B, N, K, ldb);
+  if (rc) return rc;
+  auto kern = gemm_nt_tc_kernel<Epi>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div64(N, BN), (unsigned)ceil_div64(M, BM));
+  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mB, M, N, K, epi);
+  IRONB_CHECK_LAUNCH(what);
+  return IRONB_OK;
+}
+
+}  // namespace tc
+
+// fp32 FFMA tiles (exact association) or tcgen05 3xTF32 tiles, per ironb_set_gemm_mode / IRONB_GEMM.
+template <class Epi>
+int launch_gemm_nt_auto(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const Epi& epi,
+                        cudaStream_t st, const char* what) {
+  if (tc::tc_enabled()) return tc::launch_gemm_nt_tc(A, lda, B, ldb, M, N, K, epi, st, what);
+  return launch_gemm_nt(A, lda, B, ldb, M, N, K, epi, st, what);
+}
+}  // namespace ironb

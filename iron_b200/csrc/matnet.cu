@@ -3,7 +3,7 @@
 // -> Linear -> output_scale * (x + output_bias) -> [squeeze_out_scale * sigmoid].  skip_in = () only.
 // One fp32 tile GEMM per layer (gemm.cuh); ReLU / output transform fused into the epilogues, the input
 // concatenation + positional encodings and their backward are two small elementwise kernels.
-#include "gemm.cuh"
+#include "gemm_tc.cuh"
 
 namespace ironb {
 namespace {
@@ -224,13 +224,13 @@ extern "C" int ironb_matnet_fwd(const ironb_mlp_layout* lay, const ironb_matnet_
   IRONB_CHECK_LAUNCH("assemble_kernel");
   for (int l = 0; l < last; ++l) {
     EpiRelu ep{packed + lay->off_b[l], w.U[l + 1], lay->out_pad[l], lay->out_dim[l]};
-    int rc = launch_gemm_nt(w.U[l], lay->in_pad[l], packed + lay->off_w[l], lay->in_pad[l], (int)M, lay->out_pad[l],
+    int rc = launch_gemm_nt_auto(w.U[l], lay->in_pad[l], packed + lay->off_w[l], lay->in_pad[l], (int)M, lay->out_pad[l],
                             lay->in_pad[l], ep, st, "matnet fwd gemm");
     if (rc) return rc;
   }
   EpiMatOut ep{packed + lay->off_b[last], out, lay->d_out, cfg->squeeze, cfg->out_bias, cfg->out_scale,
                cfg->squeeze_scale};
-  return launch_gemm_nt(w.U[last], lay->in_pad[last], packed + lay->off_w[last], lay->in_pad[last], (int)M,
+  return launch_gemm_nt_auto(w.U[last], lay->in_pad[last], packed + lay->off_w[last], lay->in_pad[last], (int)M,
                         lay->out_pad[last], lay->in_pad[last], ep, st, "matnet fwd out gemm");
 }
 
@@ -263,13 +263,13 @@ extern "C" int ironb_matnet_bwd(const ironb_mlp_layout* lay, const ironb_matnet_
     float* Dn = w.D[(l + 1) & 1];
     if (l > 0) {
       EpiReluBwd ep{w.U[l], Dn, lay->in_pad[l], lay->out_dim[l - 1]};
-      rc = launch_gemm_nt(D, lay->out_pad[l], packed + lay->off_wt[l], lay->out_pad[l], (int)M, lay->in_pad[l],
+      rc = launch_gemm_nt_auto(D, lay->out_pad[l], packed + lay->off_wt[l], lay->out_pad[l], (int)M, lay->in_pad[l],
                           lay->out_pad[l], ep, st, "matnet dgrad");
       if (rc) return rc;
       D = Dn;
     } else if (need_in) {
       EpiPlain ep{Dn, lay->in_pad[0]};
-      rc = launch_gemm_nt(D, lay->out_pad[0], packed + lay->off_wt[0], lay->out_pad[0], (int)M, lay->in_pad[0],
+      rc = launch_gemm_nt_auto(D, lay->out_pad[0], packed + lay->off_wt[0], lay->out_pad[0], (int)M, lay->in_pad[0],
                           lay->out_pad[0], ep, st, "matnet input dgrad");
       if (rc) return rc;
       int64_t thr = M * 32;

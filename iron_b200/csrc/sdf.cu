@@ -7,7 +7,7 @@
 //   backward of (y, feature, grad) w.r.t. W, b: part B (through grad, ascending l) then part A (ordinary
 //   back-propagation, descending l), with  zbarB_l = sp''(z_l) qa_{l+1} rbar_l = beta (1 - sp'(z_l)) r_l rbar_l.
 // Every product is one fp32 tile GEMM (gemm.cuh) with the elementwise work fused into its epilogue.
-#include "gemm.cuh"
+#include "gemm_tc.cuh"
 
 namespace ironb {
 namespace {
@@ -332,13 +332,13 @@ extern "C" int ironb_sdf_getall_fwd(const ironb_mlp_layout* lay, const float* pa
     ep.Epad = Epad; ep.E = E;
     ep.beta = lay->beta;
     ep.qscale = 1.f / lay->scale;
-    int rc = launch_gemm_nt(w.U[l], lay->in_pad[l], packed + lay->off_w[l], lay->in_pad[l], (int)M,
+    int rc = launch_gemm_nt_auto(w.U[l], lay->in_pad[l], packed + lay->off_w[l], lay->in_pad[l], (int)M,
                             lay->out_pad[l], lay->in_pad[l], ep, st, "sdf fwd hidden gemm");
     if (rc) return rc;
   }
   if (y != nullptr || feat != nullptr) {
     EpiFwdLast ep{packed + lay->off_b[last], y, feat, lay->d_out, 1.f / lay->scale};
-    int rc = launch_gemm_nt(w.U[last], lay->in_pad[last], packed + lay->off_w[last], lay->in_pad[last], (int)M,
+    int rc = launch_gemm_nt_auto(w.U[last], lay->in_pad[last], packed + lay->off_w[last], lay->in_pad[last], (int)M,
                             lay->out_pad[last], lay->in_pad[last], ep, st, "sdf fwd last gemm");
     if (rc) return rc;
   }
@@ -355,7 +355,7 @@ extern "C" int ironb_sdf_getall_fwd(const ironb_mlp_layout* lay, const float* pa
       ep.is_first = (l == 0);
       ep.Epad = Epad; ep.E = E;
       ep.beta = lay->beta;
-      int rc = launch_gemm_nt(w.R[l], lay->out_pad[l], packed + lay->off_wt[l], lay->out_pad[l], (int)M,
+      int rc = launch_gemm_nt_auto(w.R[l], lay->out_pad[l], packed + lay->off_wt[l], lay->out_pad[l], (int)M,
                               lay->in_pad[l], lay->out_pad[l], ep, st, "sdf grad gemm");
       if (rc) return rc;
     }
@@ -403,7 +403,7 @@ extern "C" int ironb_sdf_getall_bwd(const ironb_mlp_layout* lay, const float* pa
       ep.pre_skip = (l + 1 == lay->skip_layer);
       ep.Epad = Epad; ep.E = E;
       ep.beta = lay->beta;
-      rc = launch_gemm_nt(qb, lay->in_pad[l], packed + lay->off_w[l], lay->in_pad[l], (int)M, lay->out_pad[l],
+      rc = launch_gemm_nt_auto(qb, lay->in_pad[l], packed + lay->off_w[l], lay->in_pad[l], (int)M, lay->out_pad[l],
                           lay->in_pad[l], ep, st, "sdf bwd B gemm");
       if (rc) return rc;
       qb = w.QB[(l + 1) & 1];
@@ -444,7 +444,7 @@ extern "C" int ironb_sdf_getall_bwd(const ironb_mlp_layout* lay, const float* pa
     ep.n_true_prev = lay->out_dim[l - 1];
     ep.is_skip = (l == lay->skip_layer);
     ep.beta = lay->beta;
-    rc = launch_gemm_nt(D, lay->out_pad[l], packed + lay->off_wt[l], lay->out_pad[l], (int)M, lay->in_pad[l],
+    rc = launch_gemm_nt_auto(D, lay->out_pad[l], packed + lay->off_wt[l], lay->out_pad[l], (int)M, lay->in_pad[l],
                         lay->out_pad[l], ep, st, "sdf bwd A gemm");
     if (rc) return rc;
     D = w.D[(l - 1) & 1];

@@ -37,3 +37,15 @@ def golden():
         return cache[name]
 
     return load
+
+
+@pytest.fixture(params=["ffma", "tcgen05"])
+def gemm_mode(request):
+    """Runs a GPU test under both GEMM arithmetics of the differentiable part: fp32 FFMA tiles (tight value
+    tolerances) and the tcgen05 3xTF32 kernel (default; the tensor core accumulates with truncation, so forward
+    values carry ~1e-5 relative error -- still far inside the BASELINE tolerances, which the tests also assert)."""
+    from iron_b200 import _lib
+    lib = _lib.load()
+    prev = lib.ironb_set_gemm_mode(1 if request.param == "tcgen05" else 0)
+    yield request.param
+    lib.ironb_set_gemm_mode(prev)

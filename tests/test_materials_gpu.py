@@ -10,7 +10,7 @@ DEV = "cuda:0"
 NETS = ("diffuse_albedo_network", "specular_albedo_network", "specular_roughness_network")
 
 
-def test_materials_golden(golden):
+def test_materials_golden(golden, gemm_mode):
     import iron_b200
     g = golden("materials")
     torch.manual_seed(0)
@@ -23,7 +23,8 @@ def test_materials_golden(golden):
     leaves = [T(g[k]).to(DEV).requires_grad_(True) for k in ("points", "normals", "feats")]
     mats = iron_b200.get_materials(nets, leaves[0], leaves[1], leaves[2])
     for k in ("diffuse_albedo", "specular_albedo", "specular_roughness"):
-        assert_close(mats[k].detach().cpu().numpy(), g["out." + k], 2e-6, 2e-5, what=k)
+        vt = 1.0 if gemm_mode == "ffma" else 10.0
+        assert_close(mats[k].detach().cpu().numpy(), g["out." + k], 2e-6 * vt, 2e-5 * vt, what=k)
     loss = sum((mats[k] * T(g["up." + k]).to(DEV)).sum() for k in mats)
     loss.backward()
     for leaf, k in zip(leaves, ("g_points", "g_normals", "g_feats")):
@@ -39,7 +40,7 @@ def test_materials_golden(golden):
                 assert rel_l2(gr.numpy(), g[f"g.{nm}.{k}"]) < TOL_GRAD_REL, (nm, k)
 
 
-def test_rendering_network_modes_vs_oracle():
+def test_rendering_network_modes_vs_oracle(gemm_mode):
     """no_view_dir and idr nets on a ragged batch vs the oracle's material_forward + autograd."""
     import iron_b200
     from oracle import iron_oracle as O
@@ -64,7 +65,8 @@ def test_rendering_network_modes_vs_oracle():
         c = [t.detach().clone().to(DEV).requires_grad_(True) for t in (pts, nrm, fts)]
         out = net(c[0], c[1], -c[1] if cfg["mode"] == "idr" else None, c[2])
         (out * up.to(DEV)).sum().backward()
-        assert_close(out.detach().cpu().numpy(), ref.detach().numpy(), 2e-6, 2e-5, what=nm + " out")
+        vt = 1.0 if gemm_mode == "ffma" else 10.0
+        assert_close(out.detach().cpu().numpy(), ref.detach().numpy(), 2e-6 * vt, 2e-5 * vt, what=nm + " out")
         for a, b, k in zip(c, rg[:3], ("points", "normals", "feats")):
             assert_close(a.grad.cpu().numpy(), b.numpy(), 1e-5 * float(b.abs().max()), 1e-3, what=f"{nm} d_{k}")
         for k, r in zip(names, rg[3:]):

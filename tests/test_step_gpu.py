@@ -27,7 +27,7 @@ def build():
     return iron_b200, sdf, nets, cam512
 
 
-def test_step_golden(golden):
+def test_step_golden(golden, gemm_mode):
     g = golden("step_h256")
     ib, sdf, nets, cam512 = build()
     # the material nets were built after a color_network + under the same seed as the reference: check one pin
@@ -74,7 +74,7 @@ def test_step_golden(golden):
     print(f"step parity: same_mask={same_mask} worst relative gradient error {worst:.2e}")
 
 
-def test_render_camera_inference(golden):
+def test_render_camera_inference(golden, gemm_mode):
     """is_training=False path: detached outputs, no autograd graph, same images."""
     g = golden("step_h256")
     ib, sdf, nets, cam512 = build()
