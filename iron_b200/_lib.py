@@ -44,6 +44,7 @@ _PROTOS = {
     "ironb_version": (_INT, []),
     "ironb_launch_count": (_I64, []),
     "ironb_set_gemm_mode": (_INT, [_INT]),
+    "ironb_set_trace_mode": (_INT, [_INT]),
     "ironb_gemm_nt": (_INT, [_P, _INT, _P, _INT, _INT, _INT, _INT, _P, _INT, _INT, _P]),
     "ironb_sdf_layout": (_INT, [_INT, _INT, _INT, _INT, _INT, _INT, _F, _F, _LAY]),
     "ironb_matnet_layout": (_INT, [_INT, _INT, _INT, _INT, _LAY]),

@@ -46,6 +46,14 @@ __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b *
 
 int num_sms();
 
+// tracer implementations (trace.cu: fused persistent FFMA; trace_batched.cu: batched tcgen05)
+int trace_mode();   // 1 = batched tcgen05 (default), 0 = fused FFMA
+int64_t trace_batched_workspace_bytes(const ironb_mlp_layout* lay, int64_t N);
+int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float* ray_o, const float* ray_d,
+                  const float* min_dis, const float* max_dis, const uint8_t* work_mask, int64_t N, float thr, int iters,
+                  int n_steps, const float* linspace, uint8_t* conv, float* points, float* sdf, float* dist,
+                  int64_t* stats, void* ws, int64_t ws_bytes, cudaStream_t st);
+
 // ---- the two scalar activations of the SDF net, written exactly as torch evaluates them ----
 // nn.Softplus(beta): x*beta > 20 ? x : log1p(exp(x*beta))/beta        (models/fields.py:80)
 __device__ __forceinline__ float softplus_beta(float z, float beta) {

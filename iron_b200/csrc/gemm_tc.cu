@@ -52,6 +52,16 @@ bool tc_enabled() {
   }
   return m == 1;
 }
+static std::atomic<int> g_write_hi{-1};
+bool split_writes_hi() {
+  int m = g_write_hi.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = getenv("IRONB_SPLIT_WRITE_HI");
+    m = (e && e[0] == '0') ? 0 : 1;
+    g_write_hi.store(m, std::memory_order_relaxed);
+  }
+  return m == 1;
+}
 int set_mode(int mode) {
   int prev = tc_enabled() ? 1 : 0;
   g_mode.store(mode ? 1 : 0, std::memory_order_relaxed);
@@ -80,6 +90,7 @@ extern "C" int ironb_gemm_nt(const float* A, int lda, const float* B, int ldb, i
   IRONB_REQUIRE(A && B && C, "gemm_nt: null pointer");
   IRONB_REQUIRE((N & 3) == 0 && (K & 3) == 0 && (ldc & 3) == 0, "gemm_nt: N, K, ldc must be multiples of 4");
   EpiStore ep{C, ldc};
-  if (mode == 1) return tc::launch_gemm_nt_tc(A, lda, B, ldb, M, N, K, ep, as_stream(stream), "gemm_nt (tcgen05)");
+  if (mode == 1) return tc::launch_gemm_nt_tc(A, lda, B, ldb, M, N, K, ep, as_stream(stream), "gemm_nt (tcgen05)", 1);
+  if (mode == 2) return tc::launch_gemm_nt_tc(A, lda, B, ldb, M, N, K, ep, as_stream(stream), "gemm_nt (tcgen05, raw hi)", 0);
   return launch_gemm_nt(A, lda, B, ldb, M, N, K, ep, as_stream(stream), "gemm_nt (simt)");
 }

@@ -96,16 +96,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// hi = x with the 13 low mantissa bits cleared (exactly a tf32 value), lo = tf32_rna(x - hi) (x - hi is exact in fp32;
+// rounding its magnitude half-up to 11 significant bits is one integer add + mask).  x = hi + lo to ~2^-22 |x|, unbiased.
+__device__ __forceinline__ void split1(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xffffe000u);
+}
+// Split `per_thread` 16-byte chunks (stride nthreads) of a staged [A|B] tile pair in place (hi) and into lo.
+// write_hi == 0 leaves the raw fp32 in the hi tile and relies on kind::tf32 ignoring the 13 low mantissa bits.
+__device__ __forceinline__ void split_stage(float4* __restrict__ hi, float4* __restrict__ lo, int t, int nthreads,
+                                            int per_thread, int write_hi) {
+#pragma unroll 4
+  for (int j = 0; j < per_thread; ++j) {
+    const int c = t + j * nthreads;
+    const float4 v = hi[c];
+    float4 h, l;
+    split1(v.x, h.x, l.x); split1(v.y, h.y, l.y); split1(v.z, h.z, l.z); split1(v.w, h.w, l.w);
+    if (write_hi) hi[c] = h;
+    lo[c] = l;
+  }
 }
 
 template <class Epi>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N, int K,
-                  Epi epi) {
+                  Epi epi, const int* __restrict__ m_dev, int m_mul, int write_hi) {
+  if (m_dev != nullptr) {   // row count produced on the device (compacted ray lists): whole CTAs beyond it leave at once
+    const int md = *m_dev * m_mul;
+    if (md < M) M = md;
+  }
+  if ((int)blockIdx.y * BM >= M) return;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                       // SWIZZLE_128B tiles need 1024 B alignment
@@ -191,15 +211,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       mbar_wait(full(s), ph);
       float4* hi = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES);
       float4* lo = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES + HI_BYTES);
-#pragma unroll 4
-      for (int j = 0; j < HI_BYTES / 16 / 128; ++j) {
-        const int c = t + j * 128;
-        float4 v = hi[c];
-        float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-        float4 l = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
-        hi[c] = h;
-        lo[c] = l;
-      }
+      split_stage(hi, lo, t, 128, HI_BYTES / 16 / 128, write_hi);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       mbar_arrive(conv(s));
     }
@@ -248,16 +260,13 @@ EncodeTiledFn encode_fn();
 // rows x K fp32 matrix with row pitch ld floats -> 2-D map with a (BK x 128) SWIZZLE_128B box, zero fill out of bounds
 int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld);
 bool tc_enabled();
+bool split_writes_hi();   // 1: the splitter stores the truncated hi back (default); 0: raw fp32 stays as the hi operand
 
 template <class Epi>
-int launch_gemm_nt_tc(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const Epi& epi, cudaStream_t st,
-                      const char* what) {
+int launch_gemm_nt_tc_maps(const CUtensorMap& mA, const CUtensorMap& mB, int M, int N, int K, const Epi& epi,
+                           const int* m_dev, int m_mul, cudaStream_t st, const char* what, int write_hi = -1) {
+  if (write_hi < 0) write_hi = split_writes_hi() ? 1 : 0;
   if (M <= 0 || N <= 0) return IRONB_OK;
-  CUtensorMap mA, mB;
-  int rc = make_map(&mA, A, M, K, lda);
-  if (rc) return rc;
-  rc = make_map(&mB, B, N, K, ldb);
-  if (rc) return rc;
   auto kern = gemm_nt_tc_kernel<Epi>;
   static bool configured = false;
   if (!configured) {
@@ -266,9 +275,21 @@ int launch_gemm_nt_tc(const float* A, int lda, const float* B, int ldb, int M, i
     configured = true;
   }
   dim3 grid((unsigned)ceil_div64(N, BN), (unsigned)ceil_div64(M, BM));
-  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mB, M, N, K, epi);
+  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mB, M, N, K, epi, m_dev, m_mul, write_hi);
   IRONB_CHECK_LAUNCH(what);
   return IRONB_OK;
+}
+
+template <class Epi>
+int launch_gemm_nt_tc(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const Epi& epi, cudaStream_t st,
+                      const char* what, int write_hi = -1) {
+  if (M <= 0 || N <= 0) return IRONB_OK;
+  CUtensorMap mA, mB;
+  int rc = make_map(&mA, A, M, K, lda);
+  if (rc) return rc;
+  rc = make_map(&mB, B, N, K, ldb);
+  if (rc) return rc;
+  return launch_gemm_nt_tc_maps(mA, mB, M, N, K, epi, nullptr, 1, st, what, write_hi);
 }
 
 }  // namespace tc

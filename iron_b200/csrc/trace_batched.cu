@@ -1,0 +1,461 @@
+// Batched tensor-core tracer: RayTracer.forward (models/raytracer.py:45-220) as rounds of
+//   [ 8 hidden-layer GEMMs + 1 sdf-row GEMM on tcgen05 (gemm_tc.cuh) ]  +  [ one state-machine kernel ]
+// over device-side compacted lists of live work items, with no host round trip: every kernel of a round reads
+// its row count from device memory and whole CTAs beyond it leave at once, so the host launches the worst-case
+// schedule (sphere-tracing iters + sampler chunks + bisection bound) and the device decides what runs.
+//
+//   sphere tracing   item = ray.       Survivors of a round are re-compacted (atomic slot) and their next
+//                                      encoded point e(x) is written straight into the next round's A operand.
+//   dense sampler    item = sample.    32 consecutive samples per unfinished ray and round, in order, until the
+//                                      first negative one (the reference evaluates all 128 and takes the first
+//                                      negative: same root, fewer evaluations).  One warp per ray: ballot + ffs.
+//   bisection        item = root ray.  Exactly the reference loop: every root of the call halves while ANY root
+//                                      still works (the flag is an atomicMax'd row count), then one final eval.
+//
+// The fused persistent FFMA tracer (trace.cu) remains as the exact-fp32 implementation; this one trades
+// ~4e-6 of sdf accuracy (truncating tensor-core accumulation, see gemm_tc.cuh) for tensor-core throughput.
+#include <stdlib.h>
+
+#include <atomic>
+
+#include "gemm_tc.cuh"
+
+namespace ironb {
+
+int launch_trace_mlp_fused(const ironb_mlp_layout* lay, const float* packed, const CUtensorMap& mE, const CUtensorMap mU[2],
+                           const CUtensorMap* mW, const float* E, float* const U[2], float* Fpart, int rows_cap, int cap,
+                           const int* m_dev, int m_mul, cudaStream_t st);
+
+namespace {
+
+struct BArgs {
+  // inputs
+  const float *ray_o, *ray_d, *min_dis, *max_dis;
+  const uint8_t* work_mask;
+  const float* linspace;
+  int N, iters, n_steps, bound;
+  float thr, two_thr;
+  // network bits the elementwise kernels need
+  int multires, Epad, H;
+  float scale;
+  // outputs
+  uint8_t* conv;
+  float *points, *sdf, *dist;
+  unsigned long long* stats;
+  // workspace
+  int* c;                       // counters, see indices below
+  float* t; int* k; int* flags; float* x;            // per ray
+  int* list[2];                 // sphere-tracing item -> ray
+  int* unf_list; float *smin, *smax, *prev_f, *prev_t;   // per unfinished ray
+  int* glist[2];                // sampler group -> unfinished-ray index
+  int* root_ray; float *root_lo, *root_hi, *root_mid; int* root_work;
+  float* E; float* F;           // [CAP][Epad] encoded points, [CAP] sdf values
+  const float* Fpart;           // fused MLP: [nparts][cap] partial sums of the sdf row (nparts == 0: F holds the sdf)
+  const float* b_last;
+  int nparts, cap;
+  int cap_groups;
+};
+// counter indices
+constexpr int C_ST = 0;      // 0..2 rotating row counts (sphere tracing)
+constexpr int C_NUNF = 3, C_NROOT = 4, C_KMAX = 5;
+constexpr int C_SG = 8;      // 8..10 rotating group counts (sampler)
+constexpr int C_BR = 16;     // 16.. row count of bisection round j (0 = nobody works any more)
+constexpr int NCOUNTERS = 64;
+
+__device__ __forceinline__ void write_pe(float* __restrict__ e, const float x[3], int multires, float scale, int Epad) {
+  const float xs[3] = {x[0] * scale, x[1] * scale, x[2] * scale};
+  e[0] = xs[0]; e[1] = xs[1]; e[2] = xs[2];
+  int w = 3;
+  float f = 1.f;
+  for (int k = 0; k < multires; ++k) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s, co;
+      sincosf(xs[c] * f, &s, &co);
+      e[w + c] = s;
+      e[w + 3 + c] = co;
+    }
+    w += 6;
+    f *= 2.f;
+  }
+  for (; w < Epad; ++w) e[w] = 0.f;
+}
+
+// sdf of work item i: either the sdf-row GEMM's output, or the fused MLP's partial sums added in a fixed order
+__device__ __forceinline__ float read_f(const BArgs& A, size_t i) {
+  if (A.nparts == 0) return A.F[i];
+  float s = 0.f;
+  for (int p = 0; p < A.nparts; ++p) s += A.Fpart[(size_t)p * A.cap + i];
+  return __fdiv_rn(s + __ldg(A.b_last), A.scale);
+}
+
+__device__ __forceinline__ void ray_point(const BArgs& A, int r, float t, float x[3]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(A.ray_o[(size_t)r * 3 + c], __fmul_rn(A.ray_d[(size_t)r * 3 + c], t));
+}
+__device__ __forceinline__ void write_miss(const BArgs& A, int r) {   // raytracer.py:158-160
+  A.points[(size_t)r * 3] = 0.f; A.points[(size_t)r * 3 + 1] = 0.f; A.points[(size_t)r * 3 + 2] = 0.f;
+  A.sdf[r] = 0.f; A.dist[r] = 0.f; A.conv[r] = 0;
+}
+
+// ---------------------------------------------------------------- sphere tracing (:105-140)
+__global__ void __launch_bounds__(256) st_init_kernel(BArgs A) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { A.c[C_ST] = A.N; A.c[C_ST + 1] = 0; A.c[C_ST + 2] = 0; }
+  if (i >= A.N) return;
+  float t = A.min_dis[i], x[3];
+  ray_point(A, i, t, x);                                           // :109
+  A.t[i] = t; A.k[i] = 0; A.flags[i] = A.work_mask[i] ? 3 : 0;
+  A.x[(size_t)i * 3] = x[0]; A.x[(size_t)i * 3 + 1] = x[1]; A.x[(size_t)i * 3 + 2] = x[2];
+  A.list[0][i] = i;
+  write_pe(A.E + (size_t)i * A.Epad, x, A.multires, A.scale, A.Epad);
+}
+
+__global__ void __launch_bounds__(256) st_update_kernel(BArgs A, int round) {
+  const int cur = C_ST + round % 3, nxt = C_ST + (round + 1) % 3, clr = C_ST + (round + 2) % 3;
+  const int rows = A.c[cur];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    A.c[clr] = 0;
+    if (A.stats && rows > 0) { atomicAdd(A.stats + 0, (unsigned long long)rows); atomicAdd(A.stats + 6, (unsigned long long)((rows + 127) / 128)); }
+  }
+  if (i >= rows) return;
+  const int r = A.list[round & 1][i];
+  const float f = read_f(A, i);
+  float t = A.t[r];
+  const float tmax = A.max_dis[r];
+  const int fl = A.flags[r];
+  const bool work = fl & 1;
+  bool unf = (fl & 2) != 0;
+  unf = unf && (fabsf(f) > A.thr) && (t < tmax);                   // :113-116
+  float x[3] = {A.x[(size_t)r * 3], A.x[(size_t)r * 3 + 1], A.x[(size_t)r * 3 + 2]};
+  const int k = A.k[r];
+  if (k == A.iters || !unf) {                                      // :117-119
+    const bool conv = work && !unf && (fabsf(f) <= A.thr) && (t < tmax);   // :133-138
+    A.points[(size_t)r * 3] = x[0]; A.points[(size_t)r * 3 + 1] = x[1]; A.points[(size_t)r * 3 + 2] = x[2];
+    A.sdf[r] = f; A.dist[r] = t; A.conv[r] = conv ? 1 : 0;
+    if (unf) A.unf_list[atomicAdd(A.c + C_NUNF, 1)] = r;          // -> dense sampler (:55-67)
+  } else {
+    t = __fadd_rn(t, f);                                           // :123-125
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(x[c], __fmul_rn(A.ray_d[(size_t)r * 3 + c], f));
+    A.t[r] = t; A.k[r] = k + 1; A.flags[r] = (work ? 1 : 0) | 2;
+    A.x[(size_t)r * 3] = x[0]; A.x[(size_t)r * 3 + 1] = x[1]; A.x[(size_t)r * 3 + 2] = x[2];
+    const int slot = atomicAdd(A.c + nxt, 1);
+    A.list[(round + 1) & 1][slot] = r;
+    write_pe(A.E + (size_t)slot * A.Epad, x, A.multires, A.scale, A.Epad);
+  }
+}
+
+// ---------------------------------------------------------------- dense sampler (:142-197), one warp per ray
+__device__ __forceinline__ float sample_t(const BArgs& A, float smin, float smax, int j) {
+  const int jc = min(j, A.n_steps - 1);
+  return __fadd_rn(smin, __fmul_rn(__ldg(A.linspace + jc), __fsub_rn(smax, smin)));   // :144-147
+}
+
+__global__ void __launch_bounds__(256) smp_prepare_kernel(BArgs A, int pass) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int n_unf = A.c[C_NUNF];
+  const int first = pass * A.cap_groups;
+  const int groups = max(0, min(A.cap_groups, n_unf - first));
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    A.c[C_SG] = groups; A.c[C_SG + 1] = 0; A.c[C_SG + 2] = 0;
+    if (A.stats && pass == 0) atomicAdd(A.stats + 3, (unsigned long long)n_unf);
+  }
+  if (g >= groups) return;
+  const int u = first + g;
+  const int r = A.unf_list[u];
+  const float t = A.dist[r], f = A.sdf[r];
+  const bool outside = f > 0.f;                                    // :59-65
+  const float smin = outside ? t : A.min_dis[r];
+  const float smax = outside ? A.max_dis[r] : t;
+  if (lane == 0) { A.smin[u] = smin; A.smax[u] = smax; A.prev_f[u] = 0.f; A.prev_t[u] = 0.f; A.glist[0][g] = u; }
+  float x[3];
+  ray_point(A, r, sample_t(A, smin, smax, lane), x);
+  write_pe(A.E + ((size_t)g * 32 + lane) * A.Epad, x, A.multires, A.scale, A.Epad);
+}
+
+__global__ void __launch_bounds__(256) smp_update_kernel(BArgs A, int chunk) {
+  const int cur = C_SG + chunk % 3, nxt = C_SG + (chunk + 1) % 3, clr = C_SG + (chunk + 2) % 3;
+  const int groups = A.c[cur];
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    A.c[clr] = 0;
+    if (A.stats && groups > 0) { atomicAdd(A.stats + 1, (unsigned long long)groups * 32ull); atomicAdd(A.stats + 6, (unsigned long long)((groups * 32 + 127) / 128)); }
+  }
+  if (g >= groups) return;
+  const int u = A.glist[chunk & 1][g];
+  const int r = A.unf_list[u];
+  const float smin = A.smin[u], smax = A.smax[u];
+  const int j = chunk * 32 + lane;
+  const float val = read_f(A, (size_t)g * 32 + lane);
+  const float ts = sample_t(A, smin, smax, j);
+  const bool neg = (j < A.n_steps) && (val < 0.f);                 // first negative sample (:162-166)
+  const unsigned m = __ballot_sync(0xffffffffu, neg);
+  float pv = __shfl_up_sync(0xffffffffu, val, 1), pt = __shfl_up_sync(0xffffffffu, ts, 1);
+  if (lane == 0) { pv = A.prev_f[u]; pt = A.prev_t[u]; }
+  const bool last_chunk = (chunk + 1) * 32 >= A.n_steps;
+  if (m != 0u) {
+    const int jj = __ffs(m) - 1;
+    if (lane == jj) {
+      if (j >= 1) {                                                // :167
+        const int idx = atomicAdd(A.c + C_NROOT, 1);
+        A.root_ray[idx] = r; A.root_lo[idx] = pt; A.root_hi[idx] = ts;
+        A.root_work[idx] = ((pv > 0.f) && (val < 0.f)) ? 1 : 0;   // rootfind work mask (:201)
+      } else {
+        write_miss(A, r);
+      }
+    }
+  } else if (last_chunk) {
+    if (lane == 0) write_miss(A, r);
+  } else {
+    int slot = 0;
+    if (lane == 0) slot = atomicAdd(A.c + nxt, 1);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (lane == 31) { A.prev_f[u] = val; A.prev_t[u] = ts; }
+    if (lane == 0) A.glist[(chunk + 1) & 1][slot] = u;
+    float x[3];
+    ray_point(A, r, sample_t(A, smin, smax, j + 32), x);
+    write_pe(A.E + ((size_t)slot * 32 + lane) * A.Epad, x, A.multires, A.scale, A.Epad);
+  }
+}
+
+// ---------------------------------------------------------------- bisection (:199-220)
+__global__ void __launch_bounds__(256) bis_prepare_kernel(BArgs A) {
+  const int n_root = A.c[C_NROOT];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && A.stats) atomicAdd(A.stats + 4, (unsigned long long)n_root);
+  if (i >= n_root) return;
+  const float mid = __fmul_rn(__fadd_rn(A.root_lo[i], A.root_hi[i]), 0.5f);   // :203
+  A.root_mid[i] = mid;
+  if (A.root_work[i]) atomicMax(A.c + C_BR, n_root);                // while work.any()  (:204)
+  float x[3];
+  ray_point(A, A.root_ray[i], mid, x);                              // :205
+  write_pe(A.E + (size_t)i * A.Epad, x, A.multires, A.scale, A.Epad);
+}
+
+__global__ void __launch_bounds__(256) bis_update_kernel(BArgs A, int round) {
+  const int rows = A.c[C_BR + round];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && rows > 0) {
+    A.c[C_KMAX] = round + 1;
+    if (A.stats) { atomicAdd(A.stats + 2, (unsigned long long)rows); atomicAdd(A.stats + 6, (unsigned long long)((rows + 127) / 128)); }
+  }
+  if (i >= rows) return;
+  const float f = read_f(A, i);
+  float lo = A.root_lo[i], hi = A.root_hi[i], mid = A.root_mid[i];
+  if (f > 0.f) lo = mid; else hi = mid;                             // every ray of the call (:207-212)
+  mid = __fmul_rn(__fadd_rn(lo, hi), 0.5f);                         // :213
+  A.root_lo[i] = lo; A.root_hi[i] = hi; A.root_mid[i] = mid;
+  const bool work = A.root_work[i] && (__fsub_rn(hi, lo) > A.two_thr);   // :214
+  A.root_work[i] = work ? 1 : 0;
+  if (work) atomicMax(A.c + C_BR + round + 1, rows);
+  float x[3];
+  ray_point(A, A.root_ray[i], mid, x);
+  write_pe(A.E + (size_t)i * A.Epad, x, A.multires, A.scale, A.Epad);
+}
+
+__global__ void __launch_bounds__(256) bis_final_kernel(BArgs A) {
+  const int n_root = A.c[C_NROOT];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && A.stats) {
+    atomicMax(A.stats + 5, (unsigned long long)A.c[C_KMAX]);
+    if (n_root > 0) { atomicAdd(A.stats + 2, (unsigned long long)n_root); atomicAdd(A.stats + 6, (unsigned long long)((n_root + 127) / 128)); }
+  }
+  if (i >= n_root) return;
+  const int r = A.root_ray[i];
+  const float mid = A.root_mid[i];
+  float x[3];
+  ray_point(A, r, mid, x);                                          // :216-219
+  A.points[(size_t)r * 3] = x[0]; A.points[(size_t)r * 3 + 1] = x[1]; A.points[(size_t)r * 3 + 2] = x[2];
+  A.sdf[r] = read_f(A, i); A.dist[r] = mid; A.conv[r] = 1;               // :75
+}
+
+// ---------------------------------------------------------------- MLP epilogues
+struct EpiTraceHidden {
+  const float* bias;
+  float* Unext;
+  const float* e;
+  int ld, n_true, pre_skip, Epad, E;
+  float beta;
+  __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[4]) const {
+    float u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + j;
+      if (n < n_true) {
+        float a = softplus_beta(acc[j] + __ldg(bias + n), beta);
+        u[j] = pre_skip ? __fdiv_rn(a, IRONB_SQRT2F) : a;
+      } else {
+        const int c = n - n_true;
+        u[j] = (pre_skip && c < E) ? __fdiv_rn(e[(size_t)m * Epad + c], IRONB_SQRT2F) : 0.f;
+      }
+    }
+    *reinterpret_cast<float4*>(Unext + (size_t)m * ld + n0) = make_float4(u[0], u[1], u[2], u[3]);
+  }
+};
+struct EpiTraceLast {
+  const float* b_last;
+  float* F;
+  float scale;
+  __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[4]) const {
+    if (n0 == 0) F[m] = __fdiv_rn(acc[0] + __ldg(b_last), scale);
+  }
+};
+
+struct BWs {
+  int* c; float* t; int* k; int* flags; float* x; int* list[2]; int* unf_list; float *smin, *smax, *prev_f, *prev_t;
+  int* glist[2]; int* root_ray; float *root_lo, *root_hi, *root_mid; int* root_work; float *E, *F, *U[2], *Fpart;
+  int64_t cap; int64_t bytes;
+};
+
+BWs carve_b(const ironb_mlp_layout* lay, int64_t N, unsigned char* base) {
+  BWs w;
+  memset(&w, 0, sizeof(w));
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) { unsigned char* p = base ? base + off : nullptr; off += (bytes + 255) / 256 * 256; return p; };
+  int64_t cap = 16 * N;                     // sampler items per pass: 50 % unfinished rays fit in one pass
+  if (cap < 4096) cap = 4096;
+  if (cap > (1 << 21)) cap = (1 << 21);
+  if (cap < N) cap = N;
+  cap = (cap + 127) / 128 * 128;
+  w.cap = cap;
+  const int H = lay->d_hidden, Epad = lay->in_pad[0];
+  w.c = (int*)take(NCOUNTERS * 4);
+  w.t = (float*)take(N * 4); w.k = (int*)take(N * 4); w.flags = (int*)take(N * 4); w.x = (float*)take(N * 12);
+  w.list[0] = (int*)take(N * 4); w.list[1] = (int*)take(N * 4);
+  w.unf_list = (int*)take(N * 4);
+  w.smin = (float*)take(N * 4); w.smax = (float*)take(N * 4); w.prev_f = (float*)take(N * 4); w.prev_t = (float*)take(N * 4);
+  w.glist[0] = (int*)take(cap / 32 * 4); w.glist[1] = (int*)take(cap / 32 * 4);
+  w.root_ray = (int*)take(N * 4); w.root_lo = (float*)take(N * 4); w.root_hi = (float*)take(N * 4);
+  w.root_mid = (float*)take(N * 4); w.root_work = (int*)take(N * 4);
+  w.E = (float*)take(cap * Epad * 4);
+  w.F = (float*)take(cap * 4);
+  w.Fpart = (float*)take(cap * 4 * 8);
+  w.U[0] = (float*)take(cap * (int64_t)H * 4);
+  w.U[1] = (float*)take(cap * (int64_t)H * 4);
+  w.bytes = off;
+  return w;
+}
+
+static std::atomic<int> g_trace_mode{-1};
+
+}  // namespace
+
+int trace_mode() {
+  int m = g_trace_mode.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = getenv("IRONB_TRACE");
+    m = (e && (e[0] == 'f' || e[0] == 'F' || e[0] == '0')) ? 0 : 1;   // IRONB_TRACE=fused selects the FFMA tracer
+    g_trace_mode.store(m, std::memory_order_relaxed);
+  }
+  return m;
+}
+int set_trace_mode(int mode) {
+  int prev = trace_mode();
+  g_trace_mode.store(mode ? 1 : 0, std::memory_order_relaxed);
+  return prev;
+}
+
+int64_t trace_batched_workspace_bytes(const ironb_mlp_layout* lay, int64_t N) { return carve_b(lay, N, nullptr).bytes; }
+
+int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float* ray_o, const float* ray_d,
+                  const float* min_dis, const float* max_dis, const uint8_t* work_mask, int64_t N, float thr, int iters,
+                  int n_steps, const float* linspace, uint8_t* conv, float* points, float* sdf, float* dist,
+                  int64_t* stats, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  const int H = lay->d_hidden, Epad = lay->in_pad[0], last = lay->n_lin - 1;
+  for (int l = 0; l < last; ++l)
+    if (lay->out_pad[l] != H || (l > 0 && lay->in_pad[l] != H)) { set_error("trace: layer %d is not %d wide", l, H); return IRONB_ENOSUP; }
+  BWs w = carve_b(lay, N, reinterpret_cast<unsigned char*>(ws));
+  if (ws_bytes < w.bytes) { set_error("trace: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)w.bytes); return IRONB_EINVAL; }
+  IRONB_CUDA(cudaMemsetAsync(w.c, 0, NCOUNTERS * 4, st));
+
+  BArgs A;
+  memset(&A, 0, sizeof(A));
+  A.ray_o = ray_o; A.ray_d = ray_d; A.min_dis = min_dis; A.max_dis = max_dis; A.work_mask = work_mask; A.linspace = linspace;
+  A.N = (int)N; A.iters = iters; A.n_steps = n_steps;
+  A.thr = thr; A.two_thr = 2.0f * thr;
+  // halvings until an interval of at most 2r/(n_steps-1) (r = 1) is <= 2*thr, plus slack; the loop is data driven below it
+  int bound = 1;
+  for (double len = 2.0 / (n_steps - 1); len > 2.0 * thr && bound < 40; len *= 0.5) ++bound;
+  bound += 2;
+  if (bound > NCOUNTERS - C_BR - 2) bound = NCOUNTERS - C_BR - 2;
+  A.bound = bound;
+  A.multires = lay->multires; A.Epad = Epad; A.H = H; A.scale = lay->scale;
+  A.conv = conv; A.points = points; A.sdf = sdf; A.dist = dist;
+  A.stats = reinterpret_cast<unsigned long long*>(stats);
+  A.c = w.c; A.t = w.t; A.k = w.k; A.flags = w.flags; A.x = w.x; A.list[0] = w.list[0]; A.list[1] = w.list[1];
+  A.unf_list = w.unf_list; A.smin = w.smin; A.smax = w.smax; A.prev_f = w.prev_f; A.prev_t = w.prev_t;
+  A.glist[0] = w.glist[0]; A.glist[1] = w.glist[1];
+  A.root_ray = w.root_ray; A.root_lo = w.root_lo; A.root_hi = w.root_hi; A.root_mid = w.root_mid; A.root_work = w.root_work;
+  A.E = w.E; A.F = w.F;
+  A.cap_groups = (int)(w.cap / 32);
+  const int C = H / 128;
+  const bool fused = (H % 128 == 0) && (C == 1 || C == 2 || C == 4) && getenv("IRONB_TRACE_PER_LAYER") == nullptr;
+  A.Fpart = w.Fpart; A.b_last = packed + lay->off_b[last]; A.nparts = fused ? 2 * C : 0; A.cap = (int)w.cap;
+
+  // tensor maps: operands are fixed for the whole call
+  CUtensorMap mE, mU[2], mW[IRONB_MAX_LIN];
+  int rc;
+  if ((rc = tc::make_map(&mE, w.E, (int)w.cap, Epad, Epad))) return rc;
+  for (int i = 0; i < 2; ++i)
+    if ((rc = tc::make_map(&mU[i], w.U[i], (int)w.cap, H, H))) return rc;
+  for (int l = 0; l < last; ++l)
+    if ((rc = tc::make_map(&mW[l], packed + lay->off_w[l], lay->out_pad[l], lay->in_pad[l], lay->in_pad[l]))) return rc;
+  if ((rc = tc::make_map(&mW[last], packed + lay->off_w[last], 8, lay->in_pad[last], lay->in_pad[last]))) return rc;
+
+  // one MLP evaluation of the first `rows_cap` rows (device count *m_dev x m_mul): E -> U0 -> U1 -> ... -> F
+  auto mlp = [&](int rows_cap, const int* m_dev, int m_mul) -> int {
+    if (fused)   // all hidden layers + the sdf row in one cluster launch (mlp_tc.cu)
+      return launch_trace_mlp_fused(lay, packed, mE, mU, mW, w.E, w.U, w.Fpart, rows_cap, (int)w.cap, m_dev, m_mul, st);
+    for (int l = 0; l < last; ++l) {
+      EpiTraceHidden ep{packed + lay->off_b[l], w.U[l & 1], w.E, H, lay->out_dim[l], (l + 1 == lay->skip_layer) ? 1 : 0,
+                        Epad, lay->pe_dim, lay->beta};
+      const CUtensorMap& a = (l == 0) ? mE : mU[(l - 1) & 1];
+      int r2 = tc::launch_gemm_nt_tc_maps(a, mW[l], rows_cap, H, lay->in_pad[l], ep, m_dev, m_mul, st, "trace mlp layer");
+      if (r2) return r2;
+    }
+    EpiTraceLast ep{packed + lay->off_b[last], w.F, lay->scale};
+    return tc::launch_gemm_nt_tc_maps(mU[(last - 1) & 1], mW[last], rows_cap, 8, lay->in_pad[last], ep, m_dev, m_mul, st,
+                                      "trace mlp sdf row");
+  };
+  const int nb = (int)ceil_div64(N, 256);
+
+  // ---- sphere tracing: iters + 1 evaluations
+  st_init_kernel<<<nb, 256, 0, st>>>(A);
+  IRONB_CHECK_LAUNCH("st_init_kernel");
+  for (int r = 0; r <= iters; ++r) {
+    if ((rc = mlp((int)N, w.c + C_ST + r % 3, 1))) return rc;
+    st_update_kernel<<<nb, 256, 0, st>>>(A, r);
+    IRONB_CHECK_LAUNCH("st_update_kernel");
+  }
+  // ---- dense sampler: passes of cap/32 rays, chunks of 32 samples
+  const int chunks = (n_steps + 31) / 32;
+  const int64_t passes = ceil_div64(N * 32, w.cap);
+  const int gb = (int)ceil_div64(w.cap / 32 * 32, 256);
+  for (int64_t p = 0; p < passes; ++p) {
+    smp_prepare_kernel<<<gb, 256, 0, st>>>(A, (int)p);
+    IRONB_CHECK_LAUNCH("smp_prepare_kernel");
+    for (int ch = 0; ch < chunks; ++ch) {
+      if ((rc = mlp((int)w.cap, w.c + C_SG + ch % 3, 32))) return rc;
+      smp_update_kernel<<<gb, 256, 0, st>>>(A, ch);
+      IRONB_CHECK_LAUNCH("smp_update_kernel");
+    }
+  }
+  // ---- bisection: the reference loop, then the final evaluation
+  bis_prepare_kernel<<<nb, 256, 0, st>>>(A);
+  IRONB_CHECK_LAUNCH("bis_prepare_kernel");
+  for (int j = 0; j < bound; ++j) {
+    if ((rc = mlp((int)N, w.c + C_BR + j, 1))) return rc;
+    bis_update_kernel<<<nb, 256, 0, st>>>(A, j);
+    IRONB_CHECK_LAUNCH("bis_update_kernel");
+  }
+  if ((rc = mlp((int)N, w.c + C_NROOT, 1))) return rc;
+  bis_final_kernel<<<nb, 256, 0, st>>>(A);
+  IRONB_CHECK_LAUNCH("bis_final_kernel");
+  return IRONB_OK;
+}
+
+}  // namespace ironb
+
+extern "C" int ironb_set_trace_mode(int mode) { return ironb::set_trace_mode(mode); }

@@ -49,3 +49,13 @@ def gemm_mode(request):
     prev = lib.ironb_set_gemm_mode(1 if request.param == "tcgen05" else 0)
     yield request.param
     lib.ironb_set_gemm_mode(prev)
+
+
+@pytest.fixture(params=["fused-ffma", "batched-tcgen05"])
+def trace_mode(request):
+    """Both tracer implementations: the fused persistent fp32-FFMA kernels and the batched tcgen05 rounds (default)."""
+    from iron_b200 import _lib
+    lib = _lib.load()
+    prev = lib.ironb_set_trace_mode(1 if request.param == "batched-tcgen05" else 0)
+    yield request.param
+    lib.ironb_set_trace_mode(prev)

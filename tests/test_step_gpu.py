@@ -27,7 +27,7 @@ def build():
     return iron_b200, sdf, nets, cam512
 
 
-def test_step_golden(golden, gemm_mode):
+def test_step_golden(golden, gemm_mode, trace_mode):
     g = golden("step_h256")
     ib, sdf, nets, cam512 = build()
     # the material nets were built after a color_network + under the same seed as the reference: check one pin

@@ -58,7 +58,7 @@ def compare(res, g, tag, pooled):
         assert_close(a, g[f"{tag}.depth"].reshape(-1)[both], TOL_DEPTH, what=f"{tag}.depth", frac=0.999)
 
 
-def test_trace_golden(golden, net256):
+def test_trace_golden(golden, net256, trace_mode):
     import iron_b200
     g = golden("trace_h256")
     rt = iron_b200.RayTracer()
@@ -88,7 +88,7 @@ def test_trace_golden(golden, net256):
     assert agree >= 0.9999, f"pooled hit-mask agreement {100 * agree:.4f}% over {pooled['n']} rays (need 99.99%)"
 
 
-def test_trace_inputs_not_mutated_and_stats(golden, net256):
+def test_trace_inputs_not_mutated_and_stats(golden, net256, trace_mode):
     import iron_b200
     g = golden("trace_h256")
     rt = iron_b200.RayTracer()
@@ -114,7 +114,7 @@ def test_trace_inputs_not_mutated_and_stats(golden, net256):
     assert res["points"].shape == (n, 3) and res["convergent_mask"].dtype == torch.bool
 
 
-def test_trace_empty_and_all_masked(net256):
+def test_trace_empty_and_all_masked(net256, trace_mode):
     import iron_b200
     rt = iron_b200.RayTracer()
     z = torch.zeros(0, 3, device=DEV)
@@ -129,7 +129,7 @@ def test_trace_empty_and_all_masked(net256):
     assert_close(res["distance"].cpu().numpy(), t0.cpu().numpy(), 0.0, what="masked distance")
 
 
-def test_trace_h512_vs_oracle():
+def test_trace_h512_vs_oracle(trace_mode):
     """H=512 (the BASELINE width), 48x48 silhouette crop, against the oracle run on the same weights."""
     import iron_b200
     torch.manual_seed(0)
