@@ -48,6 +48,7 @@ int num_sms();
 
 // tracer implementations (trace.cu: fused persistent FFMA; trace_batched.cu: batched tcgen05)
 int trace_mode();   // 1 = batched tcgen05 (default), 0 = fused FFMA
+bool trace_mlp_fused_supported(const ironb_mlp_layout* lay);   // shapes the tcgen05 tracer handles (else: FFMA tracer)
 int64_t trace_batched_workspace_bytes(const ironb_mlp_layout* lay, int64_t N);
 int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float* ray_o, const float* ray_d,
                   const float* min_dis, const float* max_dis, const uint8_t* work_mask, int64_t N, float thr, int iters,

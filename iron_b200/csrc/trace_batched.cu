@@ -22,9 +22,11 @@
 
 namespace ironb {
 
-int launch_trace_mlp_fused(const ironb_mlp_layout* lay, const float* packed, const CUtensorMap& mE, const CUtensorMap mU[2],
-                           const CUtensorMap* mW, const float* E, float* const U[2], float* Fpart, int rows_cap, int cap,
-                           const int* m_dev, int m_mul, cudaStream_t st);
+bool trace_mlp_fused_supported(const ironb_mlp_layout* lay);
+int split_weights(const float* src, int64_t n, float* hi, float* lo, cudaStream_t st);
+int launch_trace_mlp_fused(const ironb_mlp_layout* lay, const float* packed, const CUtensorMap* mE, const CUtensorMap* mU,
+                           const CUtensorMap* mW, const float* Ehi, const float* Elo, float* const* Uhi, float* const* Ulo,
+                           float* Fpart, int rows_cap, int cap, const int* m_dev, int m_mul, cudaStream_t st);
 
 namespace {
 
@@ -49,8 +51,8 @@ struct BArgs {
   int* unf_list; float *smin, *smax, *prev_f, *prev_t;   // per unfinished ray
   int* glist[2];                // sampler group -> unfinished-ray index
   int* root_ray; float *root_lo, *root_hi, *root_mid; int* root_work;
-  float* E; float* F;           // [CAP][Epad] encoded points, [CAP] sdf values
-  const float* Fpart;           // fused MLP: [nparts][cap] partial sums of the sdf row (nparts == 0: F holds the sdf)
+  float* Ehi; float* Elo;       // [CAP][Epad] encoded points, already split into tf32-exact hi / lo (the MLP's A operand)
+  const float* Fpart;           // [nparts][cap] partial sums of the sdf row, written by the fused MLP kernel
   const float* b_last;
   int nparts, cap;
   int cap_groups;
@@ -62,31 +64,42 @@ constexpr int C_SG = 8;      // 8..10 rotating group counts (sampler)
 constexpr int C_BR = 16;     // 16.. row count of bisection round j (0 = nobody works any more)
 constexpr int NCOUNTERS = 64;
 
-__device__ __forceinline__ void write_pe(float* __restrict__ e, const float x[3], int multires, float scale, int Epad) {
-  const float xs[3] = {x[0] * scale, x[1] * scale, x[2] * scale};
-  e[0] = xs[0]; e[1] = xs[1]; e[2] = xs[2];
+__device__ __forceinline__ void put_split(float* __restrict__ ehi, float* __restrict__ elo, int i, float v) {
+  float h, l;
+  tc::split1(v, h, l);
+  ehi[i] = h;
+  elo[i] = l;
+}
+struct BArgs;
+__device__ __forceinline__ void write_pe(const BArgs& A, size_t row, const float x[3]);
+
+// sdf of work item i: either the sdf-row GEMM's output, or the fused MLP's partial sums added in a fixed order
+__device__ __forceinline__ float read_f(const BArgs& A, size_t i) {
+  float s = 0.f;
+  for (int p = 0; p < A.nparts; ++p) s += A.Fpart[(size_t)p * A.cap + i];
+  return __fdiv_rn(s + __ldg(A.b_last), A.scale);
+}
+
+// encoded point of work item `row`, written as the split A operand of the MLP's first layer
+__device__ __forceinline__ void write_pe(const BArgs& A, size_t row, const float x[3]) {
+  float* __restrict__ ehi = A.Ehi + row * A.Epad;
+  float* __restrict__ elo = A.Elo + row * A.Epad;
+  const float xs[3] = {x[0] * A.scale, x[1] * A.scale, x[2] * A.scale};
+  put_split(ehi, elo, 0, xs[0]); put_split(ehi, elo, 1, xs[1]); put_split(ehi, elo, 2, xs[2]);
   int w = 3;
   float f = 1.f;
-  for (int k = 0; k < multires; ++k) {
+  for (int k = 0; k < A.multires; ++k) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float s, co;
-      sincosf(xs[c] * f, &s, &co);
-      e[w + c] = s;
-      e[w + 3 + c] = co;
+      float sn, co;
+      sincosf(xs[c] * f, &sn, &co);
+      put_split(ehi, elo, w + c, sn);
+      put_split(ehi, elo, w + 3 + c, co);
     }
     w += 6;
     f *= 2.f;
   }
-  for (; w < Epad; ++w) e[w] = 0.f;
-}
-
-// sdf of work item i: either the sdf-row GEMM's output, or the fused MLP's partial sums added in a fixed order
-__device__ __forceinline__ float read_f(const BArgs& A, size_t i) {
-  if (A.nparts == 0) return A.F[i];
-  float s = 0.f;
-  for (int p = 0; p < A.nparts; ++p) s += A.Fpart[(size_t)p * A.cap + i];
-  return __fdiv_rn(s + __ldg(A.b_last), A.scale);
+  for (; w < A.Epad; ++w) { ehi[w] = 0.f; elo[w] = 0.f; }
 }
 
 __device__ __forceinline__ void ray_point(const BArgs& A, int r, float t, float x[3]) {
@@ -108,7 +121,7 @@ __global__ void __launch_bounds__(256) st_init_kernel(BArgs A) {
   A.t[i] = t; A.k[i] = 0; A.flags[i] = A.work_mask[i] ? 3 : 0;
   A.x[(size_t)i * 3] = x[0]; A.x[(size_t)i * 3 + 1] = x[1]; A.x[(size_t)i * 3 + 2] = x[2];
   A.list[0][i] = i;
-  write_pe(A.E + (size_t)i * A.Epad, x, A.multires, A.scale, A.Epad);
+  write_pe(A, (size_t)i, x);
 }
 
 __global__ void __launch_bounds__(256) st_update_kernel(BArgs A, int round) {
@@ -143,7 +156,7 @@ __global__ void __launch_bounds__(256) st_update_kernel(BArgs A, int round) {
     A.x[(size_t)r * 3] = x[0]; A.x[(size_t)r * 3 + 1] = x[1]; A.x[(size_t)r * 3 + 2] = x[2];
     const int slot = atomicAdd(A.c + nxt, 1);
     A.list[(round + 1) & 1][slot] = r;
-    write_pe(A.E + (size_t)slot * A.Epad, x, A.multires, A.scale, A.Epad);
+    write_pe(A, (size_t)slot, x);
   }
 }
 
@@ -172,7 +185,7 @@ __global__ void __launch_bounds__(256) smp_prepare_kernel(BArgs A, int pass) {
   if (lane == 0) { A.smin[u] = smin; A.smax[u] = smax; A.prev_f[u] = 0.f; A.prev_t[u] = 0.f; A.glist[0][g] = u; }
   float x[3];
   ray_point(A, r, sample_t(A, smin, smax, lane), x);
-  write_pe(A.E + ((size_t)g * 32 + lane) * A.Epad, x, A.multires, A.scale, A.Epad);
+  write_pe(A, (size_t)g * 32 + lane, x);
 }
 
 __global__ void __launch_bounds__(256) smp_update_kernel(BArgs A, int chunk) {
@@ -216,7 +229,7 @@ __global__ void __launch_bounds__(256) smp_update_kernel(BArgs A, int chunk) {
     if (lane == 0) A.glist[(chunk + 1) & 1][slot] = u;
     float x[3];
     ray_point(A, r, sample_t(A, smin, smax, j + 32), x);
-    write_pe(A.E + ((size_t)slot * 32 + lane) * A.Epad, x, A.multires, A.scale, A.Epad);
+    write_pe(A, (size_t)slot * 32 + lane, x);
   }
 }
 
@@ -231,7 +244,7 @@ __global__ void __launch_bounds__(256) bis_prepare_kernel(BArgs A) {
   if (A.root_work[i]) atomicMax(A.c + C_BR, n_root);                // while work.any()  (:204)
   float x[3];
   ray_point(A, A.root_ray[i], mid, x);                              // :205
-  write_pe(A.E + (size_t)i * A.Epad, x, A.multires, A.scale, A.Epad);
+  write_pe(A, (size_t)i, x);
 }
 
 __global__ void __launch_bounds__(256) bis_update_kernel(BArgs A, int round) {
@@ -252,7 +265,7 @@ __global__ void __launch_bounds__(256) bis_update_kernel(BArgs A, int round) {
   if (work) atomicMax(A.c + C_BR + round + 1, rows);
   float x[3];
   ray_point(A, A.root_ray[i], mid, x);
-  write_pe(A.E + (size_t)i * A.Epad, x, A.multires, A.scale, A.Epad);
+  write_pe(A, (size_t)i, x);
 }
 
 __global__ void __launch_bounds__(256) bis_final_kernel(BArgs A) {
@@ -271,41 +284,10 @@ __global__ void __launch_bounds__(256) bis_final_kernel(BArgs A) {
   A.sdf[r] = read_f(A, i); A.dist[r] = mid; A.conv[r] = 1;               // :75
 }
 
-// ---------------------------------------------------------------- MLP epilogues
-struct EpiTraceHidden {
-  const float* bias;
-  float* Unext;
-  const float* e;
-  int ld, n_true, pre_skip, Epad, E;
-  float beta;
-  __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[4]) const {
-    float u[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + j;
-      if (n < n_true) {
-        float a = softplus_beta(acc[j] + __ldg(bias + n), beta);
-        u[j] = pre_skip ? __fdiv_rn(a, IRONB_SQRT2F) : a;
-      } else {
-        const int c = n - n_true;
-        u[j] = (pre_skip && c < E) ? __fdiv_rn(e[(size_t)m * Epad + c], IRONB_SQRT2F) : 0.f;
-      }
-    }
-    *reinterpret_cast<float4*>(Unext + (size_t)m * ld + n0) = make_float4(u[0], u[1], u[2], u[3]);
-  }
-};
-struct EpiTraceLast {
-  const float* b_last;
-  float* F;
-  float scale;
-  __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[4]) const {
-    if (n0 == 0) F[m] = __fdiv_rn(acc[0] + __ldg(b_last), scale);
-  }
-};
-
 struct BWs {
   int* c; float* t; int* k; int* flags; float* x; int* list[2]; int* unf_list; float *smin, *smax, *prev_f, *prev_t;
-  int* glist[2]; int* root_ray; float *root_lo, *root_hi, *root_mid; int* root_work; float *E, *F, *U[2], *Fpart;
+  int* glist[2]; int* root_ray; float *root_lo, *root_hi, *root_mid; int* root_work;
+  float *Ehi, *Elo, *Uhi[2], *Ulo[2], *Fpart, *Whi[IRONB_MAX_LIN], *Wlo[IRONB_MAX_LIN];
   int64_t cap; int64_t bytes;
 };
 
@@ -320,7 +302,7 @@ BWs carve_b(const ironb_mlp_layout* lay, int64_t N, unsigned char* base) {
   if (cap < N) cap = N;
   cap = (cap + 127) / 128 * 128;
   w.cap = cap;
-  const int H = lay->d_hidden, Epad = lay->in_pad[0];
+  const int H = lay->d_hidden, Epad = lay->in_pad[0], last = lay->n_lin - 1;
   w.c = (int*)take(NCOUNTERS * 4);
   w.t = (float*)take(N * 4); w.k = (int*)take(N * 4); w.flags = (int*)take(N * 4); w.x = (float*)take(N * 12);
   w.list[0] = (int*)take(N * 4); w.list[1] = (int*)take(N * 4);
@@ -329,11 +311,13 @@ BWs carve_b(const ironb_mlp_layout* lay, int64_t N, unsigned char* base) {
   w.glist[0] = (int*)take(cap / 32 * 4); w.glist[1] = (int*)take(cap / 32 * 4);
   w.root_ray = (int*)take(N * 4); w.root_lo = (float*)take(N * 4); w.root_hi = (float*)take(N * 4);
   w.root_mid = (float*)take(N * 4); w.root_work = (int*)take(N * 4);
-  w.E = (float*)take(cap * Epad * 4);
-  w.F = (float*)take(cap * 4);
+  w.Ehi = (float*)take(cap * Epad * 4); w.Elo = (float*)take(cap * Epad * 4);
   w.Fpart = (float*)take(cap * 4 * 8);
-  w.U[0] = (float*)take(cap * (int64_t)H * 4);
-  w.U[1] = (float*)take(cap * (int64_t)H * 4);
+  for (int b = 0; b < 2; ++b) { w.Uhi[b] = (float*)take(cap * (int64_t)H * 4); w.Ulo[b] = (float*)take(cap * (int64_t)H * 4); }
+  for (int l = 0; l < last; ++l) {
+    int64_t n = (int64_t)lay->out_pad[l] * lay->in_pad[l];
+    w.Whi[l] = (float*)take(n * 4); w.Wlo[l] = (float*)take(n * 4);
+  }
   w.bytes = off;
   return w;
 }
@@ -364,6 +348,7 @@ int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float*
                   int n_steps, const float* linspace, uint8_t* conv, float* points, float* sdf, float* dist,
                   int64_t* stats, void* ws, int64_t ws_bytes, cudaStream_t st) {
   const int H = lay->d_hidden, Epad = lay->in_pad[0], last = lay->n_lin - 1;
+  if (!trace_mlp_fused_supported(lay)) { set_error("trace: batched tcgen05 tracer needs d_hidden in {128,256,512}"); return IRONB_ENOSUP; }
   for (int l = 0; l < last; ++l)
     if (lay->out_pad[l] != H || (l > 0 && lay->in_pad[l] != H)) { set_error("trace: layer %d is not %d wide", l, H); return IRONB_ENOSUP; }
   BWs w = carve_b(lay, N, reinterpret_cast<unsigned char*>(ws));
@@ -388,36 +373,29 @@ int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float*
   A.unf_list = w.unf_list; A.smin = w.smin; A.smax = w.smax; A.prev_f = w.prev_f; A.prev_t = w.prev_t;
   A.glist[0] = w.glist[0]; A.glist[1] = w.glist[1];
   A.root_ray = w.root_ray; A.root_lo = w.root_lo; A.root_hi = w.root_hi; A.root_mid = w.root_mid; A.root_work = w.root_work;
-  A.E = w.E; A.F = w.F;
+  A.Ehi = w.Ehi; A.Elo = w.Elo;
   A.cap_groups = (int)(w.cap / 32);
   const int C = H / 128;
-  const bool fused = (H % 128 == 0) && (C == 1 || C == 2 || C == 4) && getenv("IRONB_TRACE_PER_LAYER") == nullptr;
-  A.Fpart = w.Fpart; A.b_last = packed + lay->off_b[last]; A.nparts = fused ? 2 * C : 0; A.cap = (int)w.cap;
+  A.Fpart = w.Fpart; A.b_last = packed + lay->off_b[last]; A.nparts = 2 * C; A.cap = (int)w.cap;
 
-  // tensor maps: operands are fixed for the whole call
-  CUtensorMap mE, mU[2], mW[IRONB_MAX_LIN];
+  // weights -> tf32-exact hi / lo copies (once per call), then the tensor maps: operands are fixed for the whole call
   int rc;
-  if ((rc = tc::make_map(&mE, w.E, (int)w.cap, Epad, Epad))) return rc;
-  for (int i = 0; i < 2; ++i)
-    if ((rc = tc::make_map(&mU[i], w.U[i], (int)w.cap, H, H))) return rc;
   for (int l = 0; l < last; ++l)
-    if ((rc = tc::make_map(&mW[l], packed + lay->off_w[l], lay->out_pad[l], lay->in_pad[l], lay->in_pad[l]))) return rc;
-  if ((rc = tc::make_map(&mW[last], packed + lay->off_w[last], 8, lay->in_pad[last], lay->in_pad[last]))) return rc;
-
-  // one MLP evaluation of the first `rows_cap` rows (device count *m_dev x m_mul): E -> U0 -> U1 -> ... -> F
+    if ((rc = split_weights(packed + lay->off_w[l], (int64_t)lay->out_pad[l] * lay->in_pad[l], w.Whi[l], w.Wlo[l], st))) return rc;
+  CUtensorMap mE[2], mU[4], mW[2 * IRONB_MAX_LIN];
+  if ((rc = tc::make_map(&mE[0], w.Ehi, (int)w.cap, Epad, Epad))) return rc;
+  if ((rc = tc::make_map(&mE[1], w.Elo, (int)w.cap, Epad, Epad))) return rc;
+  for (int b = 0; b < 2; ++b) {
+    if ((rc = tc::make_map(&mU[b * 2], w.Uhi[b], (int)w.cap, H, H))) return rc;
+    if ((rc = tc::make_map(&mU[b * 2 + 1], w.Ulo[b], (int)w.cap, H, H))) return rc;
+  }
+  for (int l = 0; l < last; ++l) {
+    if ((rc = tc::make_map(&mW[l * 2], w.Whi[l], lay->out_pad[l], lay->in_pad[l], lay->in_pad[l]))) return rc;
+    if ((rc = tc::make_map(&mW[l * 2 + 1], w.Wlo[l], lay->out_pad[l], lay->in_pad[l], lay->in_pad[l]))) return rc;
+  }
+  // one MLP evaluation of the first (*m_dev x m_mul) rows: all hidden layers + the sdf row in one cluster launch (mlp_tc.cu)
   auto mlp = [&](int rows_cap, const int* m_dev, int m_mul) -> int {
-    if (fused)   // all hidden layers + the sdf row in one cluster launch (mlp_tc.cu)
-      return launch_trace_mlp_fused(lay, packed, mE, mU, mW, w.E, w.U, w.Fpart, rows_cap, (int)w.cap, m_dev, m_mul, st);
-    for (int l = 0; l < last; ++l) {
-      EpiTraceHidden ep{packed + lay->off_b[l], w.U[l & 1], w.E, H, lay->out_dim[l], (l + 1 == lay->skip_layer) ? 1 : 0,
-                        Epad, lay->pe_dim, lay->beta};
-      const CUtensorMap& a = (l == 0) ? mE : mU[(l - 1) & 1];
-      int r2 = tc::launch_gemm_nt_tc_maps(a, mW[l], rows_cap, H, lay->in_pad[l], ep, m_dev, m_mul, st, "trace mlp layer");
-      if (r2) return r2;
-    }
-    EpiTraceLast ep{packed + lay->off_b[last], w.F, lay->scale};
-    return tc::launch_gemm_nt_tc_maps(mU[(last - 1) & 1], mW[last], rows_cap, 8, lay->in_pad[last], ep, m_dev, m_mul, st,
-                                      "trace mlp sdf row");
+    return launch_trace_mlp_fused(lay, packed, mE, mU, mW, w.Ehi, w.Elo, w.Uhi, w.Ulo, w.Fpart, rows_cap, (int)w.cap, m_dev, m_mul, st);
   };
   const int nb = (int)ceil_div64(N, 256);
 

@@ -38,5 +38,18 @@ for i in range(a.reps + 1):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     print(f"trace {i}: {dt * 1e3:.3f} ms, hits {int(res['convergent_mask'].sum())}/{uv.shape[0] * uv.shape[1]}")
+import ctypes
+lib = _lib.load()
+if os.environ.get("IRONB_MLP_DBG"):
+    lib.ironb_debug_mlp_timeline(None, 0)      # allocate the stamp buffer
+    res = ib.raytrace_pixels(net, rt, uv, cam)
+    torch.cuda.synchronize()
+    buf = (ctypes.c_longlong * 64)()
+    lib.ironb_debug_mlp_timeline(buf, 64)
+    v = list(buf)
+    t0 = v[0]
+    print("fused MLP timeline of the LAST launch (cycles from layer-0 start; cols: wait-full-start, first-full, mma-issued, acc-ready, epi-done, barrier-exit)")
+    for l in range(8):
+        print(l, [x - t0 for x in v[l * 8:l * 8 + 6]])
 st = rt.last_stats.cpu().tolist()
 print("stats (summed over calls):", st)
