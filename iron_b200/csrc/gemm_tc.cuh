@@ -27,7 +27,8 @@ constexpr int TILE_BYTES = BM * BK * 4;            // 16 KiB: one operand tile (
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // [A_hi][B_hi][A_lo][B_lo]
 constexpr int HI_BYTES = 2 * TILE_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers + tmem ptr*/;
-constexpr int NTHREADS = 192;                      // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-5 split + epilogue
+constexpr int NTHREADS = 320;                      // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-9 split + epilogue
+constexpr int NSPLIT = 256;
 constexpr uint32_t TMEM_COLS = 512;               // three 128-column accumulators (even k-steps, odd k-steps, lo-terms)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -96,9 +97,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
-// hi = x with the 13 low mantissa bits cleared (exactly a tf32 value), lo = tf32_rna(x - hi) (x - hi is exact in fp32;
-// rounding its magnitude half-up to 11 significant bits is one integer add + mask).  x = hi + lo to ~2^-22 |x|, unbiased.
+// Round-to-nearest split: hi = tf32_rna(x), lo = tf32_rna(x - hi).  x - hi is exact in fp32 and SIGNED, so the term the
+// 3xTF32 product drops (lo*lo) is zero-mean; rounding a magnitude half-up to 11 significant bits is one integer add + mask.
 __device__ __forceinline__ void split1(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xffffe000u);
+}
+// Truncating split for operands that stay raw fp32 in shared memory (kind::tf32 ignores the 13 low mantissa bits, i.e. the
+// tensor core itself sees hi = trunc(x)): lo = tf32_rna(x - trunc(x)).  Cheaper (no hi write-back), but lo has the sign of
+// x, so the dropped lo*lo term is a small systematic underestimate of |a*b|.
+__device__ __forceinline__ void split1_trunc(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
   lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xffffe000u);
 }
@@ -111,8 +119,12 @@ __device__ __forceinline__ void split_stage(float4* __restrict__ hi, float4* __r
     const int c = t + j * nthreads;
     const float4 v = hi[c];
     float4 h, l;
-    split1(v.x, h.x, l.x); split1(v.y, h.y, l.y); split1(v.z, h.z, l.z); split1(v.w, h.w, l.w);
-    if (write_hi) hi[c] = h;
+    if (write_hi) {
+      split1(v.x, h.x, l.x); split1(v.y, h.y, l.y); split1(v.z, h.z, l.z); split1(v.w, h.w, l.w);
+      hi[c] = h;
+    } else {
+      split1_trunc(v.x, h.x, l.x); split1_trunc(v.y, h.y, l.y); split1_trunc(v.z, h.z, l.z); split1_trunc(v.w, h.w, l.w);
+    }
     lo[c] = l;
   }
 }
@@ -147,7 +159,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full(s), 1);
-      mbar_init(conv(s), 128);
+      mbar_init(conv(s), NSPLIT);
       mbar_init(empty(s), 1);
     }
     mbar_init(acc_bar, 1);
@@ -203,25 +215,29 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       tc_commit(acc_bar);             // accumulator complete
     }
   } else {
-    // ================= splitter, then epilogue (warps 2..5) =================
-    const int t = threadIdx.x - 64;   // 0..127
+    // ================= splitter, then epilogue (warps 2..9) =================
+    const int t = threadIdx.x - 64;   // 0..255
     for (int it = 0; it < nk; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
       mbar_wait(full(s), ph);
       float4* hi = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES);
       float4* lo = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES + HI_BYTES);
-      split_stage(hi, lo, t, 128, HI_BYTES / 16 / 128, write_hi);
+      split_stage(hi, lo, t, NSPLIT, HI_BYTES / 16 / NSPLIT, write_hi);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       mbar_arrive(conv(s));
     }
-    // epilogue: TMEM lane = tile row (warp%4 selects the 32-lane quarter), column = tile column
+    // epilogue, phase 1: TMEM (lane = tile row; warp%4 selects the 32-lane quarter, (warp-2)/4 the 64-column half) ->
+    // registers (the three accumulators are added in fp32 RN) -> a row-major fp32 tile in the idle pipeline stages
     mbar_wait(acc_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;
+    constexpr int TLD = BN + 4;                       // padded row pitch: conflict-free 128-bit rows
+    float* tile = reinterpret_cast<float*>(base_ptr);
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c0 = half * 64 + cc * 32;
       uint32_t r[32], r1[32], r2[32];
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
       tmem_ld32(taddr, r);
@@ -229,18 +245,27 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       tmem_ld32(taddr + 256u, r2);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        r[i] = __float_as_uint(__fadd_rn(__fadd_rn(__uint_as_float(r[i]), __uint_as_float(r1[i])), __uint_as_float(r2[i])));
-      if (m < M) {
+      for (int g = 0; g < 8; ++g) {
+        float v[4];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int n = n0 + c0 + g * 4;
-          if (n < N) {
-            const float v[4] = {__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]), __uint_as_float(r[g * 4 + 2]),
-                                __uint_as_float(r[g * 4 + 3])};
-            epi(m, n, v);
-          }
-        }
+        for (int j = 0; j < 4; ++j)
+          v[j] = __fadd_rn(__fadd_rn(__uint_as_float(r[g * 4 + j]), __uint_as_float(r1[g * 4 + j])), __uint_as_float(r2[g * 4 + j]));
+        *reinterpret_cast<float4*>(tile + row * TLD + c0 + g * 4) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // phase 2: one warp per tile row, lanes along the columns: every global access of the epilogue functor (bias,
+    // saved activations, outputs) is a coalesced 512-byte row segment
+    const int w8 = warp - 2;
+#pragma unroll 2
+    for (int rr = 0; rr < BM / 8; ++rr) {
+      const int trow = w8 * (BM / 8) + rr;
+      const int m = m0 + trow;
+      const int n = n0 + lane * 4;
+      if (m < M && n < N) {
+        const float4 v4 = *reinterpret_cast<const float4*>(tile + trow * TLD + lane * 4);
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+        epi(m, n, v);
       }
     }
   }
@@ -260,7 +285,7 @@ EncodeTiledFn encode_fn();
 // rows x K fp32 matrix with row pitch ld floats -> 2-D map with a (BK x 128) SWIZZLE_128B box, zero fill out of bounds
 int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld);
 bool tc_enabled();
-bool split_writes_hi();   // 1: the splitter stores the truncated hi back (default); 0: raw fp32 stays as the hi operand
+bool split_writes_hi();   // 0 (default): raw fp32 stays as the hi operand; 1 (IRONB_SPLIT_WRITE_HI=1): store the truncated hi back
 
 template <class Epi>
 int launch_gemm_nt_tc_maps(const CUtensorMap& mA, const CUtensorMap& mB, int M, int N, int K, const Epi& epi,

@@ -152,9 +152,10 @@ __global__ void __launch_bounds__(NT, 1) mlp_fused_kernel(const __grid_constant_
             for (int kk = 0; kk < BK / 8; ++kk) {
               const uint64_t adv = (uint64_t)(kk * 2);
               const int g = i * (BK / 8) + kk;
-              tc_mma_tf32(tmem + ((g & 1) ? 128u : 0u), a_hi + adv, b_hi + adv, IDESC, g >= 2 ? 1u : 0u);
-              tc_mma_tf32(tmem + 256u, a_lo + adv, b_hi + adv, IDESC, g >= 1 ? 1u : 0u);
-              tc_mma_tf32(tmem + 256u, a_hi + adv, b_lo + adv, IDESC, 1u);
+              // hi*hi rotates over three accumulators (shorter truncating chains), the lo cross terms use the fourth
+              tc_mma_tf32(tmem + 128u * (uint32_t)(g % 3), a_hi + adv, b_hi + adv, IDESC, g >= 3 ? 1u : 0u);
+              tc_mma_tf32(tmem + 384u, a_lo + adv, b_hi + adv, IDESC, g >= 1 ? 1u : 0u);
+              tc_mma_tf32(tmem + 384u, a_hi + adv, b_lo + adv, IDESC, 1u);
             }
             tc_commit(empty(s));
           }
@@ -190,7 +191,11 @@ __global__ void __launch_bounds__(NT, 1) mlp_fused_kernel(const __grid_constant_
           const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
           tmem_ld32(taddr, r);
           tmem_ld32(taddr + 128u, r1);
-          tmem_ld32(taddr + 256u, r2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__fadd_rn(__uint_as_float(r[i]), __uint_as_float(r1[i])));
+          tmem_ld32(taddr + 256u, r1);
+          tmem_ld32(taddr + 384u, r2);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           // output staging in the (now idle) pipeline stages, in the SWIZZLE_128B box layout the TMA store expects
           unsigned char* stg_hi = base_ptr + blk * TILE_BYTES + row * 128;
