@@ -92,11 +92,11 @@ class ClockSampler:
 
 
 def crop_corner(rank: int, patch: int):
-    """Per-rank 64x64 crop of the 512x512 view: rank 0 = the canonical centre crop, others tile around it."""
+    """Per-rank crop of the 512x512 view: rank 0 = the canonical centre crop, others tile around it."""
     offs = [(0, 0), (1, 0), (-1, 0), (0, 1), (0, -1), (1, 1), (-1, -1), (1, -1)]
     dx, dy = offs[rank % 8]
     c = 256 - patch // 2
-    return (c + dx * patch, c + dy * patch)
+    return (min(max(c + dx * patch, 0), 512 - patch), min(max(c + dy * patch, 0), 512 - patch))
 
 
 # ------------------------------------------------------------------------------------------ CPU oracle arm
@@ -213,6 +213,7 @@ def run_ours(args):
 
     import iron_b200 as ib
     from iron_b200 import _lib
+    from iron_b200.parallel import allreduce_gradients
     from oracle import iron_oracle as O   # fixture constants only (camera K / W2C); nothing is computed with it here
     lib = _lib.load()
     if args.tracer != "default":
@@ -275,13 +276,7 @@ def run_ours(args):
             tracer.forward = orig
             trace_ms.append(evs)
         if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            flat.div_(world)
-            off = 0
-            for p in params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
-                off += p.numel()
+            allreduce_gradients(params, world)      # the only collective of the path: flat fp32 gradient buffer, NCCL
         return loss, res
 
     def barrier():

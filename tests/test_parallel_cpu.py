@@ -1,0 +1,67 @@
+"""World-size-2 gloo tests (CPU) of the data-parallel host logic: ray sharding and the flat gradient all-reduce."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from iron_b200.parallel import allreduce_gradients, collect_params
+    torch.manual_seed(0)                              # replicated weights
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    extra = torch.nn.Linear(2, 2)                     # a module that gets no gradient on rank 1
+    params = collect_params([net, extra])
+    x = torch.full((4, 5), float(rank + 1))
+    net(x).sum().backward()
+    if rank == 0:
+        extra(torch.ones(1, 2)).sum().backward()
+    local = [None if p.grad is None else p.grad.clone() for p in params]
+    n = allreduce_gradients(params, world)
+    out[rank] = (n, [p.grad.clone() for p in params], local)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        (n0, g0, l0), (n1, g1, l1) = out[0], out[1]
+    assert n0 == n1 == sum(t.numel() for t in g0)
+    for a, b, la, lb in zip(g0, g1, l0, l1):
+        assert torch.equal(a, b)                      # every rank ends with the same averaged gradient
+        za = la if la is not None else torch.zeros_like(a)
+        zb = lb if lb is not None else torch.zeros_like(a)
+        assert torch.allclose(a, (za + zb) / 2, atol=1e-6)
+
+
+def test_shard_range_partitions_exactly():
+    from iron_b200.parallel import crop_for_rank, shard_range
+    for n in (0, 1, 7, 4096, 65537):
+        for world in (1, 2, 3, 8):
+            cover = []
+            for r in range(world):
+                a, b = shard_range(n, r, world)
+                assert 0 <= a <= b <= n and (b - a) in (n // world, n // world + 1)
+                cover += list(range(a, b))
+            assert cover == list(range(n))
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+    corners = {crop_for_rank(r, 64) for r in range(8)}
+    assert len(corners) == 8 and crop_for_rank(0, 64) == (224, 224)
+    assert all(0 <= x <= 448 and 0 <= y <= 448 for x, y in corners)
