@@ -78,6 +78,11 @@ int ironb_set_trace_mode(int mode);
 int ironb_gemm_nt(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float* C, int ldc,
                   int mode, void* stream);
 
+/* C[Nd][ldc] += A[M][lda]^T * B[M][ldb] (the weight-gradient product; C is accumulated): unit-test entry. */
+int64_t ironb_gemm_tn_scratch_bytes(int M, int Nd, int Kd);
+int ironb_gemm_tn(const float* A, int lda, const float* B, int ldb, int M, int Nd, int Kd, float* C, int ldc,
+                  int mode, void* scratch, void* stream);
+
 /* ---------------------------------------------------------------- layouts (host only) */
 int ironb_sdf_layout(int d_in, int d_out, int d_hidden, int n_layers, int skip_layer, int multires,
                      float scale, float beta, ironb_mlp_layout* out);

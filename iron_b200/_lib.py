@@ -46,6 +46,8 @@ _PROTOS = {
     "ironb_set_gemm_mode": (_INT, [_INT]),
     "ironb_set_trace_mode": (_INT, [_INT]),
     "ironb_gemm_nt": (_INT, [_P, _INT, _P, _INT, _INT, _INT, _INT, _P, _INT, _INT, _P]),
+    "ironb_gemm_tn_scratch_bytes": (_I64, [_INT, _INT, _INT]),
+    "ironb_gemm_tn": (_INT, [_P, _INT, _P, _INT, _INT, _INT, _INT, _P, _INT, _INT, _P, _P]),
     "ironb_sdf_layout": (_INT, [_INT, _INT, _INT, _INT, _INT, _INT, _F, _F, _LAY]),
     "ironb_matnet_layout": (_INT, [_INT, _INT, _INT, _INT, _LAY]),
     "ironb_mlp_fold": (_INT, [_LAY, _PP, _PP, _PP, _P, _P]),

@@ -94,3 +94,19 @@ extern "C" int ironb_gemm_nt(const float* A, int lda, const float* B, int ldb, i
   if (mode == 2) return tc::launch_gemm_nt_tc(A, lda, B, ldb, M, N, K, ep, as_stream(stream), "gemm_nt (tcgen05, raw hi)", 0);
   return launch_gemm_nt(A, lda, B, ldb, M, N, K, ep, as_stream(stream), "gemm_nt (simt)");
 }
+
+// C[Nd][ldc] += A[M][lda]^T * B[M][ldb]  (weight-gradient shape): unit-test entry; mode 1 = tcgen05 (transpose + split-K
+// K-major GEMM, needs ironb_gemm_tn_scratch_bytes of scratch), 0 = FFMA tiles
+extern "C" int64_t ironb_gemm_tn_scratch_bytes(int M, int Nd, int Kd) {
+  return wgrad_scratch_floats(M, Nd > Kd ? Nd : Kd) * (int64_t)sizeof(float);
+}
+extern "C" int ironb_gemm_tn(const float* A, int lda, const float* B, int ldb, int M, int Nd, int Kd, float* C, int ldc,
+                             int mode, void* scratch, void* stream) {
+  IRONB_REQUIRE(A && B && C, "gemm_tn: null pointer");
+  IRONB_REQUIRE((Nd & 3) == 0 && (Kd & 3) == 0 && (ldc & 3) == 0, "gemm_tn: Nd, Kd, ldc must be multiples of 4");
+  if (mode == 1) {
+    IRONB_REQUIRE(scratch != nullptr, "gemm_tn: tcgen05 mode needs scratch");
+    return launch_wgrad_tc(A, lda, B, ldb, M, Nd, Kd, C, ldc, reinterpret_cast<float*>(scratch), as_stream(stream), "gemm_tn (tcgen05)");
+  }
+  return launch_gemm_tn(A, lda, B, ldb, M, Nd, Kd, C, ldc, as_stream(stream), "gemm_tn (simt)");
+}

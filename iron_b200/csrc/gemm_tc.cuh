@@ -132,7 +132,7 @@ __device__ __forceinline__ void split_stage(float4* __restrict__ hi, float4* __r
 template <class Epi>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N, int K,
-                  Epi epi, const int* __restrict__ m_dev, int m_mul, int write_hi) {
+                  Epi epi, const int* __restrict__ m_dev, int m_mul, int write_hi, int k_chunk) {
   if (m_dev != nullptr) {   // row count produced on the device (compacted ray lists): whole CTAs beyond it leave at once
     const int md = *m_dev * m_mul;
     if (md < M) M = md;
@@ -152,7 +152,11 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int nk = (K + BK - 1) / BK;
+  // split-K (weight gradients): blockIdx.z owns k in [kbeg, kend), k_chunk a multiple of BK; the epilogue accumulates
+  const int kbeg = (k_chunk > 0) ? (int)blockIdx.z * k_chunk : 0;
+  const int kend = (k_chunk > 0) ? min(K, kbeg + k_chunk) : K;
+  const int nk = (kend - kbeg + BK - 1) / BK;
+  if (nk <= 0) return;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -183,8 +187,8 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         mbar_wait(empty(s), ph ^ 1);
         mbar_arrive_expect_tx(full(s), HI_BYTES);
         const uint32_t st = base + s * STAGE_BYTES;
-        tma_load_2d(st, &mapA, it * BK, m0, full(s));
-        tma_load_2d(st + TILE_BYTES, &mapB, it * BK, n0, full(s));
+        tma_load_2d(st, &mapA, kbeg + it * BK, m0, full(s));
+        tma_load_2d(st + TILE_BYTES, &mapB, kbeg + it * BK, n0, full(s));
       }
     }
   } else if (warp == 1) {
@@ -278,6 +282,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 }
 
 // ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency) ----
+typedef CUtensorMap CUtensorMapAlias;
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -289,7 +294,7 @@ bool split_writes_hi();   // 0 (default): raw fp32 stays as the hi operand; 1 (I
 
 template <class Epi>
 int launch_gemm_nt_tc_maps(const CUtensorMap& mA, const CUtensorMap& mB, int M, int N, int K, const Epi& epi,
-                           const int* m_dev, int m_mul, cudaStream_t st, const char* what, int write_hi = -1) {
+                           const int* m_dev, int m_mul, cudaStream_t st, const char* what, int write_hi = -1, int k_chunk = 0) {
   if (write_hi < 0) write_hi = split_writes_hi() ? 1 : 0;
   if (M <= 0 || N <= 0) return IRONB_OK;
   auto kern = gemm_nt_tc_kernel<Epi>;
@@ -299,8 +304,8 @@ int launch_gemm_nt_tc_maps(const CUtensorMap& mA, const CUtensorMap& mB, int M, 
     if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div64(N, BN), (unsigned)ceil_div64(M, BM));
-  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mB, M, N, K, epi, m_dev, m_mul, write_hi);
+  dim3 grid((unsigned)ceil_div64(N, BN), (unsigned)ceil_div64(M, BM), (unsigned)(k_chunk > 0 ? ceil_div64(K, k_chunk) : 1));
+  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mB, M, N, K, epi, m_dev, m_mul, write_hi, k_chunk);
   IRONB_CHECK_LAUNCH(what);
   return IRONB_OK;
 }
@@ -320,6 +325,73 @@ int launch_gemm_nt_tc(const float* A, int lda, const float* B, int ldb, int M, i
 }  // namespace tc
 
 // fp32 FFMA tiles (exact association) or tcgen05 3xTF32 tiles, per ironb_set_gemm_mode / IRONB_GEMM.
+// ---- weight gradients on the tensor cores:  C[n][k] += sum_m A[m][n] * B[m][k] ---------------------------------------
+// tcgen05.mma.kind::tf32 wants K-major 32-bit operands here (the MN-major path with the 16-byte SWIZZLE_128B atom produced
+// nothing on sm_100a), so both operands are first transposed into scratch ([cols][round4(M)], zero padded) by a coalesced
+// smem-tile transpose, then the K-major GEMM above runs split over the row range with an atomically accumulating epilogue.
+struct EpiAtomicAdd {
+  float* C;
+  int ldc;
+  __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[4]) const {
+    float* dst = C + (size_t)m * ldc + n0;
+    atomicAdd(dst, acc[0]); atomicAdd(dst + 1, acc[1]); atomicAdd(dst + 2, acc[2]); atomicAdd(dst + 3, acc[3]);
+  }
+};
+
+// dst[c][m] = src[m][c] for c < cols, m < M; dst row pitch ldt >= round4(M), columns m in [M, ldt) zeroed
+static __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, int lds, int M, int cols,
+                                                               float* __restrict__ dst, int ldt) {
+  __shared__ float tile[32][33];
+  const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty + i * 8, c = c0 + tx;
+    tile[ty + i * 8][tx] = (m < M && c < cols) ? src[(size_t)m * lds + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + i * 8, m = m0 + tx;
+    if (c < cols && m < ldt) dst[(size_t)c * ldt + m] = tile[tx][ty + i * 8];
+  }
+}
+
+inline int64_t wgrad_scratch_floats(int64_t M, int max_cols) { return 2 * (int64_t)max_cols * ((M + 3) / 4 * 4); }
+
+// scratch: wgrad_scratch_floats(M, max(Nd, Kd)) floats
+inline int launch_wgrad_tc(const float* A, int lda, const float* B, int ldb, int M, int Nd, int Kd, float* C, int ldc,
+                           float* scratch, cudaStream_t st, const char* what) {
+  if (M <= 0 || Nd <= 0 || Kd <= 0) return IRONB_OK;
+  const int ldt = (M + 3) / 4 * 4;
+  float* At = scratch;
+  float* Bt = scratch + (size_t)(Nd > Kd ? Nd : Kd) * ldt;
+  dim3 ga((unsigned)ceil_div64(ldt, 32), (unsigned)ceil_div64(Nd, 32)), gb((unsigned)ceil_div64(ldt, 32), (unsigned)ceil_div64(Kd, 32));
+  transpose_kernel<<<ga, 256, 0, st>>>(A, lda, M, Nd, At, ldt);
+  IRONB_CHECK_LAUNCH("transpose_kernel");
+  transpose_kernel<<<gb, 256, 0, st>>>(B, ldb, M, Kd, Bt, ldt);
+  IRONB_CHECK_LAUNCH("transpose_kernel");
+  tc::CUtensorMapAlias mA, mB;
+  int rc = tc::make_map(&mA, At, Nd, ldt, ldt);
+  if (rc) return rc;
+  rc = tc::make_map(&mB, Bt, Kd, ldt, ldt);
+  if (rc) return rc;
+  const int64_t tiles = ceil_div64(Nd, tc::BM) * ceil_div64(Kd, tc::BN);
+  int64_t splits = num_sms() / tiles;
+  const int64_t maxs = ceil_div64(M, 128);
+  if (splits > maxs) splits = maxs;
+  if (splits < 1) splits = 1;
+  const int k_chunk = (int)(ceil_div64(ceil_div64(ldt, splits), tc::BK) * tc::BK);
+  EpiAtomicAdd ep{C, ldc};
+  return tc::launch_gemm_nt_tc_maps(mA, mB, Nd, Kd, ldt, ep, nullptr, 1, st, what, -1, k_chunk);
+}
+
+inline int launch_wgrad_auto(const float* A, int lda, const float* B, int ldb, int M, int Nd, int Kd, float* C, int ldc,
+                             float* scratch, cudaStream_t st, const char* what) {
+  if (tc::tc_enabled() && scratch != nullptr) return launch_wgrad_tc(A, lda, B, ldb, M, Nd, Kd, C, ldc, scratch, st, what);
+  return launch_gemm_tn(A, lda, B, ldb, M, Nd, Kd, C, ldc, st, what);
+}
+
 template <class Epi>
 int launch_gemm_nt_auto(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const Epi& epi,
                         cudaStream_t st, const char* what) {

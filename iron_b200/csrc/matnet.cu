@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(256) mat_dlast_kernel(const float* __restrict_
 struct MatWs {
   float* U[IRONB_MAX_LIN];
   float* D[2];
+  float* wg;
   int64_t floats;
 };
 
@@ -183,6 +184,8 @@ MatWs carve_mat(const ironb_mlp_layout* L, int64_t M, float* base) {
   for (int l = 0; l < L->n_lin; ++l) w.U[l] = take(L->in_pad[l]);
   w.D[0] = take(mp);
   w.D[1] = take(mp);
+  w.wg = base ? base + off : nullptr;
+  off += (wgrad_scratch_floats(M, mp) + 63) / 64 * 64;
   w.floats = off;
   return w;
 }
@@ -255,8 +258,8 @@ extern "C" int ironb_matnet_bwd(const ironb_mlp_layout* lay, const ironb_matnet_
   const float* D = w.D[last & 1];
   const bool need_in = d_points || d_normals || d_view || d_feats;
   for (int l = last; l >= 0; --l) {
-    int rc = launch_gemm_tn(D, lay->out_pad[l], w.U[l], lay->in_pad[l], (int)M, lay->out_pad[l], lay->in_pad[l],
-                            dpacked + lay->off_w[l], lay->in_pad[l], st, "matnet wgrad");
+    int rc = launch_wgrad_auto(D, lay->out_pad[l], w.U[l], lay->in_pad[l], (int)M, lay->out_pad[l], lay->in_pad[l],
+                               dpacked + lay->off_w[l], lay->in_pad[l], w.wg, st, "matnet wgrad");
     if (rc) return rc;
     rc = launch_colsum(D, lay->out_pad[l], (int)M, lay->out_dim[l], 1.f, dpacked + lay->off_b[l], st, "matnet bias grad");
     if (rc) return rc;

@@ -255,6 +255,7 @@ struct SdfWs {
   float* Z[IRONB_MAX_LIN];
   float* R[IRONB_MAX_LIN];
   float* QB[2]; float* D[2];
+  float* wg;                 // transposed-operand scratch of the tensor-core weight gradients
   int64_t floats;
 };
 
@@ -284,6 +285,8 @@ SdfWs carve(const ironb_mlp_layout* L, int64_t M, bool full, float* base) {
     for (int l = 0; l < last; ++l) w.R[l] = take(L->out_pad[l]);
     w.QB[0] = take(mp); w.QB[1] = take(mp);
     w.D[0] = take(mp); w.D[1] = take(mp);
+    w.wg = base ? base + off : nullptr;
+    off += (wgrad_scratch_floats(M, mp) + 63) / 64 * 64;
   }
   w.floats = off;
   return w;
@@ -391,8 +394,8 @@ extern "C" int ironb_sdf_getall_bwd(const ironb_mlp_layout* lay, const float* pa
     const float* qb = w.P;
     for (int l = 0; l < last; ++l) {
       // dW_l += r_l^T qbar_l
-      int rc = launch_gemm_tn(w.R[l], lay->out_pad[l], qb, lay->in_pad[l], (int)M, lay->out_pad[l], lay->in_pad[l],
-                              dpacked + lay->off_w[l], lay->in_pad[l], st, "sdf bwd B wgrad");
+      int rc = launch_wgrad_auto(w.R[l], lay->out_pad[l], qb, lay->in_pad[l], (int)M, lay->out_pad[l], lay->in_pad[l],
+                                 dpacked + lay->off_w[l], lay->in_pad[l], w.wg, st, "sdf bwd B wgrad");
       if (rc) return rc;
       EpiB ep;
       ep.Z = w.Z[l]; ep.R = w.R[l];
@@ -429,8 +432,8 @@ extern "C" int ironb_sdf_getall_bwd(const ironb_mlp_layout* lay, const float* pa
     D = w.R[lstart];
   }
   for (int l = lstart; l >= 0; --l) {
-    int rc = launch_gemm_tn(D, lay->out_pad[l], w.U[l], lay->in_pad[l], (int)M, lay->out_pad[l], lay->in_pad[l],
-                            dpacked + lay->off_w[l], lay->in_pad[l], st, "sdf bwd A wgrad");
+    int rc = launch_wgrad_auto(D, lay->out_pad[l], w.U[l], lay->in_pad[l], (int)M, lay->out_pad[l], lay->in_pad[l],
+                               dpacked + lay->off_w[l], lay->in_pad[l], w.wg, st, "sdf bwd A wgrad");
     if (rc) return rc;
     rc = launch_colsum(D, lay->out_pad[l], (int)M, lay->out_dim[l], 1.f, dpacked + lay->off_b[l], st,
                        "sdf bwd A bias");

@@ -50,3 +50,26 @@ def test_gemm_modes_agree_on_structured_input():
         C = run(mode, A, B)
         err = (C.double() - ref).abs().max().item()
         assert err <= 1e-3 * ref.abs().max().item() * 1e-3, (mode, err)
+
+
+@pytest.mark.parametrize("M,Nd,Kd", [(128, 128, 128), (256, 128, 128), (4096, 512, 512), (1000, 264, 512), (53, 8, 296), (2048, 512, 40),
+                                     (70000, 256, 256)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gemm_tn(M, Nd, Kd, mode):
+    """C += A^T B (weight gradients): FFMA tiles, or transpose + split-K tcgen05 GEMM with an atomically adding epilogue."""
+    from iron_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + Nd + Kd)
+    A = (torch.randn(M, Nd, generator=g) / np.sqrt(M)).to(DEV)
+    B = torch.randn(M, Kd, generator=g).to(DEV)
+    C0 = torch.randn(Nd, Kd, generator=g).to(DEV)
+    C = C0.clone()
+    scratch = torch.empty(int(lib.ironb_gemm_tn_scratch_bytes(M, Nd, Kd)), dtype=torch.uint8, device=DEV)
+    _lib.check(lib.ironb_gemm_tn(_lib.ptr(A), Nd, _lib.ptr(B), Kd, M, Nd, Kd, _lib.ptr(C), Kd, mode, _lib.ptr(scratch),
+                                 _lib.stream()), "gemm_tn")
+    torch.cuda.synchronize()
+    ref = C0.double() + A.double().t() @ B.double()
+    scale = A.double().abs().t() @ B.double().abs() + C0.double().abs()
+    rel = ((C.double() - ref).abs() / scale).max().item()
+    print(f"tn mode {mode} M={M} Nd={Nd} Kd={Kd}: max |err| / scale = {rel:.2e}")
+    assert torch.isfinite(C).all() and rel < 2e-6, rel
