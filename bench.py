@@ -47,18 +47,21 @@ def peaks():
 
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, index: int):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock / throttle reasons of the samples whose timestamp falls inside [t_begin, t_end] (epoch s);
+        all samples when none does (very short timed regions)."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
@@ -69,25 +72,29 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[7], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[0]), float(parts[1]), [nm for nm, v in zip(names, parts[3:7]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+        inside = [r for r in rows if t_begin is not None and t_begin - 0.05 <= r[0] <= t_end + 0.05]
+        use = inside if inside else rows
+        sm = [r[1] for r in use]
+        mx = [r[2] for r in use]
+        reasons = set(x for r in use for x in r[3])
         try:
             os.unlink(self.f.name)
         except OSError:
             pass
         if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                   "samples_inside_timed_region": len(inside)}
         return out
 
 
@@ -193,7 +200,8 @@ def workload_config(args, patch):
     return {"workload": f"BASELINE configs[1]: IRON stage-2 step, {patch}x{patch} crop ({patch * patch} rays/GPU) of the 512x512 "
                         f"colocated-flash fixture view, trace+shade+loss+backward",
             "sdf_mlp": f"8x{args.hidden}, PE L=6, skip@4, softplus(100), weight-norm", "material_mlps": "3 x (4x256, ReLU)",
-            "rays_per_gpu": patch * patch, "eikonal_points": patch * patch // 2, "parallelism": f"dp{args.gpus} (rays sharded, weights replicated)",
+            "rays_per_gpu": patch * patch, "eikonal_points": patch * patch // 2,
+            "sharding": "every rank traces/shades its own copy of the same crop (identical work per GPU), own target/eikonal seeds", "parallelism": f"dp{args.gpus} (rays sharded, weights replicated)",
             "l2": "256 MiB flush between steps, outside the per-step CUDA-event pairs",
             "init": "seed-0 geometric init, light=32"}
 
@@ -238,7 +246,7 @@ def run_ours(args):
     tracer.collect_stats = True
     K_h = torch.tensor(O.FIXTURE_K, dtype=torch.float64).reshape(4, 4).float().pin_memory()
     W2C_h = torch.tensor(O.FIXTURE_W2C, dtype=torch.float64).reshape(4, 4).float().pin_memory()
-    ul = crop_corner(rank, S)
+    ul = crop_corner(0, S)     # weak scaling: every rank does the SAME amount of work (the canonical centre crop)
     target_h = (torch.rand(S, S, 3, generator=torch.Generator().manual_seed(11 + rank)) * 0.5).pin_memory()
     eik_h = torch.empty(S * S // 2, 3).uniform_(-1.0, 1.0, generator=torch.Generator().manual_seed(12 + rank)).pin_memory()
 
@@ -284,19 +292,20 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None
     # ---- warm-up
     for _ in range(max(args.warmup, 3)):
         step(cam, target, eik)
     barrier()
 
     # ---- timed: K steps, per-step CUDA events, L2 flushed between steps
-    sampler = ClockSampler(local) if rank == 0 else None
     tracer.last_stats = None
     l0 = lib.ironb_launch_count()
     evs = []
     hits = 0
     barrier()
     wall0 = time.perf_counter()
+    epoch0 = time.time()
     for _ in range(args.steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -306,8 +315,8 @@ def run_ours(args):
         evs.append((e0, e1))
     barrier()
     wall = time.perf_counter() - wall0
+    epoch1 = time.time()
     launches = lib.ironb_launch_count() - l0
-    clocks = sampler.stop() if sampler else None
     step_ms = [a.elapsed_time(b) for a, b in evs]
     my_ms = sum(step_ms)
     tr_ms = [sum(a.elapsed_time(b) for a, b in ev) for ev in trace_ms]
@@ -338,6 +347,7 @@ def run_ours(args):
     h2d = K_h.numel() * 4 + W2C_h.numel() * 4 + target_h.numel() * 4 + eik_h.numel() * 4
     d2h = 4 + 4   # loss + the hit count the shading chunk reads back
 
+    clocks = sampler.stop(epoch0, epoch1) if sampler else None
     if rank == 0:
         pk = peaks()
         evals = stats[0] + stats[1] + stats[2]                       # SDF evaluations the tracer executed, all K steps
@@ -366,7 +376,7 @@ def run_ours(args):
                          "kernel_share_of_step": tr_total_ms / my_ms if my_ms else None},
             "tracer": {"evals_sphere": stats[0] / args.steps, "evals_sampler": stats[1] / args.steps,
                        "evals_bisect": stats[2] / args.steps, "sampler_rays": stats[3] / args.steps,
-                       "root_rays": stats[4] / args.steps, "k_max": stats[5] / args.steps, "hits": hits, "rays": S * S,
+                       "root_rays": stats[4] / args.steps, "k_max": stats[5], "hits": hits, "rays": S * S,
                        "implementation": tracer_impl},
             "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps, "grad_params": n_params,
             "loss": loss_host,

@@ -100,8 +100,13 @@ class RayTracer(nn.Module):
                                        int(self.sphere_tracing_iters), int(self.n_steps), _lib.ptr(self._lin(dev)),
                                        _lib.ptr(conv), _lib.ptr(points), _lib.ptr(sdf_out), _lib.ptr(dist),
                                        _lib.ptr(stats), _lib.ptr(ws), ws.numel(), _lib.stream()), "trace")
-        if stats is not None:
-            self.last_stats = stats if self.last_stats is None else self.last_stats + stats
+        if stats is not None:   # summed over calls, except [5] (k_max), which keeps the maximum
+            if self.last_stats is None:
+                self.last_stats = stats
+            else:
+                kmax = torch.maximum(self.last_stats[5], stats[5])
+                self.last_stats = self.last_stats + stats
+                self.last_stats[5] = kmax
         return {
             "convergent_mask": conv.bool().reshape(sh),
             "points": points.reshape(sh + [3]),
