@@ -15,7 +15,7 @@
 //     128 x H row block visible before any CTA of the cluster TMA-loads it as the next layer's A operand.
 //
 // The last hidden layer never stores its activations: its epilogue dots them with row 0 of the output layer (the sdf row)
-// and writes per-(rank, column-half) partial sums; the tracer's state-machine kernel adds the 2C partials in a fixed
+// and writes per-(rank, 32-column block) partial sums; the tracer's state-machine kernel adds the 4C partials in a fixed
 // order (deterministic) and applies bias / scale.
 #include "gemm_tc.cuh"
 
@@ -25,8 +25,8 @@ namespace mlp {
 using namespace tc;
 
 constexpr int MAXH = 8;                     // hidden layers the fused kernel supports
-constexpr int NT = 320;                     // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..9 epilogue
-constexpr int NEPI = 256;
+constexpr int NT = 576;                     // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..17 epilogue (4 per scheduler)
+constexpr int NEPI = 512;
 constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256 + 2 * BN * 4;
 
 struct Maps {
@@ -40,7 +40,7 @@ struct Args {
   const float* w_last;       // row 0 of the output layer [H]
   const float* Ehi; const float* Elo;
   float* Uhi[2]; float* Ulo[2];
-  float* Fpart;              // [2C][cap] partial sdf sums
+  float* Fpart;              // [4C][cap] partial sdf sums
   int n_true[MAXH];
   int kpad[MAXH];
   int n_hidden, skip_layer, Epad, Edim, H;
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_fused_kernel(const __grid_constant_
         }
         __syncwarp();
       } else {
-        // ================= epilogue (8 warps: 4 lane quarters x 2 column halves) =================
+        // ================= epilogue (16 warps: 4 TMEM lane quarters x 4 blocks of 32 columns) =================
         const int t = threadIdx.x - 64;
         const bool last = (l == a.n_hidden - 1);
         const bool pre_skip = (l + 1 == a.skip_layer);
@@ -175,40 +175,37 @@ __global__ void __launch_bounds__(NT, 1) mlp_fused_kernel(const __grid_constant_
           sbias[t] = (n < n_true) ? __ldg(a.bias[l] + n) : 0.f;
           if (last) swl[t] = __ldg(a.w_last + n);
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 512;" ::: "memory");
         mbar_wait(acc_bar, acc_phase);
         if (a.dbg && threadIdx.x == 64 && blockIdx.x == 0 && blockIdx.y == 0 && tile == 0) a.dbg[l * 8 + 3] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int q = warp & 3, blk = (warp - 2) >> 2;
         const int row = q * 32 + lane;          // row inside the tile == TMEM lane
         const int m = m0 + row;
         float dot = 0.f;
+        // output staging in the (now idle) pipeline stages, in the SWIZZLE_128B box layout the TMA store expects
+        unsigned char* stg_hi = base_ptr + blk * TILE_BYTES + row * 128;
+        unsigned char* stg_lo = stg_hi + 4 * TILE_BYTES;
 #pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-          const int blk = half * 2 + cc;        // 32-column block of the tile
-          const int c0 = blk * 32;
-          uint32_t r[32], r1[32], r2[32];
+        for (int h = 0; h < 2; ++h) {
+          const int c0 = blk * 32 + h * 16;     // 16 columns at a time keeps the 16-warp epilogue under 112 registers
+          uint32_t r0[16], r1[16], r2[16], r3[16];
           const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-          tmem_ld32(taddr, r);
-          tmem_ld32(taddr + 128u, r1);
+          tmem_ld16(taddr, r0);
+          tmem_ld16(taddr + 128u, r1);
+          tmem_ld16(taddr + 256u, r2);
+          tmem_ld16(taddr + 384u, r3);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__fadd_rn(__uint_as_float(r[i]), __uint_as_float(r1[i])));
-          tmem_ld32(taddr + 256u, r1);
-          tmem_ld32(taddr + 384u, r2);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          // output staging in the (now idle) pipeline stages, in the SWIZZLE_128B box layout the TMA store expects
-          unsigned char* stg_hi = base_ptr + blk * TILE_BYTES + row * 128;
-          unsigned char* stg_lo = stg_hi + 4 * TILE_BYTES;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
+          for (int g = 0; g < 4; ++g) {
             const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + g * 4);
             const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
             float u[4], hi[4], lo[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int i = g * 4 + j;
-              const float z = __fadd_rn(__fadd_rn(__uint_as_float(r[i]), __uint_as_float(r1[i])), __uint_as_float(r2[i]));
+              const float z = __fadd_rn(__fadd_rn(__fadd_rn(__uint_as_float(r0[i]), __uint_as_float(r1[i])), __uint_as_float(r2[i])),
+                                        __uint_as_float(r3[i]));
               u[j] = softplus_fast(z + bb[j], a.beta, a.inv_beta);
             }
             if (pre_skip) {   // cat(h, PE)/sqrt(2): warp-uniform branch, only the layer before the skip takes it
@@ -233,24 +230,24 @@ __global__ void __launch_bounds__(NT, 1) mlp_fused_kernel(const __grid_constant_
             } else {
 #pragma unroll
               for (int j = 0; j < 4; ++j) split1(u[j], hi[j], lo[j]);
-              const int off = ((g ^ (row & 7)) << 4);          // 16-byte chunk g of the 128-byte row, XOR-swizzled
+              const int off = (((h * 4 + g) ^ (row & 7)) << 4);   // 16-byte chunk of the 128-byte row, XOR-swizzled
               *reinterpret_cast<float4*>(stg_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
               *reinterpret_cast<float4*>(stg_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
           }
         }
         if (last) {
-          if (m < M) a.Fpart[(size_t)(rank * 2 + half) * a.cap + m] = dot;
+          if (m < M) a.Fpart[(size_t)(rank * 4 + blk) * a.cap + m] = dot;
         } else {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged tile -> visible to the TMA store engine
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 1, 512;" ::: "memory");
           if (t == 0) {
             const CUtensorMap* mh = &maps.u[l & 1][0];
             const CUtensorMap* ml = &maps.u[l & 1][1];
 #pragma unroll
-            for (int blk = 0; blk < 4; ++blk) {
-              tma_store_2d(mh, base + blk * TILE_BYTES, n0 + blk * 32, m0);
-              tma_store_2d(ml, base + (4 + blk) * TILE_BYTES, n0 + blk * 32, m0);
+            for (int bk = 0; bk < 4; ++bk) {
+              tma_store_2d(mh, base + bk * TILE_BYTES, n0 + bk * 32, m0);
+              tma_store_2d(ml, base + (4 + bk) * TILE_BYTES, n0 + bk * 32, m0);
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete (and smem free) before the barrier

@@ -312,7 +312,7 @@ BWs carve_b(const ironb_mlp_layout* lay, int64_t N, unsigned char* base) {
   w.root_ray = (int*)take(N * 4); w.root_lo = (float*)take(N * 4); w.root_hi = (float*)take(N * 4);
   w.root_mid = (float*)take(N * 4); w.root_work = (int*)take(N * 4);
   w.Ehi = (float*)take(cap * Epad * 4); w.Elo = (float*)take(cap * Epad * 4);
-  w.Fpart = (float*)take(cap * 4 * 8);
+  w.Fpart = (float*)take(cap * 4 * 16);
   for (int b = 0; b < 2; ++b) { w.Uhi[b] = (float*)take(cap * (int64_t)H * 4); w.Ulo[b] = (float*)take(cap * (int64_t)H * 4); }
   for (int l = 0; l < last; ++l) {
     int64_t n = (int64_t)lay->out_pad[l] * lay->in_pad[l];
@@ -376,7 +376,7 @@ int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float*
   A.Ehi = w.Ehi; A.Elo = w.Elo;
   A.cap_groups = (int)(w.cap / 32);
   const int C = H / 128;
-  A.Fpart = w.Fpart; A.b_last = packed + lay->off_b[last]; A.nparts = 2 * C; A.cap = (int)w.cap;
+  A.Fpart = w.Fpart; A.b_last = packed + lay->off_b[last]; A.nparts = 4 * C; A.cap = (int)w.cap;
 
   // weights -> tf32-exact hi / lo copies (once per call), then the tensor maps: operands are fixed for the whole call
   int rc;
