@@ -21,8 +21,8 @@
  *   ironb_camera_rays                    Camera.get_rays + intersect_sphere   models/raytracer.py:254-286, 223-237
  *   ironb_trace                          RayTracer.forward (sphere_tracing, ray_sampler, rootfind)
  *                                                                             models/raytracer.py:45-220
- *   ironb_shade_prep / _bwd              reparam_points + normal/distance glue of render_fn
- *                                                                             models/raytracer.py:17-24, render_surface.py:127-133
+ *   ironb_depth_closing                  kornia.morphology.closing in raytrace_camera (fill_holes)
+ *                                                                             models/raytracer.py:554-557
  */
 #ifndef IRON_B200_H
 #define IRON_B200_H
@@ -186,6 +186,10 @@ int ironb_compact_mask(const uint8_t* mask, int64_t N, int32_t* idx, int32_t* co
 int ironb_gather_rows(const float* src, const int32_t* idx, int64_t M, int width, float* dst, void* stream);
 /* Scatter rows into a zero-initialised dense buffer: dst[idx[i],:] = src[i,:]. */
 int ironb_scatter_rows(const float* src, const int32_t* idx, int64_t M, int width, float* dst, void* stream);
+
+/* Hole filling of raytrace_camera (models/raytracer.py:554-557): 3x3 morphological closing of the [H,W] depth map
+ * (kornia.morphology.closing with an all-ones kernel, geodesic border).  tmp / out: H*W floats each. */
+int ironb_depth_closing(const float* depth, int H, int W, float* tmp, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -140,6 +140,26 @@ __global__ void __launch_bounds__(256) compact_scatter_kernel(const uint8_t* __r
     if (flags[q]) idx[woff + pre[q]] = (int32_t)(base + warp * 128 + q * 32 + lane);
 }
 
+// 3x3 flat grey-scale dilation (is_max) / erosion over the valid neighbours of each pixel: kornia.morphology with the
+// 'geodesic' border (the image border never wins), which raytrace_camera's hole filling uses (models/raytracer.py:554-557)
+__global__ void __launch_bounds__(256) morph3x3_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W,
+                                                       int is_max) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  int y = i / W, x = i - y * W;
+  float v = src[i];
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      int yy = y + dy, xx = x + dx;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      float u = src[yy * W + xx];
+      v = is_max ? fmaxf(v, u) : fminf(v, u);
+    }
+  dst[i] = v;
+}
+
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
                                                           int64_t M, int width, float* __restrict__ dst) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -218,5 +238,17 @@ extern "C" int ironb_scatter_rows(const float* src, const int32_t* idx, int64_t 
   IRONB_REQUIRE(src && idx && dst, "scatter_rows: null pointer");
   scatter_rows_kernel<<<(unsigned)ceil_div64(M * width, 256), 256, 0, as_stream(stream)>>>(src, idx, M, width, dst);
   IRONB_CHECK_LAUNCH("scatter_rows_kernel");
+  return IRONB_OK;
+}
+
+// closing = erosion(dilation(depth)) with a 3x3 all-ones structuring element; tmp and out are H*W floats
+extern "C" int ironb_depth_closing(const float* depth, int H, int W, float* tmp, float* out, void* stream) {
+  IRONB_REQUIRE(H > 0 && W > 0 && (int64_t)H * W < (1ll << 31), "depth_closing: bad size");
+  IRONB_REQUIRE(depth && tmp && out, "depth_closing: null pointer");
+  unsigned nb = (unsigned)ceil_div64((int64_t)H * W, 256);
+  morph3x3_kernel<<<nb, 256, 0, as_stream(stream)>>>(depth, tmp, H, W, 1);
+  IRONB_CHECK_LAUNCH("morph3x3_kernel (dilate)");
+  morph3x3_kernel<<<nb, 256, 0, as_stream(stream)>>>(tmp, out, H, W, 0);
+  IRONB_CHECK_LAUNCH("morph3x3_kernel (erode)");
   return IRONB_OK;
 }

@@ -8,8 +8,10 @@ What differs from the reference, by design:
     the module, is the primary entry.  A callable that cannot be resolved raises TypeError (no fallback).
   * no host round trip per marching iteration; hit points are compacted on the device (stable, ascending
     pixel order, like boolean-mask indexing) with ONE size read-back per shading chunk.
-  * `fill_holes` / `detect_edges` (kornia morphology + Sobel + edge walk, models/raytracer.py:554-585) are
-    rows f-1 / f-4 of SURVEY.md section 8 ("next"), not built yet: passing True raises NotImplementedError.
+  * `fill_holes` (3x3 closing of the depth map, models/raytracer.py:554-564) is built (ironb_depth_closing); kornia is
+    not installable here, so its border semantics ('geodesic') are restated from its documentation -- parity of that one
+    row is unpinned.  `detect_edges` (Sobel + edge walk, :566-585) is row f-1 of SURVEY.md section 8 ("next"): True raises
+    NotImplementedError.
 """
 from __future__ import annotations
 
@@ -256,12 +258,40 @@ def raytrace_pixels(sdf_network, raytracer, uv, camera, mask=None, max_num_rays=
 
 @torch.no_grad()
 def raytrace_camera(camera, sdf_network, raytracer, max_num_rays=200000, fill_holes=False, detect_edges=False):
-    """models/raytracer.py:542-590 without hole filling / edge detection."""
-    if fill_holes or detect_edges:
-        raise NotImplementedError("fill_holes / detect_edges are 'next' rows of the scope table (SURVEY.md 8f), not built")
+    """models/raytracer.py:542-590 with hole filling (:554-564); edge detection (:566-585) is row f-1 of the scope table
+     and is not built."""
+    if detect_edges:
+        raise NotImplementedError("detect_edges (edge sampling) is a 'next' row of the scope table (SURVEY.md 8f), not built")
     results = raytrace_pixels(sdf_network, raytracer, camera.get_uv(), camera, max_num_rays=max_num_rays)
     results["depth"] = results["depth"] * results["convergent_mask"].float()
+    if fill_holes:
+        depth = depth_closing(results["depth"])
+        new_convergent_mask = depth > 1e-2
+        update_mask = new_convergent_mask & (~results["convergent_mask"])
+        # the reference branches on update_mask.any() (a host sync); the update is a no-op when the mask is empty, except
+        # that distance/points of existing hits are then NOT re-derived from depth -- reproduce that with a device select
+        any_update = update_mask.any()
+        new_depth = torch.where(update_mask, depth, results["depth"])
+        new_distance = new_depth * results["ray_d_norm"]
+        new_points = results["ray_o"] + results["ray_d"] * new_distance.unsqueeze(-1)
+        results["depth"] = new_depth
+        results["convergent_mask"] = torch.where(any_update, new_convergent_mask, results["convergent_mask"])
+        results["distance"] = torch.where(any_update, new_distance, results["distance"])
+        results["points"] = torch.where(any_update, new_points, results["points"])
     return results
+
+
+@torch.no_grad()
+def depth_closing(depth):
+    """3x3 morphological closing of an [H,W] depth map (kornia.morphology.closing, all-ones kernel, geodesic border)."""
+    H, W = depth.shape
+    d = _lib.f32c(depth)
+    tmp = torch.empty_like(d)
+    out = torch.empty_like(d)
+    with torch.cuda.device(d.device):
+        _lib.check(_lib.load().ironb_depth_closing(_lib.ptr(d), H, W, _lib.ptr(tmp), _lib.ptr(out), _lib.stream()),
+                   "depth_closing")
+    return out
 
 
 def compact_hits(mask_flat: torch.Tensor):

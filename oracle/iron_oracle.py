@@ -642,6 +642,31 @@ def trace_pixels(p: Params, cam: OCamera, uv: Tensor, max_num_rays: int = 200000
     return out
 
 
+def morph_closing3(depth: Tensor) -> Tensor:
+    """kornia.morphology.closing(depth[None,None], ones(3,3)) restated: flat 3x3 dilation then erosion with the
+    'geodesic' border (borders never win), models/raytracer.py:555-557.  kornia is not installable in the build
+    container, so this row is restated from kornia's documentation: PARITY UNPINNED for this function."""
+    x = depth[None, None]
+    dil = torch.nn.functional.max_pool2d(x, 3, stride=1, padding=1)            # implicit -inf padding
+    ero = -torch.nn.functional.max_pool2d(-dil, 3, stride=1, padding=1)
+    return ero[0, 0]
+
+
+def fill_holes(res: Dict[str, Tensor]) -> Dict[str, Tensor]:
+    """raytrace_camera's hole filling, models/raytracer.py:552-564 (depth already masked by the hit mask)."""
+    res = dict(res)
+    res["depth"] = res["depth"] * res["convergent_mask"].float()
+    depth = morph_closing3(res["depth"])
+    new_mask = depth > 1e-2
+    upd = new_mask & (~res["convergent_mask"])
+    if upd.any():
+        res["depth"] = torch.where(upd, depth, res["depth"])
+        res["convergent_mask"] = new_mask
+        res["distance"] = res["depth"] * res["ray_d_norm"]
+        res["points"] = res["ray_o"] + res["ray_d"] * res["distance"].unsqueeze(-1)
+    return res
+
+
 # --------------------------------------------------------------------------
 # shading of hit points            models/raytracer.py:17-24, 593-662; render_surface.py:117-156
 # --------------------------------------------------------------------------

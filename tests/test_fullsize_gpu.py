@@ -1,0 +1,126 @@
+"""Full-size property tests (BASELINE configs 3 and 4: 1024x1024 forward render; 65,536-ray training step), where the
+CPU oracle is too slow to be the checker.  Size-independent properties of the domain:
+
+  * every converged ray's point lies on its ray at the reported distance, inside the unit sphere clip interval;
+  * re-evaluating the SDF at the converged points with the exact fp32 FFMA get_all gives |sdf| <= threshold for
+    sphere-tracing hits and a bracketed root (|sdf| <= |grad| * interval) for sampler/bisection hits;
+  * depth = distance / ray_d_norm, colours / normals are zero outside the hit mask, everything is finite;
+  * the two tracer implementations agree on the hit mask (>= 99.99 %) and on depth (>= 99.9 % within 1e-4);
+  * a strided subsample of rays is traced by the CPU oracle and compared directly;
+  * the training step's gradients are finite, non-zero for every tensor, and identical run to run up to the
+    atomics' summation order (relative 1e-5).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import iron_oracle as O
+from util import TOL_DEPTH, assert_close, oracle_params, perturb
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def build(H=256, sigma=0.005):
+    import iron_b200 as ib
+    torch.manual_seed(0)
+    nets = ib.init_rendering_network_dict("ggx")
+    torch.manual_seed(0)
+    sdf = ib.SDFNetwork(d_in=3, d_out=257, d_hidden=H, n_layers=8, skip_in=[4], multires=6, bias=0.5, scale=1.0,
+                        geometric_init=True, weight_norm=True)
+    perturb(sdf, sigma, seed=1)
+    sdf = sdf.to(DEV)
+    nets["point_light_network"].set_light(32.0)
+    K = torch.tensor(O.FIXTURE_K, dtype=torch.float64).reshape(4, 4).float().to(DEV)
+    W2C = torch.tensor(O.FIXTURE_W2C, dtype=torch.float64).reshape(4, 4).float().to(DEV)
+    return ib, sdf, nets, ib.Camera(512, 512, K, W2C)
+
+
+def test_full_frame_1024_forward_render():
+    ib, sdf, nets, cam512 = build()
+    lib = __import__("iron_b200")._lib.load()
+    cam, _ = cam512.resize(2.0)                                   # 1024 x 1024 = 1,048,576 rays, 50,000-ray tracer calls
+    rend = ib.GGXColocatedRenderer(use_cuda=True)
+    res = ib.render_camera(cam, sdf, ib.RayTracer(), nets, ib.make_render_fn(rend), fill_holes=False, handle_edges=False,
+                           is_training=False)
+    m = res["convergent_mask"]
+    n_hit = int(m.sum())
+    assert 0.2 * m.numel() < n_hit < 0.8 * m.numel(), n_hit
+    for k in ("points", "distance", "depth", "color", "normal", "diffuse_albedo", "specular_roughness"):
+        assert torch.isfinite(res[k]).all(), k
+    # geometry: point = o + d * t, depth = t / |d_unnormalised|
+    p = res["ray_o"] + res["ray_d"] * res["distance"].unsqueeze(-1)
+    assert float((p - res["points"])[m].abs().max()) <= 2e-6
+    assert float((res["depth"] - res["distance"] / res["ray_d_norm"])[m].abs().max()) <= 1e-6
+    assert float(res["points"][m].norm(dim=-1).max()) <= 1.0 + 1e-4
+    assert float(res["color"][~m].abs().max()) == 0.0 and float(res["normal"][~m].abs().max()) == 0.0
+    nn = res["normal"][m].norm(dim=-1)
+    assert float((nn - 1).abs().max()) <= 1e-5
+    # self-consistency: exact fp32 SDF at the converged points
+    prev = lib.ironb_set_gemm_mode(0)
+    try:
+        with torch.no_grad():
+            f = sdf.sdf(res["points"][m])[:, 0]
+    finally:
+        lib.ironb_set_gemm_mode(prev)
+    # sphere-tracing hits sit inside the +-5e-5 band (plus the tensor-core tracer's sdf error); bisection hits are
+    # bracketed within 2*thr along the ray, i.e. |sdf| <= ~1e-4
+    assert float((f.abs() <= 5e-5 + 1e-5).float().mean()) >= 0.90
+    assert float(f.abs().max()) <= 2.5e-4, float(f.abs().max())
+    # a strided subsample against the CPU oracle (one tracer call: the bisection coupling is per call, so compare
+    # masks and distances with the usual quantile statement)
+    uv = cam.get_uv()[::37, ::41].reshape(-1, 2)                  # 28 x 25 = 700 rays
+    sub = ib.raytrace_pixels(sdf, ib.RayTracer(), uv, cam)
+    ocam = O.OCamera.fixture().resize(2.0)
+    ref = O.trace_pixels(oracle_params(sdf), ocam, uv.cpu())
+    ms, mr = sub["convergent_mask"].cpu().numpy(), ref["convergent_mask"].numpy()
+    assert (ms == mr).mean() >= 0.995, (ms == mr).mean()
+    both = ms & mr
+    assert_close(sub["distance"].cpu().numpy()[both], ref["distance"].numpy()[both], TOL_DEPTH, what="distance vs oracle", frac=0.99)
+
+
+def test_tracers_agree_on_65536_rays():
+    ib, sdf, nets, cam512 = build()
+    lib = __import__("iron_b200")._lib.load()
+    cam, _, _ = cam512.crop_region(256, 256, ul_corner=(128, 128))   # BASELINE configs[3]/[4] ray set
+    out = {}
+    for mode in (0, 1):
+        prev = lib.ironb_set_trace_mode(mode)
+        try:
+            out[mode] = ib.raytrace_pixels(sdf, ib.RayTracer(), cam.get_uv(), cam, max_num_rays=50000)
+        finally:
+            lib.ironb_set_trace_mode(prev)
+    m0, m1 = out[0]["convergent_mask"], out[1]["convergent_mask"]
+    agree = float((m0 == m1).float().mean())
+    assert agree >= 0.9999, f"fused FFMA vs batched tcgen05 hit-mask agreement {agree:.5f}"
+    both = (m0 & m1)
+    d = (out[0]["distance"] - out[1]["distance"])[both].abs()
+    assert float((d <= 1e-4).float().mean()) >= 0.999, float((d <= 1e-4).float().mean())
+    assert float(d.max()) <= 2.0 / 127 * 1.5
+
+
+def test_training_step_65536_rays_properties():
+    ib, sdf, nets, cam512 = build()
+    cam, _, _ = cam512.crop_region(256, 256, ul_corner=(128, 128))
+    rend = ib.GGXColocatedRenderer(use_cuda=True)
+    rf = ib.make_render_fn(rend)
+    g = torch.Generator().manual_seed(3)
+    target = (torch.rand(256, 256, 3, generator=g) * 0.5).to(DEV)
+    eik = torch.empty(256 * 256 // 2, 3).uniform_(-1.0, 1.0, generator=g).to(DEV)
+    params = [("sdf." + k, p) for k, p in sdf.named_parameters()]
+    for nm in ("diffuse_albedo_network", "specular_albedo_network", "specular_roughness_network", "point_light_network"):
+        params += [(nm + "." + k, p) for k, p in nets[nm].named_parameters()]
+    runs = []
+    for _ in range(2):
+        for _, p in params:
+            p.grad = None
+        loss, res = ib.stage2_step(sdf, nets, ib.RayTracer(), rf, cam, target, eik)
+        runs.append((float(loss), [p.grad.clone() for _, p in params], res["convergent_mask"].clone()))
+    assert np.isfinite(runs[0][0]) and runs[0][0] > 0
+    assert torch.equal(runs[0][2], runs[1][2])                     # the tracer is deterministic
+    assert abs(runs[0][0] - runs[1][0]) <= 1e-5 * abs(runs[0][0])
+    for (name, _), g0, g1 in zip(params, runs[0][1], runs[1][1]):
+        assert torch.isfinite(g0).all(), name
+        assert float(g0.abs().sum()) > 0.0, f"{name}: zero gradient"
+        denom = float(g0.norm()) + 1e-30
+        assert float((g0 - g1).norm()) / denom <= 1e-4, (name, float((g0 - g1).norm()) / denom)   # fp32 atomics order only
