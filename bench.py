@@ -189,7 +189,7 @@ def run_reference(args):
     line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": workload_config(args, size),
+            "config": workload_config(args, args.patch),   # the arm's workload; the bounded sample actually timed is in cpu_baseline.sample
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -243,7 +243,8 @@ def workload_config(args, patch):
             "rays_per_gpu": patch * patch, "eikonal_points": patch * patch // 2,
             "sharding": "every rank traces/shades its own copy of the same crop (identical work per GPU), own target/eikonal seeds", "parallelism": f"dp{args.gpus} (rays sharded, weights replicated)",
             "l2": "256 MiB flush between steps, outside the per-step CUDA-event pairs",
-            "init": "seed-0 geometric init, light=32"}
+            "init": "seed-0 geometric init, light=32",
+            "fill_holes_and_edge_sampling": bool(getattr(args, "driver_defaults", False))}
 
 
 # ------------------------------------------------------------------------------------------ CUDA arm
@@ -319,7 +320,8 @@ def run_ours(args):
                 evs.append((e0, e1))
                 return r
             tracer.forward = timed
-        loss, res = ib.stage2_step(sdf, nets, tracer, render_fn, cam_, target_, eik_)
+        loss, res = ib.stage2_step(sdf, nets, tracer, render_fn, cam_, target_, eik_, fill_holes=args.driver_defaults,
+                                   handle_edges=args.driver_defaults)
         if time_trace:
             tracer.forward = orig
             trace_ms.append(evs)
@@ -439,6 +441,8 @@ def main():
     ap.add_argument("--hidden", type=int, default=512)
     ap.add_argument("--patch", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--driver-defaults", action="store_true",
+                    help="also run hole filling + edge sampling (the reference drivers' fill_holes=True, handle_edges=True)")
     ap.add_argument("--tracer", default="default", choices=["default", "batched", "fused"])
     ap.add_argument("--gemm", default="default", choices=["default", "tcgen05", "ffma"])
     args = ap.parse_args()

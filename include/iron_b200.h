@@ -190,6 +190,8 @@ int ironb_scatter_rows(const float* src, const int32_t* idx, int64_t M, int widt
 /* Hole filling of raytrace_camera (models/raytracer.py:554-557): 3x3 morphological closing of the [H,W] depth map
  * (kornia.morphology.closing with an all-ones kernel, geodesic border).  tmp / out: H*W floats each. */
 int ironb_depth_closing(const float* depth, int H, int W, float* tmp, float* out, void* stream);
+/* Depth-edge detector of raytrace_camera (models/raytracer.py:569): kornia.filters.sobel magnitude of the [H,W] depth map. */
+int ironb_sobel_depth(const float* depth, int H, int W, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -4,8 +4,8 @@ CUDA kernels behind the reference's Python module API.  CUDA only; there is no C
 from . import _lib
 from .fields import RenderingNetwork, SDFNetwork
 from .network_conf import (PointLightNetwork, choose_renderer, init_rendering_network_dict, init_sdf_network_dict)
-from .raytracer import (Camera, RayTracer, intersect_sphere, raytrace_camera, raytrace_pixels, render_camera,
-                        render_normal_and_color, reparam_points)
+from .raytracer import (Camera, RayTracer, intersect_sphere, locate_edge_points, raytrace_camera, raytrace_pixels,
+                        render_camera, render_edge_pixels, render_normal_and_color, reparam_points)
 from .render_fn import make_render_fn
 from .renderer_ggx import GGXColocatedRenderer
 from .rendering_func import get_materials
@@ -15,6 +15,6 @@ from .step import stage2_step
 __all__ = [
     "SDFNetwork", "RenderingNetwork", "PointLightNetwork", "GGXColocatedRenderer", "RayTracer", "Camera",
     "intersect_sphere", "raytrace_pixels", "raytrace_camera", "render_camera", "render_normal_and_color",
-    "reparam_points", "get_materials", "get_embedder", "make_render_fn", "stage2_step",
+    "reparam_points", "locate_edge_points", "render_edge_pixels", "get_materials", "get_embedder", "make_render_fn", "stage2_step",
     "init_sdf_network_dict", "init_rendering_network_dict", "choose_renderer",
 ]

@@ -69,6 +69,7 @@ _PROTOS = {
     "ironb_gather_rows": (_INT, [_P, _P, _I64, _INT, _P, _P]),
     "ironb_scatter_rows": (_INT, [_P, _P, _I64, _INT, _P, _P]),
     "ironb_depth_closing": (_INT, [_P, _INT, _INT, _P, _P, _P]),
+    "ironb_sobel_depth": (_INT, [_P, _INT, _INT, _P, _P]),
 }
 
 EXPORTS = tuple(_PROTOS)

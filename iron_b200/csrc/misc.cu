@@ -160,6 +160,25 @@ __global__ void __launch_bounds__(256) morph3x3_kernel(const float* __restrict__
   dst[i] = v;
 }
 
+// Sobel gradient magnitude of the depth map: kornia.filters.sobel (normalized 3x3 Sobel / 8 on a replicate-padded image,
+// sqrt(gx^2 + gy^2 + 1e-6)), the depth-edge detector of raytrace_camera (models/raytracer.py:569)
+__global__ void __launch_bounds__(256) sobel_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  int y = i / W, x = i - y * W;
+  float v[3][3];
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      int yy = min(max(y + dy, 0), H - 1), xx = min(max(x + dx, 0), W - 1);
+      v[dy + 1][dx + 1] = src[yy * W + xx];
+    }
+  float gx = ((v[0][2] - v[0][0]) + 2.f * (v[1][2] - v[1][0]) + (v[2][2] - v[2][0])) * 0.125f;
+  float gy = ((v[2][0] - v[0][0]) + 2.f * (v[2][1] - v[0][1]) + (v[2][2] - v[0][2])) * 0.125f;
+  dst[i] = sqrtf(gx * gx + gy * gy + 1e-6f);
+}
+
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
                                                           int64_t M, int width, float* __restrict__ dst) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -250,5 +269,13 @@ extern "C" int ironb_depth_closing(const float* depth, int H, int W, float* tmp,
   IRONB_CHECK_LAUNCH("morph3x3_kernel (dilate)");
   morph3x3_kernel<<<nb, 256, 0, as_stream(stream)>>>(tmp, out, H, W, 0);
   IRONB_CHECK_LAUNCH("morph3x3_kernel (erode)");
+  return IRONB_OK;
+}
+
+extern "C" int ironb_sobel_depth(const float* depth, int H, int W, float* out, void* stream) {
+  IRONB_REQUIRE(H > 0 && W > 0 && (int64_t)H * W < (1ll << 31), "sobel_depth: bad size");
+  IRONB_REQUIRE(depth && out, "sobel_depth: null pointer");
+  sobel_kernel<<<(unsigned)ceil_div64((int64_t)H * W, 256), 256, 0, as_stream(stream)>>>(depth, out, H, W);
+  IRONB_CHECK_LAUNCH("sobel_kernel");
   return IRONB_OK;
 }

@@ -652,6 +652,17 @@ def morph_closing3(depth: Tensor) -> Tensor:
     return ero[0, 0]
 
 
+def sobel_magnitude(depth: Tensor) -> Tensor:
+    """kornia.filters.sobel(depth[None,None]) restated (normalized=True, eps=1e-6): 3x3 Sobel derivatives / 8 on a
+    replicate-padded image, magnitude sqrt(gx^2 + gy^2 + eps).  models/raytracer.py:569.  PARITY UNPINNED (kornia is not
+    installable in the build container; restated from its documentation)."""
+    x = torch.nn.functional.pad(depth[None, None], (1, 1, 1, 1), mode="replicate")
+    kx = torch.tensor([[-1.0, 0.0, 1.0], [-2.0, 0.0, 2.0], [-1.0, 0.0, 1.0]]) / 8.0
+    gx = torch.nn.functional.conv2d(x, kx[None, None])
+    gy = torch.nn.functional.conv2d(x, kx.t()[None, None])
+    return torch.sqrt(gx * gx + gy * gy + 1e-6)[0, 0]
+
+
 def fill_holes(res: Dict[str, Tensor]) -> Dict[str, Tensor]:
     """raytrace_camera's hole filling, models/raytracer.py:552-564 (depth already masked by the hit mask)."""
     res = dict(res)
@@ -721,33 +732,172 @@ def shade_hits(sdf_p: Params, nets: Dict[str, Params], light: Tensor, res: Dict[
 
 
 # --------------------------------------------------------------------------
+# edge sampling (row f-1)         models/raytracer.py:412-539, 566-585, 665-775
+# --------------------------------------------------------------------------
+
+
+def project(cam: OCamera, pts: Tensor) -> Tensor:
+    """Camera.project, models/raytracer.py:305-325."""
+    p = torch.cat([pts.reshape(-1, 3), torch.ones(pts.numel() // 3, 1)], dim=1)
+    uv = torch.matmul(torch.matmul(p, cam.W2C.t()), cam.K.t())
+    return (uv[:, :2] / uv[:, 2:3]).reshape(list(pts.shape[:-1]) + [2])
+
+
+def first_unique(x: Tensor):
+    """`unique` of models/raytracer.py:412-419: sorted unique values and the index of each value's FIRST occurrence."""
+    uniq, inv = torch.unique(x, return_inverse=True)
+    first = torch.full((uniq.numel(),), x.numel(), dtype=torch.long).scatter_reduce(0, inv, torch.arange(x.numel()), "amin")
+    return uniq, first
+
+
+@torch.no_grad()
+def locate_edge_points(sdf_p: Params, cam: OCamera, start: Tensor, mask: Tensor, max_step=16, step_size=1e-3,
+                       dot_threshold=5e-2, **sdf_kw) -> Dict[str, Tensor]:
+    """models/raytracer.py:422-539: walk along the surface towards the silhouette (|n.v| <= dot_threshold)."""
+    H, W = cam.H, cam.W
+    finish = start.clone()
+    found = mask.clone()
+    if mask.any():
+        cur = start[mask].clone().reshape(-1, 3)
+        fnd = torch.zeros(cur.shape[0], dtype=torch.bool)
+        nf = ~fnd
+        o = cam.C2W[:3, 3]
+        i = 0
+        while True:
+            v = o[None] - cur[nf]
+            v = v / (v.norm(dim=-1, keepdim=True) + 1e-10)
+            f, _, n = sdf_get_all(sdf_p, cur[nf].reshape(-1, 3), is_training=False, **sdf_kw)
+            n = n / (n.norm(dim=-1, keepdim=True) + 1e-10)
+            dot = (n * v).sum(dim=-1)
+            still = dot.abs() > dot_threshold
+            fnd[nf] = ~still
+            nf_new = ~fnd
+            if i >= max_step or nf_new.sum() == 0:
+                nf = nf_new
+                break
+            walk = n - v / dot.unsqueeze(-1)
+            walk = walk / (walk.norm(dim=-1, keepdim=True) + 1e-10)
+            walk = walk - f * n
+            cur[nf_new] += (step_size * walk)[still]
+            nf = nf_new
+            i += 1
+        finish[mask] = cur
+        found[mask] = fnd
+    pts = finish[found]
+    edge_mask = torch.zeros(H, W, dtype=torch.bool)
+    edge_uv = torch.zeros(pts.shape[0], 2)
+    pix = torch.zeros(0, dtype=torch.long)
+    if found.any():
+        edge_uv = project(cam, pts)
+        pix = torch.floor(edge_uv).long()
+        pix = pix[:, 1] * W + pix[:, 0]
+        ok = (pix < H * W) & (pix >= 0)
+        pix, pts, edge_uv = pix[ok], pts[ok], edge_uv[ok]
+        if ok.any():
+            pix, first = first_unique(pix)
+            pts, edge_uv = pts[first], edge_uv[first]
+            edge_mask.view(-1)[pix] = True
+    return {"edge_mask": edge_mask, "edge_points": pts, "edge_uv": edge_uv, "edge_pixel_idx": pix}
+
+
+@torch.no_grad()
+def trace_camera(sdf_p: Params, cam: OCamera, max_num_rays=200000, do_fill_holes=False, detect_edges=False,
+                 stats: Optional[TraceStats] = None, **sdf_kw) -> Dict[str, Tensor]:
+    """raytrace_camera, models/raytracer.py:542-590."""
+    res = trace_pixels(sdf_p, cam, cam.pixel_uv(), max_num_rays=max_num_rays, stats=stats, **sdf_kw)
+    res["depth"] = res["depth"] * res["convergent_mask"].float()
+    if do_fill_holes:
+        res = fill_holes(res)
+    if detect_edges:
+        gnorm = sobel_magnitude(res["depth"])
+        emask = (gnorm > 1e-2) & res["convergent_mask"]
+        res.update(locate_edge_points(sdf_p, cam, res["points"], emask, max_step=16, step_size=1e-3, dot_threshold=5e-2, **sdf_kw))
+        res["convergent_mask"] = res["convergent_mask"] & ~res["edge_mask"]
+    return res
+
+
+def render_edge_pixels(sdf_p: Params, nets: Dict[str, Params], light: Tensor, cam: OCamera, res: Dict[str, Tensor],
+                       is_training: bool, **sdf_kw) -> None:
+    """models/raytracer.py:665-727: blend the colours of two sub-pixel rays on either side of the located edge."""
+    pts, uv, pix = res["edge_points"], res["edge_uv"], res["edge_pixel_idx"]
+    centre = torch.floor(uv) + 0.5
+    f, _, g = sdf_get_all(sdf_p, pts, is_training=is_training, **sdf_kw)
+    n = g.detach() / (g.detach().norm(dim=-1, keepdim=True) + 1e-10)
+    if is_training:
+        pts = reparam_points(pts, g.detach(), n, f)
+        uv = project(cam, pts)
+    n2 = torch.matmul(n, cam.W2C[:3, :3].t())[:, :2]
+    n2 = n2 / (n2.norm(dim=-1, keepdim=True) + 1e-10)
+    radius = 0.707
+    pos_uv = centre - radius * n2
+    neg_uv = centre + radius * n2
+    dot2 = torch.sum((uv - centre) * n2, dim=-1)
+    alpha = 2 * torch.arccos(torch.clamp(dot2 / radius, min=0.0, max=1.0))
+    w_pos = 1.0 - (alpha - torch.sin(alpha)) / (2.0 * np.pi)
+    sides = []
+    for suv in (pos_uv, neg_uv):
+        r = trace_pixels(sdf_p, cam, suv, **sdf_kw)
+        r.update(shade_hits(sdf_p, nets, light, r, is_training=is_training, **sdf_kw))
+        sides.append(r)
+    edge_color = sides[0]["color"] * w_pos.unsqueeze(-1) + sides[1]["color"] * (1.0 - w_pos.unsqueeze(-1))
+    color = res["color"].reshape(-1, 3).clone()
+    color[pix] = edge_color
+    res["color"] = color.reshape(res["color"].shape)
+    normal = res["normal"].reshape(-1, 3).clone()
+    normal[pix] = g
+    res["normal"] = normal.reshape(res["normal"].shape)
+    res["edge_pos_neg_normal"] = torch.cat([sides[0]["normal"][sides[0]["convergent_mask"]],
+                                            sides[1]["normal"][sides[1]["convergent_mask"]]], dim=0)
+    res["uv"] = res["uv"].clone()
+    res["uv"].view(-1, 2)[pix] = uv.detach()
+    res["points"] = res["points"].clone()
+    res["points"].view(-1, 3)[pix] = pts.detach()
+
+
+def render_camera(sdf_p: Params, nets: Dict[str, Params], light: Tensor, cam: OCamera, do_fill_holes=False,
+                  handle_edges=True, is_training=False, stats: Optional[TraceStats] = None, **sdf_kw) -> Dict[str, Tensor]:
+    """models/raytracer.py:778-814."""
+    res = trace_camera(sdf_p, cam, max_num_rays=50000, do_fill_holes=do_fill_holes, detect_edges=handle_edges, stats=stats, **sdf_kw)
+    res.update(shade_hits(sdf_p, nets, light, res, is_training=is_training, **sdf_kw))
+    if handle_edges and res["edge_mask"].sum() > 0:
+        render_edge_pixels(sdf_p, nets, light, cam, res, is_training, **sdf_kw)
+    return res
+
+
+# --------------------------------------------------------------------------
 # one stage-2 step (the unit bench.py counts)       render_surface.py:533-653, BASELINE.md section 3
 # --------------------------------------------------------------------------
 
 
 def stage2_step(sdf_p: Params, nets: Dict[str, Params], light: Tensor, cam: OCamera, target: Tensor,
                 eik_points: Tensor, eik_weight: float = 0.1, stats: Optional[TraceStats] = None,
-                max_num_rays: int = 50000, **sdf_kw):
-    """trace -> shade(is_training) -> L2 image loss + eik_weight * eikonal(random pts + hit normals)
-    -> backward.  fill_holes / edge sampling / SSIM / pyramid are outside the section-8 scope (rows f-1..f-4).
+                max_num_rays: int = 50000, do_fill_holes: bool = False, handle_edges: bool = False, **sdf_kw):
+    """render_camera(is_training) -> L2 image loss + eik_weight * eikonal(random pts + hit normals [+ edge normals])
+    -> backward.  SSIM / pyramid losses are outside the section-8 scope (row f-3).  With do_fill_holes / handle_edges the
+    step is the drivers' default configuration (render_surface.py:541-549, 566-567, 601-607).
 
     The `normal` buffer holds the *normalised* normal (render_surface.py:146), so the hit-normal eikonal
     term is ~0 exactly as in the reference (render_surface.py:601-603).
     Gradients are left in `.grad` of every tensor in sdf_p / nets / light that requires grad.
     """
-    res = trace_pixels(sdf_p, cam, cam.pixel_uv(), max_num_rays=max_num_rays, stats=stats, **sdf_kw)
-    shaded = shade_hits(sdf_p, nets, light, res, is_training=True, **sdf_kw)
+    res = render_camera(sdf_p, nets, light, cam, do_fill_holes=do_fill_holes, handle_edges=handle_edges, is_training=True,
+                        stats=stats, **sdf_kw)
     mask = res["convergent_mask"]
+    if handle_edges:
+        mask = mask | res["edge_mask"]
     eg = sdf_gradient(sdf_p, eik_points, **sdf_kw).view(-1, 3)
     eik_cnt = eg.shape[0]
     eik = ((eg.norm(dim=-1) - 1) ** 2).sum()
     img = torch.zeros(())
     if mask.any():
-        img = ((shaded["color"] - target) ** 2).sum() / float(mask.numel())
-        hn = shaded["normal"][mask]
+        img = ((res["color"] - target) ** 2).sum() / float(mask.numel())
+        hn = res["normal"][mask]
         eik_cnt += hn.shape[0]
         eik = eik + ((hn.norm(dim=-1) - 1) ** 2).sum()
+        if "edge_pos_neg_normal" in res:
+            en = res["edge_pos_neg_normal"]
+            eik_cnt += en.shape[0]
+            eik = eik + ((en.norm(dim=-1) - 1) ** 2).sum()
     loss = img + eik / eik_cnt * eik_weight
     loss.backward()
-    res.update(shaded)
     return loss.detach(), res

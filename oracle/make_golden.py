@@ -30,6 +30,14 @@ def import_reference():
                 m.ic = lambda *a, **k: None
             if name == "turtle":
                 m.update = lambda *a, **k: None
+            if name == "kornia":
+                # kornia cannot be installed here.  The two calls the hot path's "next" rows make are restated from
+                # kornia's documentation (oracle/iron_oracle.py: morph_closing3, sobel_magnitude) -- those two functions are
+                # therefore UNPINNED; everything around them (edge walk, sub-pixel blending, hole update) is the reference's.
+                sys.path.insert(0, os.path.join(HERE, ".."))
+                from oracle import iron_oracle as _O
+                m.morphology = types.SimpleNamespace(closing=lambda x, kernel: _O.morph_closing3(x[0, 0])[None, None])
+                m.filters = types.SimpleNamespace(sobel=lambda x: _O.sobel_magnitude(x[0, 0])[None, None])
             sys.modules[name] = m
     if REF not in sys.path:
         sys.path.insert(0, REF)
@@ -289,6 +297,39 @@ def main():
             out["g." + k] = gr_.numpy()
     np.savez_compressed(os.path.join(OUT, "step_h256.npz"), **out)
     print("step_h256.npz  hits", int(mask.sum()), "loss", float(loss))
+
+    # ---------------- 7. stage-2 step WITH hole filling and edge sampling (the drivers' default), 32x32 silhouette crop -----
+    for p_ in [p for _, p in allp]:
+        p_.grad = None
+    results = raytracer.render_camera(cam, sdf_net, rt, nets, render_fn, fill_holes=True, handle_edges=True, is_training=True)
+    mask = results["convergent_mask"] | results["edge_mask"]
+    eg = sdf_net.gradient(eik_pts.clone()).view(-1, 3)
+    eik_cnt = eg.shape[0]
+    eik = ((eg.norm(dim=-1) - 1) ** 2).sum()
+    img = ((results["color"] - tgt) ** 2).sum() / float(mask.numel())
+    hn = results["normal"][mask]
+    eik_cnt += hn.shape[0]
+    eik = eik + ((hn.norm(dim=-1) - 1) ** 2).sum()
+    en = results["edge_pos_neg_normal"]
+    eik_cnt += en.shape[0]
+    eik = eik + ((en.norm(dim=-1) - 1) ** 2).sum()
+    loss = img + eik / eik_cnt * 0.1
+    loss.backward()
+    out = dict(ul=np.array((448, 230)), target=tgt.numpy(), eik_points=eik_pts.numpy(), loss=loss.detach().numpy(),
+               mask=results["convergent_mask"].numpy(), edge_mask=results["edge_mask"].numpy(),
+               edge_pixel_idx=results["edge_pixel_idx"].numpy(), edge_uv=results["edge_uv"].detach().numpy(),
+               edge_points=results["edge_points"].detach().numpy(), n_edge_normals=np.array(en.shape[0]))
+    for k in ("color", "normal", "points", "distance", "depth", "uv"):
+        out["res." + k] = results[k].detach().numpy()
+    for k, p_ in allp:
+        gr_ = p_.grad
+        out["gsum." + k] = np.array([gr_.double().sum().item(), gr_.double().abs().sum().item(),
+                                     gr_.double().pow(2).sum().sqrt().item()])
+        if gr_.numel() <= 1024 or k.endswith("lin8.weight_v") or k.endswith("lin0.weight_v"):
+            out["g." + k] = gr_.numpy()
+    np.savez_compressed(os.path.join(OUT, "step_edges_h256.npz"), **out)
+    print("step_edges_h256.npz  hits", int(results["convergent_mask"].sum()), "edge pixels", int(results["edge_mask"].sum()),
+          "loss", float(loss))
 
 
 if __name__ == "__main__":

@@ -198,3 +198,37 @@ def test_full_step(golden):
         if "g." + k in g:
             ref = g["g." + k]
             close(v.grad.numpy(), ref, 1e-4 * np.abs(ref).max(), 1e-3)
+
+
+def test_step_with_edges_golden(golden):
+    """The drivers' default step (fill_holes + edge sampling): oracle vs the real reference's render_camera.  The two kornia
+    calls are shared restatements (unpinned); the edge walk, uniqueness, sub-pixel blending and their gradients are pinned."""
+    import torch
+    g = golden("step_edges_h256")
+    torch.manual_seed(0)
+    mats = O.make_material_dict()
+    torch.manual_seed(0)
+    sdf = O.make_sdf_params(d_hidden=256)
+    gen = torch.Generator().manual_seed(1)
+    for l in range(1, 8):
+        v = sdf[f"lin{l}.weight_v"]
+        v.add_(torch.randn(v.shape, generator=gen) * 0.005)
+    for d in [sdf] + list(mats.values()):
+        for v in d.values():
+            v.requires_grad_(True)
+    light = torch.tensor(32.0, requires_grad=True)
+    cam = O.OCamera.fixture().crop(32, 32, tuple(int(v) for v in g["ul"]))
+    loss, res = O.stage2_step(sdf, mats, light, cam, T(g["target"]), T(g["eik_points"]), do_fill_holes=True, handle_edges=True)
+    assert (res["convergent_mask"].numpy() == g["mask"]).all()
+    assert (res["edge_mask"].numpy() == g["edge_mask"]).all()
+    assert (res["edge_pixel_idx"].numpy() == g["edge_pixel_idx"]).all()
+    close(res["edge_uv"].detach().numpy(), g["edge_uv"], 2e-4)
+    close(res["color"].detach().numpy(), g["res.color"], 2e-5, 1e-4)
+    close(res["normal"].detach().numpy(), g["res.normal"], 2e-5, 1e-4)
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert res["edge_pos_neg_normal"].shape[0] == int(g["n_edge_normals"])
+    for k, v in sdf.items():
+        ref = g["gsum.sdf." + k]
+        got = v.grad.double().pow(2).sum().sqrt().item()
+        assert abs(got - ref[2]) <= 2e-3 * ref[2] + 1e-9, (k, got, ref[2])
+    assert abs(light.grad.item() - g["g.point_light_network.light"]) <= 1e-4 * abs(g["g.point_light_network.light"])

@@ -94,3 +94,40 @@ def test_render_camera_inference(golden, gemm_mode):
     assert_close(res["color"].cpu().numpy()[both], g["res.color"][both], TOL_RGB, 1e-3, what="color", frac=0.995)
     assert res["color"].shape == (32, 32, 3) and res["specular_roughness"].shape == (32, 32)
     assert float(res["color"][~res["convergent_mask"]].abs().max()) == 0.0
+
+
+def test_step_with_edges_golden(golden, trace_mode):
+    """The reference drivers' default step: render_camera(fill_holes=True, handle_edges=True, is_training=True) + loss +
+    backward, against the golden step produced by the real reference (kornia's closing / sobel shared as restatements)."""
+    g = golden("step_edges_h256")
+    ib, sdf, nets, cam512 = build()
+    cam, _, _ = cam512.crop_region(32, 32, ul_corner=tuple(int(v) for v in g["ul"]))
+    rend = ib.GGXColocatedRenderer(use_cuda=True)
+    loss, res = ib.stage2_step(sdf, nets, ib.RayTracer(), ib.make_render_fn(rend), cam, T(g["target"]).to(DEV),
+                               T(g["eik_points"]).to(DEV), eik_weight=0.1, fill_holes=True, handle_edges=True)
+    m, em = res["convergent_mask"].cpu().numpy(), res["edge_mask"].cpu().numpy()
+    mr, emr = g["mask"], g["edge_mask"]
+    print(f"[{trace_mode}] hits {int(m.sum())}/{int(mr.sum())}  edge pixels {int(em.sum())}/{int(emr.sum())}  "
+          f"mask agree {(m == mr).mean():.4f}  edge-mask agree {(em == emr).mean():.4f}  loss {float(loss):.6f}/{float(g['loss']):.6f}")
+    assert (m == mr).mean() >= 0.995 and (em == emr).mean() >= 0.995
+    same = bool((m == mr).all() and (em == emr).all())
+    got_pix = set(res["edge_pixel_idx"].cpu().numpy().tolist())
+    ref_pix = set(g["edge_pixel_idx"].tolist())
+    assert len(got_pix & ref_pix) >= 0.9 * len(ref_pix)
+    both = (m | em) & (mr | emr) & (em == emr)
+    assert_close(res["color"].detach().cpu().numpy()[both], g["res.color"][both], TOL_RGB, 1e-3, what="color", frac=0.98)
+    if same:   # edge point order is then identical: sub-pixel positions must match
+        assert_close(res["edge_uv"].detach().cpu().numpy(), g["edge_uv"], 5e-3, what="edge_uv", frac=0.95)
+    assert abs(float(loss) - float(g["loss"])) <= (2e-3 if same else 3e-2) * abs(float(g["loss"]))
+    tol = 5e-3 if same else 6e-2     # silhouette-localised terms amplify the tracer's sub-1e-4 depth differences
+    named = [("sdf." + k, p) for k, p in sdf.named_parameters()]
+    for nm in ("diffuse_albedo_network", "specular_albedo_network", "specular_roughness_network", "point_light_network"):
+        named += [(nm + "." + k, p) for k, p in nets[nm].named_parameters()]
+    worst = 0.0
+    for k, p in named:
+        gr = p.grad.double().cpu()
+        ref = g["gsum." + k]
+        e = abs(gr.pow(2).sum().sqrt().item() - ref[2]) / max(ref[2], 1e-12)
+        worst = max(worst, e)
+        assert e <= tol, (k, e, same)
+    print(f"[{trace_mode}] step+edges parity: identical masks={same}, worst gradient-norm error {worst:.2e}")
