@@ -71,8 +71,9 @@ int64_t ironb_launch_count(void);
  * 1 = tcgen05 3xTF32 split (tensor cores, fp32-grade accuracy; the default), 0 = fp32 FFMA tiles.
  * Returns the previous mode.  The environment variable IRONB_GEMM=simt selects 0 at start-up. */
 int ironb_set_gemm_mode(int mode);
-/* Tracer implementation: 1 = batched tcgen05 rounds (default), 0 = fused persistent fp32-FFMA kernels.
- * Returns the previous mode.  IRONB_TRACE=fused selects 0 at start-up. */
+/* Tracer implementation: 2 = batched tcgen05 rounds, fp16x2-split operands (default); 1 = batched tcgen05 rounds,
+ * 3xTF32 operands; 0 = fused persistent fp32-FFMA kernels.  Returns the previous mode.
+ * IRONB_TRACE=fused / tf32 selects 0 / 1 at start-up. */
 int ironb_set_trace_mode(int mode);
 /* C[M][ldc] = A[M][lda] * B[N][ldb]^T (fp32, K-major operands, N/K/ld multiples of 4): unit-test entry of both GEMMs. */
 int ironb_gemm_nt(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float* C, int ldc,

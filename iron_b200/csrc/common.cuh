@@ -47,7 +47,7 @@ __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b *
 int num_sms();
 
 // tracer implementations (trace.cu: fused persistent FFMA; trace_batched.cu: batched tcgen05)
-int trace_mode();   // 1 = batched tcgen05 (default), 0 = fused FFMA
+int trace_mode();   // 2 = batched tcgen05 fp16x2 split (default), 1 = batched tcgen05 3xTF32, 0 = fused FFMA
 bool trace_mlp_fused_supported(const ironb_mlp_layout* lay);   // shapes the tcgen05 tracer handles (else: FFMA tracer)
 int64_t trace_batched_workspace_bytes(const ironb_mlp_layout* lay, int64_t N);
 int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float* ray_o, const float* ray_d,

@@ -42,6 +42,25 @@ int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld) {
   return IRONB_OK;
 }
 
+// rows x K fp16 matrix with row pitch ld halfs -> 2-D map with a (64 x 128) SWIZZLE_128B box (mlp_h16.cu operands)
+int make_map_h(CUtensorMap* map, const void* ptr, int rows, int K, int ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("tcgen05 mlp: cuTensorMapEncodeTiled is unavailable"); return IRONB_ENOSUP; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) || (ld & 7) || K <= 0 || rows <= 0) {
+    set_error("tcgen05 mlp: fp16 operand must be 16-byte aligned with a row pitch that is a multiple of 8 halfs");
+    return IRONB_EINVAL;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2u};
+  cuuint32_t box[2] = {64u, 128u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("tcgen05 mlp: cuTensorMapEncodeTiled(fp16) failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld); return IRONB_EINVAL; }
+  return IRONB_OK;
+}
+
 static std::atomic<int> g_mode{-1};
 bool tc_enabled() {
   int m = g_mode.load(std::memory_order_relaxed);

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) split_array_kernel(const float* __restric
 
 }  // namespace mlp
 
-static long long* g_dbg = nullptr;
+long long* g_mlp_dbg = nullptr;   // shared with mlp_h16.cu
 
 bool trace_mlp_fused_supported(const ironb_mlp_layout* lay) {
   const int H = lay->d_hidden, C = H / 128;
@@ -323,7 +323,7 @@ int launch_trace_mlp_fused(const ironb_mlp_layout* lay, const float* packed, con
   a.n_hidden = last; a.skip_layer = lay->skip_layer; a.Epad = lay->in_pad[0]; a.Edim = lay->pe_dim; a.H = H;
   a.beta = lay->beta; a.inv_beta = 1.0f / lay->beta;
   a.m_dev = m_dev; a.m_mul = m_mul; a.rows_cap = rows_cap; a.cap = cap;
-  a.dbg = g_dbg;
+  a.dbg = g_mlp_dbg;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -354,11 +354,11 @@ int launch_trace_mlp_fused(const ironb_mlp_layout* lay, const float* packed, con
 
 // debugging aid: IRONB_MLP_DBG timeline of the fused MLP kernel (cluster 0, rank 0, first tile), 8 stamps per layer
 extern "C" int ironb_debug_mlp_timeline(long long* host_out, int n) {
-  if (ironb::g_dbg == nullptr) {
-    if (cudaMalloc(&ironb::g_dbg, 64 * 8 * sizeof(long long)) != cudaSuccess) return -1;
-    cudaMemset(ironb::g_dbg, 0, 64 * 8 * sizeof(long long));
+  if (ironb::g_mlp_dbg == nullptr) {
+    if (cudaMalloc(&ironb::g_mlp_dbg, 64 * 8 * sizeof(long long)) != cudaSuccess) return -1;
+    cudaMemset(ironb::g_mlp_dbg, 0, 64 * 8 * sizeof(long long));
     return 0;
   }
-  if (host_out && n > 0) cudaMemcpy(host_out, ironb::g_dbg, (size_t)(n < 512 ? n : 512) * sizeof(long long), cudaMemcpyDeviceToHost);
+  if (host_out && n > 0) cudaMemcpy(host_out, ironb::g_mlp_dbg, (size_t)(n < 512 ? n : 512) * sizeof(long long), cudaMemcpyDeviceToHost);
   return 1;
 }

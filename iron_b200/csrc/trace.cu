@@ -511,7 +511,7 @@ using namespace ironb;
 extern "C" int64_t ironb_trace_workspace_bytes(const ironb_mlp_layout* lay, int64_t N) {
   if (N < 0 || !lay) return -1;
   int64_t fused = carve_trace(N, nullptr).bytes;
-  int64_t batched = (trace_mode() == 1 && trace_mlp_fused_supported(lay)) ? trace_batched_workspace_bytes(lay, N) : 0;
+  int64_t batched = (trace_mode() >= 1 && trace_mlp_fused_supported(lay)) ? trace_batched_workspace_bytes(lay, N) : 0;
   return fused > batched ? fused : batched;
 }
 
@@ -532,7 +532,7 @@ extern "C" int ironb_trace(const ironb_mlp_layout* lay, const float* packed, con
     return IRONB_ENOSUP;
   }
   if (lay->in_pad[0] > 64) { set_error("trace: encoding width %d > 64", lay->in_pad[0]); return IRONB_ENOSUP; }
-  if (trace_mode() == 1 && trace_mlp_fused_supported(lay))
+  if (trace_mode() >= 1 && trace_mlp_fused_supported(lay))
     return trace_batched(lay, packed, ray_o, ray_d, min_dis, max_dis, work_mask, N, sdf_threshold, sphere_tracing_iters,
                          n_steps, linspace, conv, points, sdf, dist, stats, ws, ws_bytes, as_stream(stream));
   const int last = lay->n_lin - 1;

@@ -18,6 +18,8 @@
 
 #include <atomic>
 
+#include <cuda_fp16.h>
+
 #include "gemm_tc.cuh"
 
 namespace ironb {
@@ -27,6 +29,11 @@ int split_weights(const float* src, int64_t n, float* hi, float* lo, cudaStream_
 int launch_trace_mlp_fused(const ironb_mlp_layout* lay, const float* packed, const CUtensorMap* mE, const CUtensorMap* mU,
                            const CUtensorMap* mW, const float* Ehi, const float* Elo, float* const* Uhi, float* const* Ulo,
                            float* Fpart, int rows_cap, int cap, const int* m_dev, int m_mul, cudaStream_t st);
+// fp16x2-split version (mlp_h16.cu): operands are fp16 hi and fp16 (x - hi) * 2^11
+int split_weights_h(const float* src, int64_t n, void* hi, void* lo, cudaStream_t st);
+int launch_trace_mlp_h16(const ironb_mlp_layout* lay, const float* packed, const CUtensorMap* mE, const CUtensorMap* mU,
+                         const CUtensorMap* mW, const void* Ehi, const void* Elo, float* Fpart, int rows_cap, int cap,
+                         const int* m_dev, int m_mul, cudaStream_t st);
 
 namespace {
 
@@ -51,7 +58,8 @@ struct BArgs {
   int* unf_list; float *smin, *smax, *prev_f, *prev_t;   // per unfinished ray
   int* glist[2];                // sampler group -> unfinished-ray index
   int* root_ray; float *root_lo, *root_hi, *root_mid; int* root_work;
-  float* Ehi; float* Elo;       // [CAP][Epad] encoded points, already split into tf32-exact hi / lo (the MLP's A operand)
+  float* Ehi; float* Elo;       // [CAP][Epad] encoded points, already split into hi / lo (the MLP's A operand):
+  int f16;                      // 0: tf32-exact fp32 pairs (mlp_tc.cu); 1: fp16 hi and fp16 (x - hi) * 2^11 (mlp_h16.cu)
   const float* Fpart;           // [nparts][cap] partial sums of the sdf row, written by the fused MLP kernel
   const float* b_last;
   int nparts, cap;
@@ -64,14 +72,21 @@ constexpr int C_SG = 8;      // 8..10 rotating group counts (sampler)
 constexpr int C_BR = 16;     // 16.. row count of bisection round j (0 = nobody works any more)
 constexpr int NCOUNTERS = 64;
 
+template <bool F16>
 __device__ __forceinline__ void put_split(float* __restrict__ ehi, float* __restrict__ elo, int i, float v) {
-  float h, l;
-  tc::split1(v, h, l);
-  ehi[i] = h;
-  elo[i] = l;
+  if (F16) {
+    const __half h = __float2half_rn(v);
+    reinterpret_cast<__half*>(ehi)[i] = h;
+    reinterpret_cast<__half*>(elo)[i] = __float2half_rn((v - __half2float(h)) * 2048.f);
+  } else {
+    float h, l;
+    tc::split1(v, h, l);
+    ehi[i] = h;
+    elo[i] = l;
+  }
 }
 struct BArgs;
-__device__ __forceinline__ void write_pe(const BArgs& A, size_t row, const float x[3]);
+__device__ __forceinline__ void write_pe(const BArgs& A, size_t row, const float x[3], int part);
 
 // sdf of work item i: either the sdf-row GEMM's output, or the fused MLP's partial sums added in a fixed order
 __device__ __forceinline__ float read_f(const BArgs& A, size_t i) {
@@ -81,27 +96,35 @@ __device__ __forceinline__ float read_f(const BArgs& A, size_t i) {
 }
 
 // encoded point of work item `row`, written as the split A operand of the MLP's first layer
-__device__ __forceinline__ void write_pe(const BArgs& A, size_t row, const float x[3]) {
-  float* __restrict__ ehi = A.Ehi + row * A.Epad;
-  float* __restrict__ elo = A.Elo + row * A.Epad;
+template <bool F16>
+__device__ __forceinline__ void write_pe_t(const BArgs& A, size_t row, const float x[3], int part) {
+  // row pitch: Epad elements of 4 (fp32 pairs) or 2 (fp16 pairs) bytes
+  float* __restrict__ ehi = F16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(A.Ehi) + row * A.Epad) : A.Ehi + row * A.Epad;
+  float* __restrict__ elo = F16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(A.Elo) + row * A.Epad) : A.Elo + row * A.Epad;
   const float xs[3] = {x[0] * A.scale, x[1] * A.scale, x[2] * A.scale};
-  put_split(ehi, elo, 0, xs[0]); put_split(ehi, elo, 1, xs[1]); put_split(ehi, elo, 2, xs[2]);
-  int w = 3;
-  float f = 1.f;
-  for (int k = 0; k < A.multires; ++k) {
+  if (part < 0 || part == A.multires) {                 // the raw coordinates and the zero padding
+    put_split<F16>(ehi, elo, 0, xs[0]); put_split<F16>(ehi, elo, 1, xs[1]); put_split<F16>(ehi, elo, 2, xs[2]);
+    for (int w = 3 + 6 * A.multires; w < A.Epad; ++w) put_split<F16>(ehi, elo, w, 0.f);
+  }
+  const int k0 = part < 0 ? 0 : part, k1 = part < 0 ? A.multires : min(part + 1, A.multires);
+  for (int k = k0; k < k1; ++k) {                       // frequency 2^k: sin block then cos block (embedder.py:25-33)
+    const float f = (float)(1 << k);
+    const int w = 3 + 6 * k;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float sn, co;
       sincosf(xs[c] * f, &sn, &co);
-      put_split(ehi, elo, w + c, sn);
-      put_split(ehi, elo, w + 3 + c, co);
+      put_split<F16>(ehi, elo, w + c, sn);
+      put_split<F16>(ehi, elo, w + 3 + c, co);
     }
-    w += 6;
-    f *= 2.f;
   }
-  for (; w < A.Epad; ++w) { ehi[w] = 0.f; elo[w] = 0.f; }
 }
-
+// part < 0: the whole encoding by one thread; part in [0, 8): thread `part` of the 8 that share a work item writes
+// frequency `part` (part == multires: the raw coordinates + padding), so the dependent sincos chain per thread is 3 long
+__device__ __forceinline__ void write_pe(const BArgs& A, size_t row, const float x[3], int part = -1) {
+  if (A.f16) write_pe_t<true>(A, row, x, part);
+  else write_pe_t<false>(A, row, x, part);
+}
 __device__ __forceinline__ void ray_point(const BArgs& A, int r, float t, float x[3]) {
 #pragma unroll
   for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(A.ray_o[(size_t)r * 3 + c], __fmul_rn(A.ray_d[(size_t)r * 3 + c], t));
@@ -112,23 +135,32 @@ __device__ __forceinline__ void write_miss(const BArgs& A, int r) {   // raytrac
 }
 
 // ---------------------------------------------------------------- sphere tracing (:105-140)
+// The per-ray kernels run 8 threads per work item (PE_T): all 8 compute the (cheap) state update redundantly, thread 0 of
+// the group owns the state writes and the atomics, and each thread writes one frequency band of the next encoded point.
+constexpr int PE_T = 8;
+
 __global__ void __launch_bounds__(256) st_init_kernel(BArgs A) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) { A.c[C_ST] = A.N; A.c[C_ST + 1] = 0; A.c[C_ST + 2] = 0; }
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = tid / PE_T, part = tid % PE_T;
+  if (tid == 0) { A.c[C_ST] = A.N; A.c[C_ST + 1] = 0; A.c[C_ST + 2] = 0; }
   if (i >= A.N) return;
   float t = A.min_dis[i], x[3];
   ray_point(A, i, t, x);                                           // :109
-  A.t[i] = t; A.k[i] = 0; A.flags[i] = A.work_mask[i] ? 3 : 0;
-  A.x[(size_t)i * 3] = x[0]; A.x[(size_t)i * 3 + 1] = x[1]; A.x[(size_t)i * 3 + 2] = x[2];
-  A.list[0][i] = i;
-  write_pe(A, (size_t)i, x);
+  if (part == 0) {
+    A.t[i] = t; A.k[i] = 0; A.flags[i] = A.work_mask[i] ? 3 : 0;
+    A.x[(size_t)i * 3] = x[0]; A.x[(size_t)i * 3 + 1] = x[1]; A.x[(size_t)i * 3 + 2] = x[2];
+    A.list[0][i] = i;
+  }
+  write_pe(A, (size_t)i, x, part);
 }
 
 __global__ void __launch_bounds__(256) st_update_kernel(BArgs A, int round) {
   const int cur = C_ST + round % 3, nxt = C_ST + (round + 1) % 3, clr = C_ST + (round + 2) % 3;
   const int rows = A.c[cur];
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = tid / PE_T, part = tid % PE_T;
+  const unsigned gmask = 0xffu << (threadIdx.x & 24);              // the 8 lanes of this work item
+  if (tid == 0) {
     A.c[clr] = 0;
     if (A.stats && rows > 0) { atomicAdd(A.stats + 0, (unsigned long long)rows); atomicAdd(A.stats + 6, (unsigned long long)((rows + 127) / 128)); }
   }
@@ -143,7 +175,9 @@ __global__ void __launch_bounds__(256) st_update_kernel(BArgs A, int round) {
   unf = unf && (fabsf(f) > A.thr) && (t < tmax);                   // :113-116
   float x[3] = {A.x[(size_t)r * 3], A.x[(size_t)r * 3 + 1], A.x[(size_t)r * 3 + 2]};
   const int k = A.k[r];
+  __syncwarp(gmask);                                               // every lane of the item has read the state
   if (k == A.iters || !unf) {                                      // :117-119
+    if (part != 0) return;
     const bool conv = work && !unf && (fabsf(f) <= A.thr) && (t < tmax);   // :133-138
     A.points[(size_t)r * 3] = x[0]; A.points[(size_t)r * 3 + 1] = x[1]; A.points[(size_t)r * 3 + 2] = x[2];
     A.sdf[r] = f; A.dist[r] = t; A.conv[r] = conv ? 1 : 0;
@@ -152,11 +186,15 @@ __global__ void __launch_bounds__(256) st_update_kernel(BArgs A, int round) {
     t = __fadd_rn(t, f);                                           // :123-125
 #pragma unroll
     for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(x[c], __fmul_rn(A.ray_d[(size_t)r * 3 + c], f));
-    A.t[r] = t; A.k[r] = k + 1; A.flags[r] = (work ? 1 : 0) | 2;
-    A.x[(size_t)r * 3] = x[0]; A.x[(size_t)r * 3 + 1] = x[1]; A.x[(size_t)r * 3 + 2] = x[2];
-    const int slot = atomicAdd(A.c + nxt, 1);
-    A.list[(round + 1) & 1][slot] = r;
-    write_pe(A, (size_t)slot, x);
+    int slot = 0;
+    if (part == 0) {
+      A.t[r] = t; A.k[r] = k + 1; A.flags[r] = (work ? 1 : 0) | 2;
+      A.x[(size_t)r * 3] = x[0]; A.x[(size_t)r * 3 + 1] = x[1]; A.x[(size_t)r * 3 + 2] = x[2];
+      slot = atomicAdd(A.c + nxt, 1);
+      A.list[(round + 1) & 1][slot] = r;
+    }
+    slot = __shfl_sync(gmask, slot, threadIdx.x & 24);
+    write_pe(A, (size_t)slot, x, part);
   }
 }
 
@@ -236,36 +274,44 @@ __global__ void __launch_bounds__(256) smp_update_kernel(BArgs A, int chunk) {
 // ---------------------------------------------------------------- bisection (:199-220)
 __global__ void __launch_bounds__(256) bis_prepare_kernel(BArgs A) {
   const int n_root = A.c[C_NROOT];
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0 && A.stats) atomicAdd(A.stats + 4, (unsigned long long)n_root);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = tid / PE_T, part = tid % PE_T;
+  if (tid == 0 && A.stats) atomicAdd(A.stats + 4, (unsigned long long)n_root);
   if (i >= n_root) return;
   const float mid = __fmul_rn(__fadd_rn(A.root_lo[i], A.root_hi[i]), 0.5f);   // :203
-  A.root_mid[i] = mid;
-  if (A.root_work[i]) atomicMax(A.c + C_BR, n_root);                // while work.any()  (:204)
+  if (part == 0) {
+    A.root_mid[i] = mid;
+    if (A.root_work[i]) atomicMax(A.c + C_BR, n_root);              // while work.any()  (:204)
+  }
   float x[3];
   ray_point(A, A.root_ray[i], mid, x);                              // :205
-  write_pe(A, (size_t)i, x);
+  write_pe(A, (size_t)i, x, part);
 }
 
 __global__ void __launch_bounds__(256) bis_update_kernel(BArgs A, int round) {
   const int rows = A.c[C_BR + round];
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0 && rows > 0) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = tid / PE_T, part = tid % PE_T;
+  if (tid == 0 && rows > 0) {
     A.c[C_KMAX] = round + 1;
     if (A.stats) { atomicAdd(A.stats + 2, (unsigned long long)rows); atomicAdd(A.stats + 6, (unsigned long long)((rows + 127) / 128)); }
   }
   if (i >= rows) return;
   const float f = read_f(A, i);
   float lo = A.root_lo[i], hi = A.root_hi[i], mid = A.root_mid[i];
+  const int was_work = A.root_work[i];
+  __syncwarp(0xffu << (threadIdx.x & 24));                          // every lane of the item has read the state
   if (f > 0.f) lo = mid; else hi = mid;                             // every ray of the call (:207-212)
   mid = __fmul_rn(__fadd_rn(lo, hi), 0.5f);                         // :213
-  A.root_lo[i] = lo; A.root_hi[i] = hi; A.root_mid[i] = mid;
-  const bool work = A.root_work[i] && (__fsub_rn(hi, lo) > A.two_thr);   // :214
-  A.root_work[i] = work ? 1 : 0;
-  if (work) atomicMax(A.c + C_BR + round + 1, rows);
+  if (part == 0) {
+    A.root_lo[i] = lo; A.root_hi[i] = hi; A.root_mid[i] = mid;
+    const bool work = was_work && (__fsub_rn(hi, lo) > A.two_thr);  // :214
+    A.root_work[i] = work ? 1 : 0;
+    if (work) atomicMax(A.c + C_BR + round + 1, rows);
+  }
   float x[3];
   ray_point(A, A.root_ray[i], mid, x);
-  write_pe(A, (size_t)i, x);
+  write_pe(A, (size_t)i, x, part);
 }
 
 __global__ void __launch_bounds__(256) bis_final_kernel(BArgs A) {
@@ -330,14 +376,15 @@ int trace_mode() {
   int m = g_trace_mode.load(std::memory_order_relaxed);
   if (m < 0) {
     const char* e = getenv("IRONB_TRACE");
-    m = (e && (e[0] == 'f' || e[0] == 'F' || e[0] == '0')) ? 0 : 1;   // IRONB_TRACE=fused selects the FFMA tracer
+    // IRONB_TRACE=fused: fp32 FFMA tracer; =tf32: batched tcgen05 3xTF32; default: batched tcgen05 fp16x2 split
+    m = (e && (e[0] == 'f' || e[0] == 'F' || e[0] == '0')) ? 0 : (e && (e[0] == 't' || e[0] == 'T' || e[0] == '1')) ? 1 : 2;
     g_trace_mode.store(m, std::memory_order_relaxed);
   }
   return m;
 }
 int set_trace_mode(int mode) {
   int prev = trace_mode();
-  g_trace_mode.store(mode ? 1 : 0, std::memory_order_relaxed);
+  g_trace_mode.store(mode <= 0 ? 0 : (mode == 1 ? 1 : 2), std::memory_order_relaxed);
   return prev;
 }
 
@@ -351,6 +398,7 @@ int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float*
   if (!trace_mlp_fused_supported(lay)) { set_error("trace: batched tcgen05 tracer needs d_hidden in {128,256,512}"); return IRONB_ENOSUP; }
   for (int l = 0; l < last; ++l)
     if (lay->out_pad[l] != H || (l > 0 && lay->in_pad[l] != H)) { set_error("trace: layer %d is not %d wide", l, H); return IRONB_ENOSUP; }
+  if (lay->multires >= PE_T) { set_error("trace: batched tracer supports multires <= %d", PE_T - 1); return IRONB_ENOSUP; }
   BWs w = carve_b(lay, N, reinterpret_cast<unsigned char*>(ws));
   if (ws_bytes < w.bytes) { set_error("trace: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)w.bytes); return IRONB_EINVAL; }
   IRONB_CUDA(cudaMemsetAsync(w.c, 0, NCOUNTERS * 4, st));
@@ -373,31 +421,41 @@ int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float*
   A.unf_list = w.unf_list; A.smin = w.smin; A.smax = w.smax; A.prev_f = w.prev_f; A.prev_t = w.prev_t;
   A.glist[0] = w.glist[0]; A.glist[1] = w.glist[1];
   A.root_ray = w.root_ray; A.root_lo = w.root_lo; A.root_hi = w.root_hi; A.root_mid = w.root_mid; A.root_work = w.root_work;
-  A.Ehi = w.Ehi; A.Elo = w.Elo;
+  const bool f16 = trace_mode() == 2;
+  A.Ehi = w.Ehi; A.Elo = w.Elo; A.f16 = f16 ? 1 : 0;
   A.cap_groups = (int)(w.cap / 32);
   const int C = H / 128;
   A.Fpart = w.Fpart; A.b_last = packed + lay->off_b[last]; A.nparts = 4 * C; A.cap = (int)w.cap;
 
   // weights -> tf32-exact hi / lo copies (once per call), then the tensor maps: operands are fixed for the whole call
   int rc;
-  for (int l = 0; l < last; ++l)
-    if ((rc = split_weights(packed + lay->off_w[l], (int64_t)lay->out_pad[l] * lay->in_pad[l], w.Whi[l], w.Wlo[l], st))) return rc;
+  for (int l = 0; l < last; ++l) {
+    const int64_t n = (int64_t)lay->out_pad[l] * lay->in_pad[l];
+    if ((rc = f16 ? split_weights_h(packed + lay->off_w[l], n, w.Whi[l], w.Wlo[l], st)
+                  : split_weights(packed + lay->off_w[l], n, w.Whi[l], w.Wlo[l], st))) return rc;
+  }
   CUtensorMap mE[2], mU[4], mW[2 * IRONB_MAX_LIN];
-  if ((rc = tc::make_map(&mE[0], w.Ehi, (int)w.cap, Epad, Epad))) return rc;
-  if ((rc = tc::make_map(&mE[1], w.Elo, (int)w.cap, Epad, Epad))) return rc;
+  auto mk = [&](CUtensorMap* m, const float* p, int rows, int K, int ld) -> int {   // same buffers, element type per mode
+    return f16 ? tc::make_map_h(m, p, rows, K, ld) : tc::make_map(m, p, rows, K, ld);
+  };
+  if ((rc = mk(&mE[0], w.Ehi, (int)w.cap, Epad, Epad))) return rc;
+  if ((rc = mk(&mE[1], w.Elo, (int)w.cap, Epad, Epad))) return rc;
   for (int b = 0; b < 2; ++b) {
-    if ((rc = tc::make_map(&mU[b * 2], w.Uhi[b], (int)w.cap, H, H))) return rc;
-    if ((rc = tc::make_map(&mU[b * 2 + 1], w.Ulo[b], (int)w.cap, H, H))) return rc;
+    if ((rc = mk(&mU[b * 2], w.Uhi[b], (int)w.cap, H, H))) return rc;
+    if ((rc = mk(&mU[b * 2 + 1], w.Ulo[b], (int)w.cap, H, H))) return rc;
   }
   for (int l = 0; l < last; ++l) {
-    if ((rc = tc::make_map(&mW[l * 2], w.Whi[l], lay->out_pad[l], lay->in_pad[l], lay->in_pad[l]))) return rc;
-    if ((rc = tc::make_map(&mW[l * 2 + 1], w.Wlo[l], lay->out_pad[l], lay->in_pad[l], lay->in_pad[l]))) return rc;
+    if ((rc = mk(&mW[l * 2], w.Whi[l], lay->out_pad[l], lay->in_pad[l], lay->in_pad[l]))) return rc;
+    if ((rc = mk(&mW[l * 2 + 1], w.Wlo[l], lay->out_pad[l], lay->in_pad[l], lay->in_pad[l]))) return rc;
   }
-  // one MLP evaluation of the first (*m_dev x m_mul) rows: all hidden layers + the sdf row in one cluster launch (mlp_tc.cu)
+  // one MLP evaluation of the first (*m_dev x m_mul) rows: all hidden layers + the sdf row in one cluster launch
+  // (mlp_h16.cu: fp16x2 split, two tiles in flight; mlp_tc.cu: 3xTF32)
   auto mlp = [&](int rows_cap, const int* m_dev, int m_mul) -> int {
+    if (f16) return launch_trace_mlp_h16(lay, packed, mE, mU, mW, w.Ehi, w.Elo, w.Fpart, rows_cap, (int)w.cap, m_dev, m_mul, st);
     return launch_trace_mlp_fused(lay, packed, mE, mU, mW, w.Ehi, w.Elo, w.Uhi, w.Ulo, w.Fpart, rows_cap, (int)w.cap, m_dev, m_mul, st);
   };
-  const int nb = (int)ceil_div64(N, 256);
+  const int nb = (int)ceil_div64(N * PE_T, 256);    // st_* / bis_* kernels: PE_T threads per work item
+  const int nb1 = (int)ceil_div64(N, 256);
 
   // ---- sphere tracing: iters + 1 evaluations
   st_init_kernel<<<nb, 256, 0, st>>>(A);
@@ -429,7 +487,7 @@ int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float*
     IRONB_CHECK_LAUNCH("bis_update_kernel");
   }
   if ((rc = mlp((int)N, w.c + C_NROOT, 1))) return rc;
-  bis_final_kernel<<<nb, 256, 0, st>>>(A);
+  bis_final_kernel<<<nb1, 256, 0, st>>>(A);
   IRONB_CHECK_LAUNCH("bis_final_kernel");
   return IRONB_OK;
 }

@@ -51,11 +51,15 @@ def gemm_mode(request):
     lib.ironb_set_gemm_mode(prev)
 
 
-@pytest.fixture(params=["fused-ffma", "batched-tcgen05"])
+TRACE_MODES = {"fused-ffma": 0, "batched-tf32": 1, "batched-tcgen05": 2}
+
+
+@pytest.fixture(params=list(TRACE_MODES))
 def trace_mode(request):
-    """Both tracer implementations: the fused persistent fp32-FFMA kernels and the batched tcgen05 rounds (default)."""
+    """All tracer implementations: the fused persistent fp32-FFMA kernels, the batched tcgen05 rounds with 3xTF32
+    operands, and the batched tcgen05 rounds with fp16x2-split operands and two tiles in flight (default)."""
     from iron_b200 import _lib
     lib = _lib.load()
-    prev = lib.ironb_set_trace_mode(1 if request.param == "batched-tcgen05" else 0)
+    prev = lib.ironb_set_trace_mode(TRACE_MODES[request.param])
     yield request.param
     lib.ironb_set_trace_mode(prev)

@@ -84,17 +84,20 @@ def test_tracers_agree_on_65536_rays():
     lib = __import__("iron_b200")._lib.load()
     cam, _, _ = cam512.crop_region(256, 256, ul_corner=(128, 128))   # BASELINE configs[3]/[4] ray set
     out = {}
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         prev = lib.ironb_set_trace_mode(mode)
         try:
             out[mode] = ib.raytrace_pixels(sdf, ib.RayTracer(), cam.get_uv(), cam, max_num_rays=50000)
         finally:
             lib.ironb_set_trace_mode(prev)
-    m0, m1 = out[0]["convergent_mask"], out[1]["convergent_mask"]
-    agree = float((m0 == m1).float().mean())
-    assert agree >= 0.9999, f"fused FFMA vs batched tcgen05 hit-mask agreement {agree:.5f}"
+    m0 = out[0]["convergent_mask"]
+    for mode, name in ((1, "3xTF32"), (2, "fp16x2")):
+        m1 = out[mode]["convergent_mask"]
+        agree = float((m0 == m1).float().mean())
+        assert agree >= 0.9999, f"fused FFMA vs batched tcgen05 ({name}) hit-mask agreement {agree:.5f}"
+    m1 = out[2]["convergent_mask"]
     both = (m0 & m1)
-    d = (out[0]["distance"] - out[1]["distance"])[both].abs()
+    d = (out[0]["distance"] - out[2]["distance"])[both].abs()
     assert float((d <= 1e-4).float().mean()) >= 0.999, float((d <= 1e-4).float().mean())
     assert float(d.max()) <= 2.0 / 127 * 1.5
 
