@@ -58,6 +58,18 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def wait_first(self, timeout=5.0):
+        """Blocks until nvidia-smi has written its first sample: its start-up (NVML init) stalls kernel launches for tens
+        of milliseconds, which must not land inside the timed region (it did: one 15-58 ms step per run)."""
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < timeout:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.02)
+
     def stop(self, t_begin=None, t_end=None):
         """Median SM clock / throttle reasons of the samples whose timestamp falls inside [t_begin, t_end] (epoch s);
         all samples when none does (very short timed regions)."""
@@ -335,6 +347,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.wait_first()
+    # the cyclic garbage collector is paused over warm-up + timed loops: a generation-2 pass over the module graph landed
+    # deterministically inside the 4th timed step (10-58 ms of host stall with the GPU idle)
+    import gc
+    gc.collect()
+    gc.disable()
     # ---- warm-up
     for _ in range(max(args.warmup, 3)):
         step(cam, target, eik)
@@ -389,6 +408,7 @@ def run_ours(args):
     h2d = K_h.numel() * 4 + W2C_h.numel() * 4 + target_h.numel() * 4 + eik_h.numel() * 4
     d2h = 4 + 4   # loss + the hit count the shading chunk reads back
 
+    gc.enable()
     clocks = sampler.stop(epoch0, epoch1) if sampler else None
     if rank == 0:
         pk = peaks()
@@ -432,6 +452,7 @@ def run_ours(args):
                        "implementation": tracer_impl},
             "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps, "grad_params": n_params,
             "loss": loss_host,
+            "step_ms": [round(x, 3) for x in step_ms], "tracer_ms": [round(x, 3) for x in tr_ms],
         }
         if world == 1 and not args.no_cpu:
             line["ggx_roofline"] = ggx_microbench(dev, pk)

@@ -60,6 +60,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// one lane of a converged warp: control warps run their loops warp-uniformly and predicate only the issue on it
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -189,45 +199,49 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const uint32_t tmem = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(empty(s), ph ^ 1);
+    // ================= TMA producer (warp-uniform loop: addresses stay in uniform registers; elected lane issues) ====
+    const bool leader = elect_one();
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(empty(s), ph ^ 1);
+      const uint32_t st = base + s * STAGE_BYTES;
+      if (leader) {
         mbar_arrive_expect_tx(full(s), HI_BYTES);
-        const uint32_t st = base + s * STAGE_BYTES;
         tma_load_2d(st, &mapA, kbeg + it * BK, m0, full(s));
         tma_load_2d(st + TILE_BYTES, &mapB, kbeg + it * BK, n0, full(s));
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(conv(s), ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = base + s * STAGE_BYTES;
-        const uint64_t a_hi = make_desc(st), b_hi = make_desc(st + TILE_BYTES);
-        const uint64_t a_lo = make_desc(st + 2 * TILE_BYTES), b_lo = make_desc(st + 3 * TILE_BYTES);
+    // ================= MMA issuer (warp-uniform loop, elected lane issues) =================
+    const bool leader = elect_one();
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      mbar_wait(conv(s), ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t st = base + s * STAGE_BYTES;
+      const uint64_t a_hi = make_desc(st), b_hi = make_desc(st + TILE_BYTES);
+      const uint64_t a_lo = make_desc(st + 2 * TILE_BYTES), b_lo = make_desc(st + 3 * TILE_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < BK / 8; ++kk) {
-          const uint64_t adv = (uint64_t)(kk * 2);          // 8 tf32 = 32 B = 2 x 16 B along the swizzled row
-          const int g = it * (BK / 8) + kk;                 // global k-step
-          // The tensor core accumulates into TMEM with truncation, so every accumulation step costs up to 1 ulp
-          // of the running sum, always towards zero.  Keep the chains short and the small terms apart:
-          // hi*hi alternates between two accumulators, the two lo cross terms go to a third; the epilogue adds
-          // the three in fp32 round-to-nearest.
+      for (int kk = 0; kk < BK / 8; ++kk) {
+        const uint64_t adv = (uint64_t)(kk * 2);          // 8 tf32 = 32 B = 2 x 16 B along the swizzled row
+        const int g = it * (BK / 8) + kk;                 // global k-step
+        // The tensor core accumulates into TMEM with truncation, so every accumulation step costs up to 1 ulp
+        // of the running sum, always towards zero.  Keep the chains short and the small terms apart:
+        // hi*hi alternates between two accumulators, the two lo cross terms go to a third; the epilogue adds
+        // the three in fp32 round-to-nearest.
+        if (leader) {
           tc_mma_tf32(tmem + ((g & 1) ? 128u : 0u), a_hi + adv, b_hi + adv, IDESC, g >= 2 ? 1u : 0u);
           tc_mma_tf32(tmem + 256u, a_lo + adv, b_hi + adv, IDESC, g >= 1 ? 1u : 0u);
           tc_mma_tf32(tmem + 256u, a_hi + adv, b_lo + adv, IDESC, 1u);
         }
-        tc_commit(empty(s));          // slot free once these MMAs have read it
       }
-      tc_commit(acc_bar);             // accumulator complete
+      if (leader) tc_commit(empty(s));          // slot free once these MMAs have read it
     }
+    if (leader) tc_commit(acc_bar);             // accumulator complete
+    __syncwarp();
   } else {
     // ================= splitter, then epilogue (warps 2..9) =================
     const int t = threadIdx.x - 64;   // 0..255

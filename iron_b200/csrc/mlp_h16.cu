@@ -18,9 +18,12 @@
 //         full / empty [3]   TMA loads  <-> MMA                       (64 KiB stages: A_hi, B_hi, A_lo, B_lo)
 //         acc_full [slot]    MMA -> epilogue                          (tcgen05.commit)
 //         tmem_free [slot]   epilogue -> MMA                          (accumulators drained)
-//         stg_full / empty   epilogue <-> store warp                  (32 KiB staging: one 64-column half, hi + lo box)
-//         ready [slot]       store warps of ALL CTAs of the cluster -> TMA loader (remote arrive, release/acquire.cluster):
-//                            the whole 128 x H activation block of (tile, layer) is in L2
+//         stg_full[half] / stg_empty   epilogue <-> the two store warps  (32 KiB staging: one 64-column half, hi + lo box)
+//         ready [slot][half] store warps of ALL CTAs of the cluster -> TMA loader (remote arrive; acquire at cluster
+//                            scope): one 64-column half (= one k-block of the next layer) of every CTA's 128 x 128
+//                            activation block is in L2.  Measured alternatives: a release.cluster arrive per peer costs a
+//                            GPU-scope membar each (4.7k cycles for 4 peers) -> ONE fence + relaxed arrives; plain
+//                            st.global from the epilogue warps + per-warp fences was slower still (16 membars per half).
 //     The loader prefetches the weight (B) boxes of a layer's first stages before it waits for `ready`, so only the
 //     activation (A) boxes sit on the layer-to-layer critical path.
 //
@@ -43,9 +46,10 @@ constexpr int STAGE = 4 * TILE;
 constexpr int NSTAGE = 3;
 constexpr int STG = 2 * TILE;
 constexpr int NWARP_EPI = 16;
-constexpr int NT = (3 + NWARP_EPI) * 32;      // warp 0 TMA loads, warp 1 MMA + TMEM alloc, warp 2 TMA stores, 3.. epilogue
+constexpr int NCTRL = 4;                      // warp 0 TMA loads, warp 1 MMA + TMEM alloc, warps 2 / 3 TMA stores of half 0 / 1
+constexpr int NT = (NCTRL + NWARP_EPI) * 32;  // warps 4.. epilogue
 constexpr int SMEM = NSTAGE * STAGE + STG + 1024 + 256;
-constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f;
+constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f, RSQRT2 = 0.70710678118654752f;
 // kind::f16: fp16 A and B (format 0), fp32 accumulate, both K-major, M = 128, N = 128
 constexpr uint32_t IDESC_F16 = (1u << 4) | ((uint32_t)(RN >> 3) << 17) | ((uint32_t)(RM >> 4) << 24);
 
@@ -59,19 +63,25 @@ struct Args {
   const float* bias[MAXH];
   const float* w_last;       // row 0 of the output layer [H], fp32
   const __half* Ehi; const __half* Elo;
+  __half* Uhi[2]; __half* Ulo[2];   // activation ping-pong buffers [cap][H] (the maps' memory)
   float* Fpart;              // [4C][cap] partial sdf sums
   int n_true[MAXH];
   int kpad[MAXH];
   int n_hidden, skip_layer, Epad, Edim, H, C;
-  float beta, inv_beta;
+  float nbl2e, ln2_ib;       // -beta * log2(e),  ln(2) / beta
   const int* m_dev;
-  int m_mul, rows_cap, cap, nhh;
+  int m_mul, rows_cap, cap, nhh, preb;
   long long* dbg;
 };
 
-__device__ __forceinline__ float softplus_fast(float z, float beta, float inv_beta) {
-  const float e = __expf(-fabsf(z * beta));
-  return fmaxf(z, 0.f) + __logf(1.f + e) * inv_beta;
+// softplus_beta(z) = max(z, 0) + log1p(exp(-|beta z|)) / beta with the two MUFU approximations used directly:
+// t = 2^(-|z| beta log2 e), L = log2(1 + t) in [0, 1], result = max(z, 0) + L ln2 / beta.  The log term is <= ln2 / beta, so
+// the 2^-22 relative error of ex2 / lg2 is ~1e-9 absolute; for beta z > 20 the term vanishes in fp32 (torch's threshold).
+__device__ __forceinline__ float softplus_fast(float z, float nbl2e, float ln2_ib) {
+  float t, L;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(z) * nbl2e));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(L) : "f"(1.f + t));
+  return fmaf(L, ln2_ib, fmaxf(z, 0.f));
 }
 __device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
@@ -105,36 +115,127 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         : "memory");
   } while (!ok);
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t cta) {
+// Remote arrive WITHOUT its own release: every release.cluster arrive costs a GPU-scope membar (~1k cycles, measured
+// 4 of them back to back), so the caller issues ONE fence.acq_rel.cluster and then these relaxed arrives.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t local_bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(local_bar),
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(local_bar),
       "r"(cta)
       : "memory");
-}
-// one lane of a converged warp; the control warps run their loops warp-uniformly (addresses and descriptors stay in
-// uniform registers) and only the issuing instruction is predicated on the elected lane
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// The unit sequence every role walks: tile pairs (slot 0 = t0, slot 1 = t0 + G) of this cluster, layer by layer.
+struct EpiCtx {
+  int q, blk, lane, row, n0, rank, M;
+  uint32_t tmem, stg_full0, stg_empty;
+  unsigned char *srow_hi, *srow_lo;
+};
+
+// One (tile, layer) unit of the epilogue for one thread: row = TMEM lane, 16 columns in each of the two 64-column halves.
+// PRE_SKIP: the layer before the skip connection (cat(h, PE) / sqrt 2 fills the columns past n_true); LAST: the last hidden
+// layer is not stored, it is dotted with the sdf row of the output layer.
+template <bool PRE_SKIP, bool LAST>
+__device__ __forceinline__ void epi_unit(const Args& a, const EpiCtx& c, int l, int s, int m0, float mybias, float mywl,
+                                         uint32_t tfree, uint32_t& se_n) {
+  const int m = m0 + c.row;
+  const int n_true = a.n_true[l];
+  float dot = 0.f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c0 = h * 64 + c.blk * 16;                   // column inside the CTA's 128
+    uint32_t r0[16], rl[16];
+    const uint32_t taddr = c.tmem + ((uint32_t)(c.q * 32) << 16) + (uint32_t)s * 256u + (uint32_t)c0;
+    tmem_ld16(taddr, r0);
+    if (a.nhh == 2) {
+      uint32_t r1[16];
+      tmem_ld16(taddr + 128u, r1);
+      tmem_ld16(taddr + 256u, rl);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r0[i] = __float_as_uint(__fadd_rn(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+    } else {
+      tmem_ld16(taddr + 128u, rl);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    }
+    if (h == 1) {                                         // this warp has drained its part of the slot's accumulators
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (c.lane == 0) mbar_arrive(tfree);
+    }
+    uint32_t ph[8], pl[8];                                // 16 outputs as packed halfs: hi and scaled lo
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float u[2];
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int i = g * 2 + jj;
+        const float b = __shfl_sync(0xffffffffu, mybias, h * 16 + i);
+        const float z = fmaf(__uint_as_float(rl[i]), LO_INV, __uint_as_float(r0[i])) + b;
+        u[jj] = softplus_fast(z, a.nbl2e, a.ln2_ib);
+      }
+      if (PRE_SKIP) {   // cat(h, PE)/sqrt(2)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int n = c.n0 + c0 + g * 2 + jj;
+          if (n < n_true) {
+            u[jj] *= RSQRT2;                             // the accumulators already carry ~1e-6: no need for the exact division
+          } else {
+            const int ce = n - n_true;
+            u[jj] = 0.f;
+            if (ce < a.Edim && m < c.M) {
+              const size_t o = (size_t)m * a.Epad + ce;
+              u[jj] = fmaf(__half2float(a.Elo[o]), LO_INV, __half2float(a.Ehi[o])) * RSQRT2;
+            }
+          }
+        }
+      }
+      if (LAST) {
+        dot = fmaf(u[0], __shfl_sync(0xffffffffu, mywl, h * 16 + g * 2), dot);
+        dot = fmaf(u[1], __shfl_sync(0xffffffffu, mywl, h * 16 + g * 2 + 1), dot);
+      } else {
+        const __half2 hi2 = __floats2half2_rn(u[0], u[1]);
+        const float2 hf = __half22float2(hi2);
+        const __half2 lo2 = __floats2half2_rn((u[0] - hf.x) * LO_SCALE, (u[1] - hf.y) * LO_SCALE);
+        ph[g] = *reinterpret_cast<const uint32_t*>(&hi2);
+        pl[g] = *reinterpret_cast<const uint32_t*>(&lo2);
+      }
+    }
+    if (!LAST) {
+      mbar_wait(c.stg_empty, (se_n & 1u) ^ 1u);           // the previous half's TMA store has read the staging buffer
+      ++se_n;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {                       // two 16-byte chunks (8 halfs each) per operand
+        const int off = (((c.blk * 2 + g) ^ (c.row & 7)) << 4);
+        *reinterpret_cast<uint4*>(c.srow_hi + off) = make_uint4(ph[g * 4], ph[g * 4 + 1], ph[g * 4 + 2], ph[g * 4 + 3]);
+        *reinterpret_cast<uint4*>(c.srow_lo + off) = make_uint4(pl[g * 4], pl[g * 4 + 1], pl[g * 4 + 2], pl[g * 4 + 3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the TMA store engine
+      __syncwarp();
+      if (c.lane == 0) mbar_arrive(c.stg_full0 + 8u * (uint32_t)h);
+    }
+  }
+  if (LAST && m < c.M) a.Fpart[(size_t)(c.rank * 4 + c.blk) * a.cap + m] = dot;
+}
+
+// The unit sequence every role walks: tile pairs (j = 0: t0, j = 1: t0 + G) of this cluster, layer by layer.  A pair keeps
+// each tile on its own TMEM slot (s = j).  A cluster's last, unpaired tile alternates the two slots BETWEEN LAYERS
+// (s = l & 1): the next layer's MMAs may then start on the first half of the activations while the epilogue still drains
+// the other slot.  sp is the slot the previous layer of the same tile used (whose `ready` barriers the loader waits on).
 #define MLP16_FOR_UNITS                                                     \
   for (int t0 = cid; t0 < ntiles; t0 += nslots * G)                         \
     for (int l = 0; l < a.n_hidden; ++l)                                    \
-      for (int s = 0; s < nslots; ++s)                                      \
-        if (t0 + s * G < ntiles)
+      for (int j = 0; j < nslots; ++j)                                      \
+        if (t0 + j * G < ntiles)
+#define MLP16_UNIT_SLOTS                                                    \
+  const bool two = (nslots == 2) && (t0 + G < ntiles);                      \
+  const int s = two ? j : ((nslots == 2) ? (l & 1) : 0);                    \
+  const int sp = two ? j : ((nslots == 2) ? ((l + 1) & 1) : 0);             \
+  (void)sp;
 
 __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ Maps maps, const Args a) {
   int M = a.rows_cap;
@@ -160,10 +261,11 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
   auto empty = [&](int i) { return bars + 8u * (NSTAGE + i); };
   auto acc_full = [&](int s) { return bars + 8u * (2 * NSTAGE + s); };
   auto tmem_free = [&](int s) { return bars + 8u * (2 * NSTAGE + 2 + s); };
-  auto ready = [&](int s) { return bars + 8u * (2 * NSTAGE + 4 + s); };
-  const uint32_t stg_full = bars + 8u * (2 * NSTAGE + 6), stg_empty = bars + 8u * (2 * NSTAGE + 7);
-  const uint32_t tmem_slot = bars + 8u * (2 * NSTAGE + 8);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(stg_ptr + STG + 8 * (2 * NSTAGE + 8));
+  auto ready = [&](int s, int h) { return bars + 8u * (2 * NSTAGE + 4 + s * 2 + h); };   // (slot, 64-column half)
+  auto stg_full = [&](int h) { return bars + 8u * (2 * NSTAGE + 8 + h); };
+  const uint32_t stg_empty = bars + 8u * (2 * NSTAGE + 10);
+  const uint32_t tmem_slot = bars + 8u * (2 * NSTAGE + 11);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(stg_ptr + STG + 8 * (2 * NSTAGE + 11));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -174,9 +276,11 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full(s), 1);
       mbar_init(tmem_free(s), NWARP_EPI);
-      mbar_init(ready(s), (uint32_t)a.C);
+      mbar_init(ready(s, 0), (uint32_t)a.C);
+      mbar_init(ready(s, 1), (uint32_t)a.C);
     }
-    mbar_init(stg_full, NWARP_EPI);
+    mbar_init(stg_full(0), NWARP_EPI);
+    mbar_init(stg_full(1), NWARP_EPI);
     mbar_init(stg_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -193,47 +297,44 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
   if (warp == 0) {
     // ================= TMA loads (warp-uniform loop, elected lane issues) =================
     const bool leader = elect_one();
-    uint32_t it = 0, rdy_n[2] = {0u, 0u};
+    uint32_t it = 0, rdy_bits = 0u;                     // phase parity per (slot, half) ready barrier
     MLP16_FOR_UNITS {
-      const int m0 = (t0 + s * G) * RM;
+      MLP16_UNIT_SLOTS
+      const int m0 = (t0 + j * G) * RM;
       const int nk = (a.kpad[l] + BKH - 1) / BKH;
       const CUtensorMap* mAh = (l == 0) ? &maps.e[0] : &maps.u[(l - 1) & 1][0];
       const CUtensorMap* mAl = (l == 0) ? &maps.e[1] : &maps.u[(l - 1) & 1][1];
       const CUtensorMap* mBh = &maps.w[l][0];
       const CUtensorMap* mBl = &maps.w[l][1];
-      const int pre = nk < NSTAGE ? nk : NSTAGE;
-      for (int i = 0; i < pre; ++i) {                   // weights first: they do not depend on the previous layer
-        const uint32_t sidx = (it + i) % NSTAGE, ph = ((it + i) / NSTAGE) & 1u;
-        mbar_wait(empty(sidx), ph ^ 1u);
-        const uint32_t st = base + sidx * STAGE;
-        if (leader) {
-          mbar_arrive_expect_tx(full(sidx), STAGE);
-          tma_load_2d(st + TILE, mBh, i * BKH, n0, full(sidx));
-          tma_load_2d(st + 3 * TILE, mBl, i * BKH, n0, full(sidx));
+      // k-blocks in the order the previous layer's epilogues release them: every CTA's first 64-column half
+      // (k-blocks 0, 2, 4, ..), then every CTA's second half.  Layer 0 reads the encoded points: no dependency.
+      const int C = a.C;
+      int ib = 0;                                         // stages whose barrier is armed and whose weight boxes are issued
+      for (int ia = 0; ia < nk; ++ia) {
+        const bool wait_pt = (l > 0) && (ia == 0 || ia == C);
+        const int ahead = wait_pt ? (ia + a.preb < nk ? ia + a.preb : nk) : ia + 1;
+        for (; ib < ahead; ++ib) {                        // weights do not depend on the previous layer: run ahead
+          const uint32_t sidx = (it + ib) % NSTAGE, ph = ((it + ib) / NSTAGE) & 1u;
+          const int kb = (l == 0) ? ib : 2 * (ib % C) + (ib / C);
+          mbar_wait(empty(sidx), ph ^ 1u);
+          const uint32_t st = base + sidx * STAGE;
+          if (leader) {
+            mbar_arrive_expect_tx(full(sidx), STAGE);
+            tma_load_2d(st + TILE, mBh, kb * BKH, n0, full(sidx));
+            tma_load_2d(st + 3 * TILE, mBl, kb * BKH, n0, full(sidx));
+          }
         }
-      }
-      if (l > 0) {
-        mbar_wait_cluster(ready(s), rdy_n[s] & 1u);
-        ++rdy_n[s];
-      }
-      for (int i = 0; i < pre; ++i) {
-        const uint32_t sidx = (it + i) % NSTAGE;
-        const uint32_t st = base + sidx * STAGE;
-        if (leader) {
-          tma_load_2d(st, mAh, i * BKH, m0, full(sidx));
-          tma_load_2d(st + 2 * TILE, mAl, i * BKH, m0, full(sidx));
+        if (wait_pt) {
+          const int h = (ia == 0) ? 0 : 1;
+          mbar_wait_cluster(ready(sp, h), (rdy_bits >> (sp * 2 + h)) & 1u);
+          rdy_bits ^= 1u << (sp * 2 + h);
         }
-      }
-      for (int i = pre; i < nk; ++i) {
-        const uint32_t sidx = (it + i) % NSTAGE, ph = ((it + i) / NSTAGE) & 1u;
-        mbar_wait(empty(sidx), ph ^ 1u);
+        const uint32_t sidx = (it + ia) % NSTAGE;
+        const int kb = (l == 0) ? ia : 2 * (ia % C) + (ia / C);
         const uint32_t st = base + sidx * STAGE;
         if (leader) {
-          mbar_arrive_expect_tx(full(sidx), STAGE);
-          tma_load_2d(st, mAh, i * BKH, m0, full(sidx));
-          tma_load_2d(st + TILE, mBh, i * BKH, n0, full(sidx));
-          tma_load_2d(st + 2 * TILE, mAl, i * BKH, m0, full(sidx));
-          tma_load_2d(st + 3 * TILE, mBl, i * BKH, n0, full(sidx));
+          tma_load_2d(st, mAh, kb * BKH, m0, full(sidx));
+          tma_load_2d(st + 2 * TILE, mAl, kb * BKH, m0, full(sidx));
         }
       }
       it += nk;
@@ -245,6 +346,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
     uint32_t it = 0, free_n[2] = {0u, 0u};
     const uint32_t nhh = (uint32_t)a.nhh;
     MLP16_FOR_UNITS {
+      MLP16_UNIT_SLOTS
       const int K = a.kpad[l];
       const int nk = (K + BKH - 1) / BKH, ksteps = (K + 15) / 16;
       mbar_wait(tmem_free(s), (free_n[s] & 1u) ^ 1u);
@@ -254,9 +356,9 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
       const uint32_t acc_lo = acc + 128u * nhh;
       for (int i = 0; i < nk; ++i) {
         const uint32_t sidx = (it + i) % NSTAGE, ph = ((it + i) / NSTAGE) & 1u;
-        if (stamp && leader && i == 0 && t0 == 0 && s == 0) a.dbg[l * 8 + 0] = clock64();
+        if (stamp && leader && i == 0 && t0 == 0 && j == 0) a.dbg[l * 8 + 0] = clock64();
         mbar_wait(full(sidx), ph);
-        if (stamp && leader && i == 0 && t0 == 0 && s == 0) a.dbg[l * 8 + 1] = clock64();
+        if (stamp && leader && i == 0 && t0 == 0 && j == 0) a.dbg[l * 8 + 1] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = base + sidx * STAGE;
         const uint64_t a_hi = make_desc(st), b_hi = make_desc(st + TILE);
@@ -276,138 +378,68 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
         if (leader) tc_commit(empty(sidx));
       }
       if (leader) tc_commit(acc_full(s));
-      if (stamp && leader && t0 == 0 && s == 0) a.dbg[l * 8 + 2] = clock64();
+      if (stamp && leader && t0 == 0 && j == 0) a.dbg[l * 8 + 2] = clock64();
       it += nk;
     }
     __syncwarp();
-  } else if (warp == 2) {
-    // ================= TMA stores + cluster-wide "layer ready" (warp-uniform loop, elected lane issues) =================
+  } else if (warp < NCTRL) {
+    // ================= TMA stores + cluster-wide "half ready": warp 2 owns the first 64-column half of every unit, warp 3
+    // the second, so waiting for one half's completion never delays the other's issue (bulk groups are per thread)
+    const int h = warp - 2;
     const bool leader = elect_one();
     uint32_t sf_n = 0;
     MLP16_FOR_UNITS {
       if (l == a.n_hidden - 1) continue;
-      const int m0 = (t0 + s * G) * RM;
+      MLP16_UNIT_SLOTS
+      const int m0 = (t0 + j * G) * RM;
       const CUtensorMap* mh = &maps.u[l & 1][0];
       const CUtensorMap* ml = &maps.u[l & 1][1];
-      for (int h = 0; h < 2; ++h) {
-        mbar_wait(stg_full, sf_n & 1u);
-        ++sf_n;
-        if (leader) {                                     // bulk groups are per thread: the same lane issues and waits
-          tma_store_2d(mh, stg, n0 + h * 64, m0);
-          tma_store_2d(ml, stg + TILE, n0 + h * 64, m0);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          if (h == 0) {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging may be overwritten
-            mbar_arrive(stg_empty);
-          } else {
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");        // both halves are in L2
-            mbar_arrive(stg_empty);
-            for (int r = 0; r < a.C; ++r) mbar_arrive_remote(ready(s), (uint32_t)r);
-            if (stamp && t0 == 0 && s == 0) a.dbg[l * 8 + 5] = clock64();
-          }
-        }
-        __syncwarp();
+      mbar_wait(stg_full(h), sf_n & 1u);
+      ++sf_n;
+      if (leader) {
+        if (stamp && t0 == 0 && j == 0 && h == 0) a.dbg[l * 8 + 5] = clock64();
+        tma_store_2d(mh, stg, n0 + h * 64, m0);
+        tma_store_2d(ml, stg + TILE, n0 + h * 64, m0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // staging may be overwritten
+        mbar_arrive(stg_empty);
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // this half (one k-block of the next layer) is in L2
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");               // ONE release for all peers ...
+        for (int r = 0; r < a.C; ++r) mbar_arrive_remote_relaxed(ready(s, h), (uint32_t)r);   // ... then relaxed arrives
+        if (stamp && t0 == 0 && j == 0) a.dbg[l * 8 + 6 + h] = clock64();
       }
+      __syncwarp();
     }
     __syncwarp();
   } else {
     // ================= epilogue: 16 warps = 4 TMEM lane quarters x 4 blocks of 16 columns, two 64-column halves =================
-    const int q = warp & 3, blk = (warp - 3) >> 2;
-    const int row = q * 32 + lane;                        // row inside the tile == TMEM lane
+    EpiCtx c;
+    c.q = warp & 3; c.blk = (warp - NCTRL) >> 2; c.lane = lane;
+    c.row = c.q * 32 + lane;                              // row inside the tile == TMEM lane
+    c.tmem = tmem; c.n0 = n0; c.rank = rank; c.M = M;
+    c.srow_hi = stg_ptr + c.row * 128; c.srow_lo = c.srow_hi + TILE;
+    c.stg_full0 = stg_full(0); c.stg_empty = stg_empty;
     uint32_t acc_n[2] = {0u, 0u}, se_n = 0;
-    unsigned char* srow_hi = stg_ptr + row * 128;
-    unsigned char* srow_lo = srow_hi + TILE;
     MLP16_FOR_UNITS {
-      const int m0 = (t0 + s * G) * RM, m = m0 + row;
+      MLP16_UNIT_SLOTS
+      const int m0 = (t0 + j * G) * RM;
       const bool last = (l == a.n_hidden - 1);
       const bool pre_skip = (l + 1 == a.skip_layer);
-      const int n_true = a.n_true[l];
       // bias (and, for the last layer, the sdf-row weights) of this warp's 2 x 16 columns: one value per lane, fetched
       // BEFORE the accumulator wait so the global-load latency hides behind the mainloop; broadcast by shuffle below
-      const int mycol = n0 + (lane >> 4) * 64 + blk * 16 + (lane & 15);
+      const int mycol = n0 + (lane >> 4) * 64 + c.blk * 16 + (lane & 15);
       const float mybias = __ldg(a.bias[l] + mycol);
       const float mywl = last ? __ldg(a.w_last + mycol) : 0.f;
       mbar_wait(acc_full(s), acc_n[s] & 1u);
       ++acc_n[s];
-      if (stamp && threadIdx.x == 96 && t0 == 0 && s == 0) a.dbg[l * 8 + 3] = clock64();
+      const bool st = stamp && threadIdx.x == NCTRL * 32 && t0 == 0 && j == 0;
+      if (st) a.dbg[l * 8 + 3] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float dot = 0.f;
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int c0 = h * 64 + blk * 16;                 // column inside the CTA's 128
-        uint32_t r0[16], rl[16];
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)s * ncol_slot + (uint32_t)c0;
-        tmem_ld16(taddr, r0);
-        if (a.nhh == 2) {
-          uint32_t r1[16];
-          tmem_ld16(taddr + 128u, r1);
-          tmem_ld16(taddr + 256u, rl);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int i = 0; i < 16; ++i) r0[i] = __float_as_uint(__fadd_rn(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
-        } else {
-          tmem_ld16(taddr + 128u, rl);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        }
-        if (h == 1) {                                     // this warp has drained its part of the slot's accumulators
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_free(s));
-        }
-        uint32_t ph[8], pl[8];                            // 16 outputs as packed halfs: hi and scaled lo
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float u[2];
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int i = g * 2 + j;
-            const float b = __shfl_sync(0xffffffffu, mybias, h * 16 + i);
-            const float z = fmaf(__uint_as_float(rl[i]), LO_INV, __uint_as_float(r0[i])) + b;
-            u[j] = softplus_fast(z, a.beta, a.inv_beta);
-          }
-          if (pre_skip) {   // cat(h, PE)/sqrt(2): warp-uniform branch, only the layer before the skip takes it
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int n = n0 + c0 + g * 2 + j;
-              if (n < n_true) {
-                u[j] = __fdiv_rn(u[j], IRONB_SQRT2F);
-              } else {
-                const int ce = n - n_true;
-                u[j] = 0.f;
-                if (ce < a.Edim && m < M) {
-                  const size_t o = (size_t)m * a.Epad + ce;
-                  u[j] = __fdiv_rn(fmaf(__half2float(a.Elo[o]), LO_INV, __half2float(a.Ehi[o])), IRONB_SQRT2F);
-                }
-              }
-            }
-          }
-          if (last) {
-            dot = fmaf(u[0], __shfl_sync(0xffffffffu, mywl, h * 16 + g * 2), dot);
-            dot = fmaf(u[1], __shfl_sync(0xffffffffu, mywl, h * 16 + g * 2 + 1), dot);
-          } else {
-            const __half2 hi2 = __floats2half2_rn(u[0], u[1]);
-            const float2 hf = __half22float2(hi2);
-            const __half2 lo2 = __floats2half2_rn((u[0] - hf.x) * LO_SCALE, (u[1] - hf.y) * LO_SCALE);
-            ph[g] = *reinterpret_cast<const uint32_t*>(&hi2);
-            pl[g] = *reinterpret_cast<const uint32_t*>(&lo2);
-          }
-        }
-        if (!last) {
-          mbar_wait(stg_empty, (se_n & 1u) ^ 1u);         // the previous half's TMA store has read the staging buffer
-          ++se_n;
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {                   // two 16-byte chunks (8 halfs each) per operand
-            const int off = (((blk * 2 + g) ^ (row & 7)) << 4);
-            *reinterpret_cast<uint4*>(srow_hi + off) = make_uint4(ph[g * 4], ph[g * 4 + 1], ph[g * 4 + 2], ph[g * 4 + 3]);
-            *reinterpret_cast<uint4*>(srow_lo + off) = make_uint4(pl[g * 4], pl[g * 4 + 1], pl[g * 4 + 2], pl[g * 4 + 3]);
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the TMA store engine
-          __syncwarp();
-          if (lane == 0) mbar_arrive(stg_full);
-        }
-      }
-      if (last && m < M) a.Fpart[(size_t)(rank * 4 + blk) * a.cap + m] = dot;
-      if (stamp && threadIdx.x == 96 && t0 == 0 && s == 0) a.dbg[l * 8 + 4] = clock64();
+      const uint32_t tfree = tmem_free(s);
+      if (last) epi_unit<false, true>(a, c, l, s, m0, mybias, mywl, tfree, se_n);
+      else if (pre_skip) epi_unit<true, false>(a, c, l, s, m0, mybias, mywl, tfree, se_n);
+      else epi_unit<false, false>(a, c, l, s, m0, mybias, mywl, tfree, se_n);
+      if (st) a.dbg[l * 8 + 4] = clock64();
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -451,8 +483,8 @@ int mlp16_nhh() {
 
 // maps: e[2], u[2][2], w[n_hidden][2] (hi, lo), all fp16 with 64 x 128 boxes.
 int launch_trace_mlp_h16(const ironb_mlp_layout* lay, const float* packed, const CUtensorMap* mE, const CUtensorMap* mU,
-                         const CUtensorMap* mW, const void* Ehi, const void* Elo, float* Fpart, int rows_cap, int cap,
-                         const int* m_dev, int m_mul, cudaStream_t st) {
+                         const CUtensorMap* mW, const void* Ehi, const void* Elo, void* const* Uhi, void* const* Ulo,
+                         float* Fpart, int rows_cap, int cap, const int* m_dev, int m_mul, cudaStream_t st) {
   using namespace mlp16;
   if (!trace_mlp_fused_supported(lay)) return IRONB_ENOSUP;
   const int H = lay->d_hidden, last = lay->n_lin - 1, C = H / 128;
@@ -470,11 +502,13 @@ int launch_trace_mlp_h16(const ironb_mlp_layout* lay, const float* packed, const
   }
   a.w_last = packed + lay->off_w[last];
   a.Ehi = reinterpret_cast<const __half*>(Ehi); a.Elo = reinterpret_cast<const __half*>(Elo);
+  for (int b = 0; b < 2; ++b) { a.Uhi[b] = reinterpret_cast<__half*>(Uhi[b]); a.Ulo[b] = reinterpret_cast<__half*>(Ulo[b]); }
   a.Fpart = Fpart;
   a.n_hidden = last; a.skip_layer = lay->skip_layer; a.Epad = lay->in_pad[0]; a.Edim = lay->pe_dim; a.H = H; a.C = C;
-  a.beta = lay->beta; a.inv_beta = 1.0f / lay->beta;
+  a.nbl2e = (float)(-(double)lay->beta * 1.4426950408889634); a.ln2_ib = (float)(0.6931471805599453 / (double)lay->beta);
   a.m_dev = m_dev; a.m_mul = m_mul; a.rows_cap = rows_cap; a.cap = cap;
   a.nhh = mlp16_nhh();
+  { static int preb = -1; if (preb < 0) { const char* e = getenv("IRONB_MLP_PREB"); preb = (e && atoi(e) >= 1 && atoi(e) <= NSTAGE) ? atoi(e) : NSTAGE; } a.preb = preb; }
   a.dbg = g_mlp_dbg;
 
   cudaLaunchConfig_t cfg;

@@ -32,8 +32,8 @@ int launch_trace_mlp_fused(const ironb_mlp_layout* lay, const float* packed, con
 // fp16x2-split version (mlp_h16.cu): operands are fp16 hi and fp16 (x - hi) * 2^11
 int split_weights_h(const float* src, int64_t n, void* hi, void* lo, cudaStream_t st);
 int launch_trace_mlp_h16(const ironb_mlp_layout* lay, const float* packed, const CUtensorMap* mE, const CUtensorMap* mU,
-                         const CUtensorMap* mW, const void* Ehi, const void* Elo, float* Fpart, int rows_cap, int cap,
-                         const int* m_dev, int m_mul, cudaStream_t st);
+                         const CUtensorMap* mW, const void* Ehi, const void* Elo, void* const* Uhi, void* const* Ulo,
+                         float* Fpart, int rows_cap, int cap, const int* m_dev, int m_mul, cudaStream_t st);
 
 namespace {
 
@@ -451,7 +451,11 @@ int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float*
   // one MLP evaluation of the first (*m_dev x m_mul) rows: all hidden layers + the sdf row in one cluster launch
   // (mlp_h16.cu: fp16x2 split, two tiles in flight; mlp_tc.cu: 3xTF32)
   auto mlp = [&](int rows_cap, const int* m_dev, int m_mul) -> int {
-    if (f16) return launch_trace_mlp_h16(lay, packed, mE, mU, mW, w.Ehi, w.Elo, w.Fpart, rows_cap, (int)w.cap, m_dev, m_mul, st);
+    if (f16) {
+      void* uh[2] = {w.Uhi[0], w.Uhi[1]};
+      void* ul[2] = {w.Ulo[0], w.Ulo[1]};
+      return launch_trace_mlp_h16(lay, packed, mE, mU, mW, w.Ehi, w.Elo, uh, ul, w.Fpart, rows_cap, (int)w.cap, m_dev, m_mul, st);
+    }
     return launch_trace_mlp_fused(lay, packed, mE, mU, mW, w.Ehi, w.Elo, w.Uhi, w.Ulo, w.Fpart, rows_cap, (int)w.cap, m_dev, m_mul, st);
   };
   const int nb = (int)ceil_div64(N * PE_T, 256);    // st_* / bis_* kernels: PE_T threads per work item

@@ -22,6 +22,7 @@ from oracle import iron_oracle as O  # noqa: E402  (camera constants only)
 ap = argparse.ArgumentParser()
 ap.add_argument("--big", action="store_true")
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--timeline-only", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 lib = _lib.load()
@@ -56,7 +57,7 @@ def sdf64(net, x):
 
 
 g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "sdf_seeded.npz")))
-for H in (256, 512):
+for H in (() if a.timeline_only else (256, 512)):
     net = mknet(H)
     x = torch.from_numpy(g[f"h{H}.x"]).to(dev)
     xs = torch.cat([x, (torch.rand(8192, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(5)) - 0.5) * 1.6])
@@ -80,6 +81,8 @@ cam512 = ib.Camera(512, 512, K, W2C)
 cases = [(512, 64, (224, 224)), (256, 64, (224, 224)), (512, 64, (330, 236))]
 if a.big:
     cases += [(512, 256, (128, 128)), (256, 256, (128, 128))]
+if a.timeline_only:
+    cases = []
 for H, S, ul in cases:
     net = mknet(H)
     cam, _, _ = cam512.crop_region(S, S, ul_corner=ul)
@@ -129,6 +132,6 @@ if os.environ.get("IRONB_MLP_DBG"):
     v = list(buf)
     t0 = v[0]
     print("mlp_h16 timeline, cluster 0 / rank 0 / first tile (cycles from layer-0 start): wait-full-start, first-full, mma-issued, "
-          "acc-ready, epi-done, ready-signalled")
+          "acc-ready, epi-done, half-0 staged (store warp), half-0 ready-signalled, half-1 ready-signalled")
     for l in range(8):
-        print(l, [x - t0 if x else 0 for x in v[l * 8:l * 8 + 6]])
+        print(l, [x - t0 if x else 0 for x in v[l * 8:l * 8 + 8]])
