@@ -46,67 +46,66 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
+    """SM clock + throttle reasons DURING the timed region, sampled synchronously on the main thread of rank 0 right after a
+    timed step has been enqueued (the GPU is still executing it), i.e. in the gap between two CUDA-event pairs.
+
+    Why not the recipe's `nvidia-smi -lms 50` loop or an NVML polling thread: on these boxes single NVML queries take up to
+    40-130 ms (clock query up to 1.7 s during start-up) and stall concurrent kernel launches; both variants put a 40-120 ms
+    outlier into one timed step in about half of the runs (measured, profiles/README.md).  A synchronous query between two
+    event pairs cannot overlap a timed step."""
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index: int):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.rows = []          # (epoch s, sm MHz, max MHz, [reasons])
+        self.slow = 0.0
+        self.index = index
+        self.nv = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.bits = (("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                         ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                         ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                         ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+            self.get_reasons = (getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None)
+                                or nv.nvmlDeviceGetCurrentClocksThrottleReasons)
+            self.nv = nv
+            self.how = "pynvml, synchronous, between timed steps"
         except Exception:
-            self.p = None
+            self.how = "nvidia-smi one-shot queries, between timed steps"
 
-    def wait_first(self, timeout=5.0):
-        """Blocks until nvidia-smi has written its first sample: its start-up (NVML init) stalls kernel launches for tens
-        of milliseconds, which must not land inside the timed region (it did: one 15-58 ms step per run)."""
-        t0 = time.time()
-        while self.p is not None and time.time() - t0 < timeout:
-            try:
-                if os.path.getsize(self.f.name) > 0:
-                    return
-            except OSError:
-                return
-            time.sleep(0.02)
+    def sample(self):
+        t0 = time.perf_counter()
+        try:
+            if self.nv is not None:
+                sm = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = int(self.get_reasons(self.h))
+                self.rows.append((time.time(), sm, self.mx, [nm for nm, b in self.bits if r & b]))
+            else:
+                q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+                parts = [x.strip() for x in out.split(",")]
+                self.rows.append((time.time(), float(parts[0]), float(parts[1]),
+                                  [nm for nm, v in zip(self.NAMES, parts[2:6]) if v.lower().startswith("active")]))
+        except Exception:
+            pass
+        self.slow = max(self.slow, (time.perf_counter() - t0) * 1e3)
 
     def stop(self, t_begin=None, t_end=None):
-        """Median SM clock / throttle reasons of the samples whose timestamp falls inside [t_begin, t_end] (epoch s);
-        all samples when none does (very short timed regions)."""
-        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        rows = []
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in self.f.read().splitlines():
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 8:
-                continue
-            try:
-                ts = datetime.datetime.strptime(parts[7], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                rows.append((ts, float(parts[0]), float(parts[1]), [nm for nm, v in zip(names, parts[3:7]) if v.lower().startswith("active")]))
-            except ValueError:
-                continue
-        inside = [r for r in rows if t_begin is not None and t_begin - 0.05 <= r[0] <= t_end + 0.05]
-        use = inside if inside else rows
-        sm = [r[1] for r in use]
-        mx = [r[2] for r in use]
-        reasons = set(x for r in use for x in r[3])
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
-                   "samples_inside_timed_region": len(inside)}
+        inside = [r for r in self.rows if t_begin is not None and t_begin <= r[0] <= t_end]
+        use = inside if inside else self.rows
+        if use:
+            out = {"sm_mhz": statistics.median([r[1] for r in use]), "sm_max_mhz": max(r[2] for r in use),
+                   "reasons": sorted(set(x for r in use for x in r[3])), "samples": len(use),
+                   "samples_inside_timed_region": len(inside), "sampler": self.how,
+                   "slowest_query_ms": round(self.slow, 2)}
         return out
 
 
@@ -256,7 +255,9 @@ def workload_config(args, patch):
             "sharding": "every rank traces/shades its own copy of the same crop (identical work per GPU), own target/eikonal seeds", "parallelism": f"dp{args.gpus} (rays sharded, weights replicated)",
             "l2": "256 MiB flush between steps, outside the per-step CUDA-event pairs",
             "init": "seed-0 geometric init, light=32",
-            "fill_holes_and_edge_sampling": bool(getattr(args, "driver_defaults", False))}
+            "fill_holes_and_edge_sampling": bool(getattr(args, "driver_defaults", False)),
+            "shading": ("dense: every ray of the patch is shaded and non-hit pixels are masked afterwards (no hit-count read-back)"
+                        if getattr(args, "shading", "dense") == "dense" else "compact: hits compacted first (one host sync per step)")}
 
 
 # ------------------------------------------------------------------------------------------ CUDA arm
@@ -267,6 +268,8 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # NVML is initialised before anything else (its start-up is slow and must not run next to the timed loop)
+    sampler = ClockSampler(local) if (rank == 0 and not args.no_clocks) else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -333,7 +336,7 @@ def run_ours(args):
                 return r
             tracer.forward = timed
         loss, res = ib.stage2_step(sdf, nets, tracer, render_fn, cam_, target_, eik_, fill_holes=args.driver_defaults,
-                                   handle_edges=args.driver_defaults)
+                                   handle_edges=args.driver_defaults, dense_shading=(args.shading == "dense"))
         if time_trace:
             tracer.forward = orig
             trace_ms.append(evs)
@@ -346,17 +349,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.wait_first()
     # the cyclic garbage collector is paused over warm-up + timed loops: a generation-2 pass over the module graph landed
     # deterministically inside the 4th timed step (10-58 ms of host stall with the GPU idle)
     import gc
     gc.collect()
     gc.disable()
-    # ---- warm-up
-    for _ in range(max(args.warmup, 3)):
+    # ---- warm-up: W steps (>= 3), extended to >= 0.5 s of continuous load.  ~60-80 ms after the GPU goes from idle to
+    # busy the driver stalls launches once (1-2 ms alone, 40-120 ms when an NVML query is in flight at that moment --
+    # measured, see profiles/README.md); that transition belongs to the warm-up, not to the timed steps.
+    n_warm = 0
+    t_w = time.perf_counter()
+    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_w < 0.5:
         step(cam, target, eik)
+        n_warm += 1
+        if n_warm % 4 == 0:
+            torch.cuda.synchronize()
     barrier()
 
     # ---- timed: K steps, per-step CUDA events, L2 flushed between steps
@@ -367,13 +374,21 @@ def run_ours(args):
     barrier()
     wall0 = time.perf_counter()
     epoch0 = time.time()
-    for _ in range(args.steps):
+    sample_after = {args.steps // 3, (2 * args.steps) // 3, args.steps - 1}
+    for i in range(args.steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         loss, res = step(cam, target, eik, time_trace=True)
         e1.record()
         evs.append((e0, e1))
+        if i in sample_after:
+            # clocks under load: queried right after step i was enqueued (the GPU is still running it), in the gap between
+            # two event pairs; with several ranks everybody re-aligns afterwards so a slow query cannot leak into a step
+            if sampler:
+                sampler.sample()
+            if world > 1:
+                barrier()
     barrier()
     wall = time.perf_counter() - wall0
     epoch1 = time.time()
@@ -391,13 +406,16 @@ def run_ours(args):
     value = rays_total / (total_ms * 1e-3)
 
     # ---- e2e: same step through the public API from pinned host buffers (H2D + D2H inside the timed region)
+    loss, _ = step(make_cam(K_h, W2C_h), target_h.to(dev, non_blocking=True), eik_h.to(dev, non_blocking=True))   # untimed
+    float(loss.item())
     barrier()
     e2e_steps = args.steps
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        Kd, Wd = K_h.to(dev, non_blocking=True), W2C_h.to(dev, non_blocking=True)
+        # the camera is built from the HOST matrices (inverted on the host; K, W2C and their inverses are uploaded from
+        # pinned memory: 4 x 64 B), the target patch and the eikonal samples are copied from pinned host buffers
         tg, ek = target_h.to(dev, non_blocking=True), eik_h.to(dev, non_blocking=True)
-        loss, _ = step(make_cam(Kd, Wd), tg, ek)
+        loss, _ = step(make_cam(K_h, W2C_h), tg, ek)
         loss_host = float(loss.item())          # D2H of the step's result
     barrier()
     e2e_t = time.perf_counter() - t0
@@ -405,8 +423,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = S * S * world * e2e_steps / float(te.item())
-    h2d = K_h.numel() * 4 + W2C_h.numel() * 4 + target_h.numel() * 4 + eik_h.numel() * 4
-    d2h = 4 + 4   # loss + the hit count the shading chunk reads back
+    h2d = 2 * 4 * 16 * 4 + target_h.numel() * 4 + eik_h.numel() * 4   # two cameras (full view + crop) x 4 matrices, patch, samples
+    d2h = 4 + (0 if args.shading == "dense" else 4)   # loss (+ the hit count the shading chunk reads back when compacting)
 
     gc.enable()
     clocks = sampler.stop(epoch0, epoch1) if sampler else None
@@ -430,7 +448,7 @@ def run_ours(args):
                          "arithmetic is peak/6 (tf32 = 1/2 bf16 rate, x3 MMAs)")
             split_cost = 6.0
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, S),
             "clocks": clocks,
@@ -474,6 +492,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--driver-defaults", action="store_true",
                     help="also run hole filling + edge sampling (the reference drivers' fill_holes=True, handle_edges=True)")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample clocks (diagnosing sampler interference)")
+    ap.add_argument("--shading", default="dense", choices=["dense", "compact"],
+                    help="dense: shade every ray and mask (no hit-count read-back, host runs ahead of the tracer); compact: the "
+                         "reference's order (compact the hits first: one host sync per step)")
     ap.add_argument("--tracer", default="default", choices=["default", "batched", "tf32", "fused"])
     ap.add_argument("--gemm", default="default", choices=["default", "tcgen05", "ffma"])
     args = ap.parse_args()

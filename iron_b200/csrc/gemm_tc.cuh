@@ -20,6 +20,7 @@
 #include "gemm.cuh"
 
 namespace ironb {
+extern long long* g_mlp_dbg;   // mlp_tc.cu: optional clock64 stamp buffer (ironb_debug_mlp_timeline)
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
@@ -29,6 +30,8 @@ constexpr int HI_BYTES = 2 * TILE_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers + tmem ptr*/;
 constexpr int NTHREADS = 320;                      // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2-9 split + epilogue
 constexpr int NSPLIT = 256;
+constexpr int NGRP = 2;                            // splitter warps work as NGRP groups on alternate stages, so one group's
+constexpr int NSPLIT_G = NSPLIT / NGRP;            // proxy fence + barrier latency overlaps the other group's conversion
 constexpr uint32_t TMEM_COLS = 512;               // three 128-column accumulators (even k-steps, odd k-steps, lo-terms)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -152,7 +155,9 @@ __device__ __forceinline__ void split_stage(float4* __restrict__ hi, float4* __r
 template <class Epi>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N, int K,
-                  Epi epi, const int* __restrict__ m_dev, int m_mul, int write_hi, int k_chunk) {
+                  Epi epi, const int* __restrict__ m_dev, int m_mul, int write_hi, int k_chunk, long long* dbg) {
+  const bool stamp = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (stamp && threadIdx.x == 0) dbg[0] = clock64();
   if (m_dev != nullptr) {   // row count produced on the device (compacted ray lists): whole CTAs beyond it leave at once
     const int md = *m_dev * m_mul;
     if (md < M) M = md;
@@ -183,7 +188,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full(s), 1);
-      mbar_init(conv(s), NSPLIT);
+      mbar_init(conv(s), NSPLIT_G);
       mbar_init(empty(s), 1);
     }
     mbar_init(acc_bar, 1);
@@ -197,6 +202,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot_ptr;
+  if (stamp && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
     // ================= TMA producer (warp-uniform loop: addresses stay in uniform registers; elected lane issues) ====
@@ -220,6 +226,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
       mbar_wait(conv(s), ph);
+      if (stamp && leader && it == 0) dbg[3] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t st = base + s * STAGE_BYTES;
       const uint64_t a_hi = make_desc(st), b_hi = make_desc(st + TILE_BYTES);
@@ -241,23 +248,28 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       if (leader) tc_commit(empty(s));          // slot free once these MMAs have read it
     }
     if (leader) tc_commit(acc_bar);             // accumulator complete
+    if (stamp && leader) dbg[4] = clock64();
     __syncwarp();
   } else {
     // ================= splitter, then epilogue (warps 2..9) =================
     const int t = threadIdx.x - 64;   // 0..255
-    for (int it = 0; it < nk; ++it) {
+    const int grp = t / NSPLIT_G, tg = t % NSPLIT_G;
+    for (int it = grp; it < nk; it += NGRP) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
       mbar_wait(full(s), ph);
+      if (stamp && t == 0 && it == 0) dbg[2] = clock64();
       float4* hi = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES);
       float4* lo = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES + HI_BYTES);
-      split_stage(hi, lo, t, NSPLIT, HI_BYTES / 16 / NSPLIT, write_hi);
+      split_stage(hi, lo, tg, NSPLIT_G, HI_BYTES / 16 / NSPLIT_G, write_hi);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
       mbar_arrive(conv(s));
     }
     // epilogue, phase 1: TMEM (lane = tile row; warp%4 selects the 32-lane quarter, (warp-2)/4 the 64-column half) ->
     // registers (the three accumulators are added in fp32 RN) -> a row-major fp32 tile in the idle pipeline stages
+    if (stamp && t == 0) dbg[5] = clock64();
     mbar_wait(acc_bar, 0);
+    if (stamp && t == 0) dbg[6] = clock64();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     constexpr int TLD = BN + 4;                       // padded row pitch: conflict-free 128-bit rows
     float* tile = reinterpret_cast<float*>(base_ptr);
@@ -282,6 +294,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (stamp && t == 0) dbg[7] = clock64();
     // phase 2: one warp per tile row, lanes along the columns: every global access of the epilogue functor (bias,
     // saved activations, outputs) is a coalesced 512-byte row segment
     const int w8 = warp - 2;
@@ -299,6 +312,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (stamp && threadIdx.x == 0) dbg[8] = clock64();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
@@ -330,7 +344,8 @@ int launch_gemm_nt_tc_maps(const CUtensorMap& mA, const CUtensorMap& mB, int M, 
     configured = true;
   }
   dim3 grid((unsigned)ceil_div64(N, BN), (unsigned)ceil_div64(M, BM), (unsigned)(k_chunk > 0 ? ceil_div64(K, k_chunk) : 1));
-  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mB, M, N, K, epi, m_dev, m_mul, write_hi, k_chunk);
+  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mB, M, N, K, epi, m_dev, m_mul, write_hi, k_chunk,
+                                           g_mlp_dbg ? g_mlp_dbg + 256 : nullptr);   // IRONB debug timeline (last launch wins)
   IRONB_CHECK_LAUNCH(what);
   return IRONB_OK;
 }

@@ -463,7 +463,6 @@ __global__ void __launch_bounds__(256) split_array_h_kernel(const float* __restr
 
 }  // namespace mlp16
 
-extern long long* g_mlp_dbg;
 
 int split_weights_h(const float* src, int64_t n, void* hi, void* lo, cudaStream_t st) {
   mlp16::split_array_h_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(src, n, reinterpret_cast<__half*>(hi),

@@ -9,11 +9,11 @@ from .raytracer import render_camera
 
 
 def stage2_step(sdf_network, color_network_dict, raytracer, render_fn, camera, target, eik_points, eik_weight=0.1,
-                max_num_rays=50000, fill_holes=False, handle_edges=False):
+                max_num_rays=50000, fill_holes=False, handle_edges=False, dense_shading=False):
     """Leaves gradients in .grad of every parameter; returns (loss, results).  fill_holes / handle_edges = True is the
     reference drivers' default configuration (render_surface.py:521-549)."""
     results = render_camera(camera, sdf_network, raytracer, color_network_dict, render_fn, fill_holes=fill_holes,
-                            handle_edges=handle_edges, is_training=True)
+                            handle_edges=handle_edges, is_training=True, dense_shading=dense_shading)
     mask = results["convergent_mask"]
     if handle_edges:
         mask = mask | results["edge_mask"]                                # render_surface.py:566-567

@@ -131,3 +131,33 @@ def test_step_with_edges_golden(golden, trace_mode):
         worst = max(worst, e)
         assert e <= tol, (k, e, same)
     print(f"[{trace_mode}] step+edges parity: identical masks={same}, worst gradient-norm error {worst:.2e}")
+
+
+def test_dense_shading_matches_compacted_shading(golden):
+    """dense_shading=True (shade every ray, mask afterwards: no hit-count read-back) must reproduce the reference order
+    (compact the hits first) on the silhouette crop, where half of the rays miss: identical masks and dense buffers, loss
+    and parameter gradients equal up to the summation order of the weight gradients."""
+    g = golden("step_h256")
+    outs = []
+    for dense in (False, True):
+        ib, sdf, nets, cam512 = build()
+        cam, _, _ = cam512.crop_region(32, 32, ul_corner=tuple(int(v) for v in g["ul"]))
+        rend = ib.GGXColocatedRenderer(use_cuda=True)
+        loss, res = ib.stage2_step(sdf, nets, ib.RayTracer(), ib.make_render_fn(rend), cam, T(g["target"]).to(DEV),
+                                   T(g["eik_points"]).to(DEV), eik_weight=0.1, dense_shading=dense)
+        grads = {"sdf." + k: p.grad.clone() for k, p in sdf.named_parameters()}
+        for nm in ("diffuse_albedo_network", "specular_albedo_network", "specular_roughness_network", "point_light_network"):
+            grads.update({nm + "." + k: p.grad.clone() for k, p in nets[nm].named_parameters()})
+        outs.append((float(loss), res, grads))
+    (l0, r0, g0), (l1, r1, g1) = outs
+    assert torch.equal(r0["convergent_mask"], r1["convergent_mask"])
+    assert 0 < int(r0["convergent_mask"].sum()) < r0["convergent_mask"].numel()      # the crop really has misses
+    for k in ("color", "diffuse_color", "specular_color", "diffuse_albedo", "specular_albedo", "specular_roughness", "normal"):
+        a, b = r0[k].detach(), r1[k].detach()
+        assert a.shape == b.shape, k
+        assert float((a - b).abs().max()) <= 1e-6, (k, float((a - b).abs().max()))
+        assert float(b[~r0["convergent_mask"]].abs().max()) == 0.0, k              # non-hit pixels are exactly zero
+    assert abs(l0 - l1) <= 1e-6 * abs(l0), (l0, l1)
+    worst = max(rel_l2(g1[k].cpu().numpy(), g0[k].cpu().numpy()) for k in g0)
+    print(f"dense vs compact shading: loss {l1:.7f}/{l0:.7f}, worst gradient rel-L2 {worst:.2e}")
+    assert worst <= 1e-4, worst

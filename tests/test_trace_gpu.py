@@ -147,3 +147,18 @@ def test_trace_h512_vs_oracle(trace_mode):
     assert (m == mr).mean() >= 0.999, f"mask agreement {(m == mr).mean()}"
     both = m & mr
     assert_close(res["distance"].cpu().numpy()[both], ref["distance"].numpy()[both], TOL_DEPTH, what="distance", frac=0.999)
+
+
+def test_camera_from_host_matrices_matches_device_camera():
+    """Camera built from HOST K / W2C (inverted on the host, no device sync) gives the rays of the device-built camera."""
+    import iron_b200
+    Kh = torch.tensor(O.FIXTURE_K, dtype=torch.float64).reshape(4, 4).float()
+    Wh = torch.tensor(O.FIXTURE_W2C, dtype=torch.float64).reshape(4, 4).float()
+    cd, _, _ = iron_b200.Camera(512, 512, Kh.to(DEV), Wh.to(DEV)).crop_region(64, 64, ul_corner=(300, 200))
+    ch, _, _ = iron_b200.Camera(512, 512, Kh, Wh).crop_region(64, 64, ul_corner=(300, 200))
+    for a, b in zip(cd.get_rays(cd.get_uv()), ch.get_rays(ch.get_uv())):
+        assert_close(a.cpu().numpy(), b.cpu().numpy(), 3e-7, what="host-built camera rays")
+    ch2, _ = iron_b200.Camera(512, 512, Kh, Wh).resize(0.5)
+    cd2, _ = iron_b200.Camera(512, 512, Kh.to(DEV), Wh.to(DEV)).resize(0.5)
+    for a, b in zip(cd2.get_rays(cd2.get_uv()), ch2.get_rays(ch2.get_uv())):
+        assert_close(a.cpu().numpy(), b.cpu().numpy(), 3e-7, what="host-built resized camera rays")
