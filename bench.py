@@ -204,7 +204,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def ggx_microbench(dev, pk):
@@ -256,6 +256,9 @@ def workload_config(args, patch):
             "l2": "256 MiB flush between steps, outside the per-step CUDA-event pairs",
             "init": "seed-0 geometric init, light=32",
             "fill_holes_and_edge_sampling": bool(getattr(args, "driver_defaults", False)),
+            "execution": ("one CUDA-graph replay per step (iron_b200.GraphedStage2Step)" if getattr(args, "exec_mode", "graph") == "graph"
+                          and getattr(args, "shading", "dense") == "dense" and not getattr(args, "driver_defaults", False)
+                          else "eager (Python enqueues every kernel)"),
             "shading": ("dense: every ray of the patch is shaded and non-hit pixels are masked afterwards (no hit-count read-back)"
                         if getattr(args, "shading", "dense") == "dense" else "compact: hits compacted first (one host sync per step)")}
 
@@ -320,7 +323,20 @@ def run_ours(args):
 
     trace_ms = []
 
+    use_graph = args.exec_mode == "graph" and args.shading == "dense" and not args.driver_defaults
+    gs = None
+    if use_graph:
+        tracer.collect_stats = True
+        gs = ib.GraphedStage2Step(sdf, nets, tracer, render_fn, K_h, W2C_h, (S, S), S * S // 2, crop_ul=ul, time_tracer=True)
+        gs.step(target=target_h, eik_points=eik_h)
+        torch.cuda.synchronize()
+
     def step(cam_, target_, eik_, time_trace=False):
+        if gs is not None:           # inputs are already in the graph's static buffers (cam_/target_/eik_ are those values)
+            gs.graph.replay()
+            if world > 1:
+                allreduce_gradients(params, world)
+            return gs.loss, gs.results
         for p in params:
             p.grad = None
         if time_trace:   # time the dominant kernel (the tracer's four phase launches) on the launching stream
@@ -367,7 +383,8 @@ def run_ours(args):
     barrier()
 
     # ---- timed: K steps, per-step CUDA events, L2 flushed between steps
-    tracer.last_stats = None
+    if gs is None:
+        tracer.last_stats = None
     l0 = lib.ironb_launch_count()
     evs = []
     hits = 0
@@ -395,8 +412,17 @@ def run_ours(args):
     launches = lib.ironb_launch_count() - l0
     step_ms = [a.elapsed_time(b) for a, b in evs]
     my_ms = sum(step_ms)
-    tr_ms = [sum(a.elapsed_time(b) for a, b in ev) for ev in trace_ms]
-    stats = tracer.last_stats.cpu().tolist()
+    if gs is not None:
+        # one graph replay per step: the library's kernels are graph nodes (counted at capture); the tracer's device time
+        # comes from two external-event nodes inside the graph, readable for the last replay
+        launches = gs.kernels_per_replay * args.steps
+        tms = gs.tracer_ms()
+        tr_ms = [tms] * args.steps
+        stats = [v * args.steps for v in tracer.last_stats.cpu().tolist()]
+        stats[5] = stats[5] // args.steps
+    else:
+        tr_ms = [sum(a.elapsed_time(b) for a, b in ev) for ev in trace_ms]
+        stats = tracer.last_stats.cpu().tolist()
     hits = int(res["convergent_mask"].sum().item())
     t = torch.tensor([my_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -406,17 +432,23 @@ def run_ours(args):
     value = rays_total / (total_ms * 1e-3)
 
     # ---- e2e: same step through the public API from pinned host buffers (H2D + D2H inside the timed region)
-    loss, _ = step(make_cam(K_h, W2C_h), target_h.to(dev, non_blocking=True), eik_h.to(dev, non_blocking=True))   # untimed
-    float(loss.item())
+    def e2e_step():
+        if gs is not None:     # H2D into the graph's static buffers (patch, samples, camera matrices), replay, all-reduce
+            gs.step(target=target_h, eik_points=eik_h, K=K_h, W2C=W2C_h)
+            if world > 1:
+                allreduce_gradients(params, world)
+            return gs.loss
+        # the camera is built from the HOST matrices (inverted on the host; K, W2C and their inverses are uploaded from
+        # pinned memory), the target patch and the eikonal samples are copied from pinned host buffers
+        tg, ek = target_h.to(dev, non_blocking=True), eik_h.to(dev, non_blocking=True)
+        return step(make_cam(K_h, W2C_h), tg, ek)[0]
+
+    float(e2e_step().item())   # untimed
     barrier()
     e2e_steps = args.steps
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        # the camera is built from the HOST matrices (inverted on the host; K, W2C and their inverses are uploaded from
-        # pinned memory: 4 x 64 B), the target patch and the eikonal samples are copied from pinned host buffers
-        tg, ek = target_h.to(dev, non_blocking=True), eik_h.to(dev, non_blocking=True)
-        loss, _ = step(make_cam(K_h, W2C_h), tg, ek)
-        loss_host = float(loss.item())          # D2H of the step's result
+        loss_host = float(e2e_step().item())          # D2H of the step's result
     barrier()
     e2e_t = time.perf_counter() - t0
     te = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
@@ -475,13 +507,31 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             line["ggx_roofline"] = ggx_microbench(dev, pk)
             line["cpu_baseline"] = cpu_baseline(H, S)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the process's real stdout; everything else written to fd 1 meanwhile (NCCL prints
+    'NCCL version ...' there) has been routed to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)             # C-level writers to stdout (NCCL banner) must not precede the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -492,6 +542,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--driver-defaults", action="store_true",
                     help="also run hole filling + edge sampling (the reference drivers' fill_holes=True, handle_edges=True)")
+    ap.add_argument("--exec", dest="exec_mode", default="graph", choices=["graph", "eager"],
+                    help="graph: the whole step is one CUDA-graph replay (iron_b200.GraphedStage2Step; needs --shading dense); "
+                         "eager: ~700 launches per step from Python")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample clocks (diagnosing sampler interference)")
     ap.add_argument("--shading", default="dense", choices=["dense", "compact"],
                     help="dense: shade every ray and mask (no hit-count read-back, host runs ahead of the tracer); compact: the "

@@ -10,11 +10,11 @@ from .render_fn import make_render_fn
 from .renderer_ggx import GGXColocatedRenderer
 from .rendering_func import get_materials
 from .embedder import get_embedder
-from .step import stage2_step
+from .step import GraphedStage2Step, stage2_step
 
 __all__ = [
     "SDFNetwork", "RenderingNetwork", "PointLightNetwork", "GGXColocatedRenderer", "RayTracer", "Camera",
     "intersect_sphere", "raytrace_pixels", "raytrace_camera", "render_camera", "render_normal_and_color",
-    "reparam_points", "locate_edge_points", "render_edge_pixels", "get_materials", "get_embedder", "make_render_fn", "stage2_step",
+    "reparam_points", "locate_edge_points", "render_edge_pixels", "get_materials", "get_embedder", "make_render_fn", "stage2_step", "GraphedStage2Step",
     "init_sdf_network_dict", "init_rendering_network_dict", "choose_renderer",
 ]

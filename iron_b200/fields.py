@@ -77,7 +77,8 @@ class _FoldedMLP(nn.Module):
         """Packed effective weights W = v * g/||v|| (+ transposes, biases), refolded when a parameter changed."""
         params = self._param_list()
         key = tuple((p.data_ptr(), p._version) for p in params)
-        if getattr(self, "_fold_key", None) == key and self._fold_buf is not None:
+        # under CUDA-graph capture the fold must be part of the graph (the parameters change between replays)
+        if getattr(self, "_fold_key", None) == key and self._fold_buf is not None and not torch.cuda.is_current_stream_capturing():
             return self._fold_buf
         dev = params[0].device
         v, g, b = self._v_g_b()

@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import torch
 
-from .raytracer import render_camera
+from .raytracer import Camera, render_camera
 
 
 def stage2_step(sdf_network, color_network_dict, raytracer, render_fn, camera, target, eik_points, eik_weight=0.1,
@@ -32,3 +32,113 @@ def stage2_step(sdf_network, color_network_dict, raytracer, render_fn, camera, t
     loss = img + eik / (eik_cnt + n_hit) * eik_weight
     loss.backward()
     return loss.detach(), results
+
+
+class GraphedStage2Step:
+    """stage2_step captured ONCE into a CUDA graph and replayed per step (not in the reference: its loop is eager PyTorch).
+
+    The eager step issues ~700 kernel launches (77 of them the tracer's fixed schedule) from Python / ctypes; at 4,096 rays
+    the host needs about as long to enqueue them as the GPU needs to run them.  With `dense_shading` the step has no host
+    read-back and only static shapes, so the whole thing -- weight-norm fold, trace, get_all, shading, loss, backward,
+    weight-norm chain rule -- is one `cudaGraphLaunch`.  Inputs live in static device buffers:
+
+        g = GraphedStage2Step(sdf, nets, raytracer, render_fn, K_host, W2C_host, target_shape=(64, 64), n_eik=2048,
+                              crop_ul=(224, 224))
+        loss = g.step(target=target_pinned, eik_points=eik_pinned, K=K_host, W2C=W2C_host)   # any subset may be updated
+        # gradients are in .grad of every parameter (static tensors, rewritten by every replay); g.results holds the
+        # step's dense buffers (valid until the next replay).  Parameters may be updated in place between steps (the fold
+        # is part of the graph); their storage must not be reallocated.  Build it before any eager backward through the
+        # same parameters (their AccumulateGrad nodes remember the stream they were created on).
+
+    Limits: fixed patch size / eikonal count / tracer settings; no fill_holes / edge sampling (both read counts back)."""
+
+    def __init__(self, sdf_network, color_network_dict, raytracer, render_fn, K, W2C, target_shape, n_eik, crop_ul=None,
+                 full_size=(512, 512), eik_weight=0.1, warmup=3, time_tracer=False):
+        import torch.cuda
+        self.sdf, self.nets, self.raytracer, self.render_fn = sdf_network, color_network_dict, raytracer, render_fn
+        self.eik_weight = eik_weight
+        self.full_size, self.crop_ul = full_size, crop_ul
+        H, W = target_shape
+        dev = sdf_network.lin0.bias.device
+        self.device = dev
+        self.params = list(sdf_network.parameters())
+        for nm in ("diffuse_albedo_network", "specular_albedo_network", "specular_roughness_network", "point_light_network"):
+            if nm in color_network_dict:
+                self.params += list(color_network_dict[nm].parameters())
+        self.target = torch.zeros(H, W, 3, dtype=torch.float32, device=dev)
+        self.eik = torch.zeros(n_eik, 3, dtype=torch.float32, device=dev)
+        self.camera = self._host_camera(K, W2C, H, W)       # its small device matrices are the graph's static inputs
+        self.graph = torch.cuda.CUDAGraph()
+        self.loss, self.results = None, None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                        # warm-up off the capture: lazy initialisation, allocator state
+            for _ in range(max(warmup, 1)):
+                self._eager()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if getattr(raytracer, "collect_stats", False):
+            raytracer.last_stats = None                      # the captured call's stats tensor: this replay's counts
+        self._tracer_events = None
+        orig_forward = raytracer.forward
+        if time_tracer:                                      # external events become event-record nodes of the graph
+            ev = (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
+
+            def timed(*a, **k):
+                ev[0].record()
+                r = orig_forward(*a, **k)
+                ev[1].record()
+                return r
+            raytracer.forward = timed
+            self._tracer_events = ev
+        from . import _lib
+        n0 = _lib.load().ironb_launch_count()
+        try:
+            with torch.cuda.graph(self.graph, stream=side):      # same stream as the warm-up (AccumulateGrad nodes)
+                self.loss, self.results = self._eager()
+        finally:
+            raytracer.forward = orig_forward
+        self._grads = {id(p): p.grad for p in self.params}    # the graph's static gradient tensors
+        self.kernels_per_replay = int(_lib.load().ironb_launch_count() - n0)   # this library's kernel nodes in the graph
+
+    def grads(self):
+        """{id(parameter): static gradient tensor}: rewritten by every replay.  `step` re-attaches them as `.grad`, so an
+        optimiser's `zero_grad(set_to_none=True)` between steps is harmless."""
+        return self._grads
+
+    def tracer_ms(self):
+        """Device time of the tracer call inside the LAST replay (needs time_tracer=True and a synchronize before)."""
+        if self._tracer_events is None:
+            return None
+        return self._tracer_events[0].elapsed_time(self._tracer_events[1])
+
+    def _host_camera(self, K, W2C, H, W):
+        cam = Camera(self.full_size[0], self.full_size[1], K.detach().cpu(), W2C.detach().cpu())
+        if self.crop_ul is not None:
+            cam, _, _ = cam.crop_region(W, H, ul_corner=self.crop_ul)
+        assert (cam.H, cam.W) == (H, W), "target_shape must match the (cropped) camera"
+        return cam
+
+    def _eager(self):
+        for p in self.params:
+            p.grad = None
+        return stage2_step(self.sdf, self.nets, self.raytracer, self.render_fn, self.camera, self.target, self.eik,
+                           eik_weight=self.eik_weight, dense_shading=True)
+
+    def step(self, target=None, eik_points=None, K=None, W2C=None):
+        """Copies the given inputs (host tensors: pinned memory makes the copies asynchronous) into the static buffers,
+        replays the graph and returns the loss tensor (device, valid until the next replay)."""
+        if target is not None:
+            self.target.copy_(target, non_blocking=True)
+        if eik_points is not None:
+            self.eik.copy_(eik_points, non_blocking=True)
+        if K is not None or W2C is not None:
+            new = self._host_camera(K if K is not None else self.camera._host[0], W2C if W2C is not None else self.camera._host[1],
+                                    self.camera.H, self.camera.W)
+            for name in ("_kinv3", "_rot", "_org", "K", "W2C", "K_inv", "C2W"):
+                getattr(self.camera, name).copy_(getattr(new, name), non_blocking=True)
+            self.camera._host = new._host
+        self.graph.replay()
+        for p in self.params:
+            p.grad = self._grads[id(p)]
+        return self.loss
