@@ -77,8 +77,11 @@ class _FoldedMLP(nn.Module):
         """Packed effective weights W = v * g/||v|| (+ transposes, biases), refolded when a parameter changed."""
         params = self._param_list()
         key = tuple((p.data_ptr(), p._version) for p in params)
-        # under CUDA-graph capture the fold must be part of the graph (the parameters change between replays)
-        if getattr(self, "_fold_key", None) == key and self._fold_buf is not None and not torch.cuda.is_current_stream_capturing():
+        # under CUDA-graph capture the fold must be part of the graph (the parameters change between replays): the first
+        # call of a capture always refolds, later calls of the same capture reuse it (GraphedStage2Step resets the flag)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if (getattr(self, "_fold_key", None) == key and self._fold_buf is not None
+                and (not capturing or getattr(self, "_fold_captured", False))):
             return self._fold_buf
         dev = params[0].device
         v, g, b = self._v_g_b()
@@ -93,6 +96,8 @@ class _FoldedMLP(nn.Module):
                                                   _lib.ptr_array(b), _lib.ptr(buf), _lib.stream()), "mlp_fold")
         self._fold_buf = buf
         self._fold_key = key
+        if capturing:
+            self._fold_captured = True
         return buf
 
     def unfold_grads(self, dpacked: torch.Tensor) -> List[torch.Tensor]:

@@ -7,6 +7,8 @@ from .rendering_func import get_materials
 
 
 def _scatter(dense_shape, idx, src, width):
+    if idx is None:            # dense shading: one result per ray, already in ray order
+        return src.reshape(dense_shape) if width == 1 else src.reshape(list(dense_shape) + [width])
     n = 1
     for s in dense_shape:
         n *= s
@@ -21,11 +23,12 @@ def make_render_fn(renderer, is_metal=False):
     def render_fn(interior_mask, color_network_dict, ray_o, ray_d, points, normals, features):
         dots_sh = list(interior_mask.shape)
         dev = interior_mask.device
+        dense = bool(getattr(interior_mask, "_ironb_dense", False))    # every ray is shaded: the scatter is the identity
         idx = getattr(interior_mask, "_ironb_idx", None)
-        if idx is None:
+        if idx is None and not dense:
             idx = torch.nonzero(interior_mask.reshape(-1), as_tuple=False).reshape(-1)
         z3 = lambda: torch.zeros(dots_sh + [3], dtype=torch.float32, device=dev)
-        if idx.numel() == 0:
+        if points.shape[0] == 0:
             return {"color": z3(), "diffuse_color": z3(), "specular_color": z3(), "diffuse_albedo": z3(),
                     "specular_albedo": z3(), "specular_roughness": z3()[..., 0].clone(), "normal": z3()}
         normals = normals / (normals.norm(dim=-1, keepdim=True) + 1e-10)
@@ -33,6 +36,8 @@ def make_render_fn(renderer, is_metal=False):
                                is_metal=is_metal)
         res = renderer(color_network_dict["point_light_network"](), (points - ray_o).norm(dim=-1, keepdim=True),
                        normals, -ray_d, params=params)
+        if dense:
+            idx = None
         return {
             "color": _scatter(dots_sh, idx, res["rgb"], 3),
             "diffuse_color": _scatter(dots_sh, idx, res["diffuse_rgb"], 3),

@@ -9,17 +9,32 @@ from .raytracer import Camera, render_camera
 
 
 def stage2_step(sdf_network, color_network_dict, raytracer, render_fn, camera, target, eik_points, eik_weight=0.1,
-                max_num_rays=50000, fill_holes=False, handle_edges=False, dense_shading=False):
+                max_num_rays=50000, fill_holes=False, handle_edges=False, dense_shading=False, eikonal_stream=None):
     """Leaves gradients in .grad of every parameter; returns (loss, results).  fill_holes / handle_edges = True is the
-    reference drivers' default configuration (render_surface.py:521-549)."""
+    reference drivers' default configuration (render_surface.py:521-549).
+
+    eikonal_stream: a second CUDA stream for the eikonal query on the random points (render_surface.py:580-583).  It does
+    not depend on the traced surface, so its forward can run next to the tracer (whose rounds leave most SMs idle once
+    rays converge) and its backward next to the shading backward; same arithmetic, same summation order."""
+    def eikonal_points_term():
+        eg = sdf_network.gradient(eik_points).view(-1, 3)             # render_surface.py:580-583
+        return eg.shape[0], ((eg.norm(dim=-1) - 1) ** 2).sum()
+
+    if eikonal_stream is not None:
+        cur = torch.cuda.current_stream()
+        sdf_network.folded()                                          # the shared folded weights exist before the fork
+        eikonal_stream.wait_stream(cur)
+        with torch.cuda.stream(eikonal_stream):
+            eik_cnt, eik = eikonal_points_term()
     results = render_camera(camera, sdf_network, raytracer, color_network_dict, render_fn, fill_holes=fill_holes,
                             handle_edges=handle_edges, is_training=True, dense_shading=dense_shading)
     mask = results["convergent_mask"]
     if handle_edges:
         mask = mask | results["edge_mask"]                                # render_surface.py:566-567
-    eg = sdf_network.gradient(eik_points).view(-1, 3)                 # render_surface.py:580-583
-    eik_cnt = eg.shape[0]
-    eik = ((eg.norm(dim=-1) - 1) ** 2).sum()
+    if eikonal_stream is not None:
+        torch.cuda.current_stream().wait_stream(eikonal_stream)
+    else:
+        eik_cnt, eik = eikonal_points_term()
     img = ((results["color"] - target) ** 2).sum() / float(mask.numel())
     hn = results["normal"].reshape(-1, 3)
     hm = mask.reshape(-1, 1).float()
@@ -53,7 +68,7 @@ class GraphedStage2Step:
     Limits: fixed patch size / eikonal count / tracer settings; no fill_holes / edge sampling (both read counts back)."""
 
     def __init__(self, sdf_network, color_network_dict, raytracer, render_fn, K, W2C, target_shape, n_eik, crop_ul=None,
-                 full_size=(512, 512), eik_weight=0.1, warmup=3, time_tracer=False):
+                 full_size=(512, 512), eik_weight=0.1, warmup=3, time_tracer=False, overlap_eikonal=True):
         import torch.cuda
         self.sdf, self.nets, self.raytracer, self.render_fn = sdf_network, color_network_dict, raytracer, render_fn
         self.eik_weight = eik_weight
@@ -71,6 +86,11 @@ class GraphedStage2Step:
         self.graph = torch.cuda.CUDAGraph()
         self.loss, self.results = None, None
         side = torch.cuda.Stream(device=dev)
+        self._eik_stream = torch.cuda.Stream(device=dev) if overlap_eikonal else None
+        # two streams feed the same parameters' AccumulateGrad nodes on purpose (eikonal_stream): silence the hint
+        warn = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if warn is not None and overlap_eikonal:
+            warn(False)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                        # warm-up off the capture: lazy initialisation, allocator state
             for _ in range(max(warmup, 1)):
@@ -93,11 +113,16 @@ class GraphedStage2Step:
             self._tracer_events = ev
         from . import _lib
         n0 = _lib.load().ironb_launch_count()
+        folded_nets = [sdf_network] + [m for m in color_network_dict.values() if hasattr(m, "folded")]
+        for m in folded_nets:
+            m._fold_captured = False                         # fold once per capture, at the first use
         try:
             with torch.cuda.graph(self.graph, stream=side):      # same stream as the warm-up (AccumulateGrad nodes)
                 self.loss, self.results = self._eager()
         finally:
             raytracer.forward = orig_forward
+            for m in folded_nets:
+                m._fold_captured = False
         self._grads = {id(p): p.grad for p in self.params}    # the graph's static gradient tensors
         self.kernels_per_replay = int(_lib.load().ironb_launch_count() - n0)   # this library's kernel nodes in the graph
 
@@ -123,7 +148,7 @@ class GraphedStage2Step:
         for p in self.params:
             p.grad = None
         return stage2_step(self.sdf, self.nets, self.raytracer, self.render_fn, self.camera, self.target, self.eik,
-                           eik_weight=self.eik_weight, dense_shading=True)
+                           eik_weight=self.eik_weight, dense_shading=True, eikonal_stream=self._eik_stream)
 
     def step(self, target=None, eik_points=None, K=None, W2C=None):
         """Copies the given inputs (host tensors: pinned memory makes the copies asynchronous) into the static buffers,
