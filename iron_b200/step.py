@@ -87,6 +87,7 @@ class GraphedStage2Step:
         self.loss, self.results = None, None
         side = torch.cuda.Stream(device=dev)
         self._eik_stream = torch.cuda.Stream(device=dev) if overlap_eikonal else None
+        self._mat_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if overlap_eikonal else None
         # two streams feed the same parameters' AccumulateGrad nodes on purpose (eikonal_stream): silence the hint
         warn = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
         if warn is not None and overlap_eikonal:
@@ -147,6 +148,14 @@ class GraphedStage2Step:
     def _eager(self):
         for p in self.params:
             p.grad = None
+        if self._mat_streams is not None:
+            self.nets["_ironb_streams"] = self._mat_streams       # get_materials forks the three material MLPs
+        try:
+            return self._eager_step()
+        finally:
+            self.nets.pop("_ironb_streams", None)
+
+    def _eager_step(self):
         return stage2_step(self.sdf, self.nets, self.raytracer, self.render_fn, self.camera, self.target, self.eik,
                            eik_weight=self.eik_weight, dense_shading=True, eikonal_stream=self._eik_stream)
 
