@@ -83,6 +83,14 @@ class GraphedStage2Step:
         self.target = torch.zeros(H, W, 3, dtype=torch.float32, device=dev)
         self.eik = torch.zeros(n_eik, 3, dtype=torch.float32, device=dev)
         self.camera = self._host_camera(K, W2C, H, W)       # its small device matrices are the graph's static inputs
+        # the three matrices camera_rays reads become views of ONE static device buffer, refreshed by one copy from a pinned
+        # staging buffer that step() fills with numpy (per-step host cost: two 4x4 inverses)
+        self._cam_dev = torch.cat([self.camera._kinv3.reshape(-1), self.camera._rot.reshape(-1),
+                                   self.camera._org.reshape(-1)]).contiguous()
+        self.camera._kinv3 = self._cam_dev[0:9].view(3, 3)
+        self.camera._rot = self._cam_dev[9:18].view(3, 3)
+        self.camera._org = self._cam_dev[18:21]
+        self._cam_pin = torch.empty(21, dtype=torch.float32).pin_memory()
         self.graph = torch.cuda.CUDAGraph()
         self.loss, self.results = None, None
         side = torch.cuda.Stream(device=dev)
@@ -139,6 +147,7 @@ class GraphedStage2Step:
         return self._tracer_events[0].elapsed_time(self._tracer_events[1])
 
     def _host_camera(self, K, W2C, H, W):
+        self._K_full, self._W2C_full = K.detach().cpu().float().clone(), W2C.detach().cpu().float().clone()
         cam = Camera(self.full_size[0], self.full_size[1], K.detach().cpu(), W2C.detach().cpu())
         if self.crop_ul is not None:
             cam, _, _ = cam.crop_region(W, H, ul_corner=self.crop_ul)
@@ -167,11 +176,23 @@ class GraphedStage2Step:
         if eik_points is not None:
             self.eik.copy_(eik_points, non_blocking=True)
         if K is not None or W2C is not None:
-            new = self._host_camera(K if K is not None else self.camera._host[0], W2C if W2C is not None else self.camera._host[1],
-                                    self.camera.H, self.camera.W)
-            for name in ("_kinv3", "_rot", "_org", "K", "W2C", "K_inv", "C2W"):
-                getattr(self.camera, name).copy_(getattr(new, name), non_blocking=True)
-            self.camera._host = new._host
+            import numpy as np
+            # K / W2C are those of the FULL view (like the constructor's); the crop shifts the principal point
+            # (Camera.crop_region, models/raytracer.py:327-351).  float64 inverses, like Camera's host path.
+            Kf = (K if K is not None else self._K_full).detach().cpu().numpy().astype(np.float64)
+            Wf = (W2C if W2C is not None else self._W2C_full).detach().cpu().numpy().astype(np.float64)
+            self._K_full, self._W2C_full = torch.from_numpy(Kf.astype(np.float32)), torch.from_numpy(Wf.astype(np.float32))
+            Kc = Kf.astype(np.float32).astype(np.float64)
+            if self.crop_ul is not None:
+                Kc[0, 2] = np.float32(Kc[0, 2]) - np.float32(self.crop_ul[0])
+                Kc[1, 2] = np.float32(Kc[1, 2]) - np.float32(self.crop_ul[1])
+            Kinv = np.linalg.inv(Kc).astype(np.float32)
+            C2W = np.linalg.inv(Wf.astype(np.float32).astype(np.float64)).astype(np.float32)
+            buf = self._cam_pin.numpy()
+            buf[0:9] = Kinv[:3, :3].reshape(-1)
+            buf[9:18] = C2W[:3, :3].reshape(-1)
+            buf[18:21] = C2W[:3, 3]
+            self._cam_dev.copy_(self._cam_pin, non_blocking=True)
         self.graph.replay()
         for p in self.params:
             p.grad = self._grads[id(p)]

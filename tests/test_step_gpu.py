@@ -219,3 +219,17 @@ def test_graphed_step_matches_eager_step(golden):
     worst2 = max(errs.values())
     print("after the update: loss", loss2, l_ref2, "worst gradients:", sorted(errs.items(), key=lambda kv: -kv[1])[:3])
     assert worst2 <= 1e-5, worst2
+    # re-sending the same camera through step() (numpy path: crop shift + fp64 inverses) reproduces the constructor's camera;
+    # a different camera changes the result
+    loss3 = float(gs.step(K=Kh, W2C=Wh))
+    assert abs(loss3 - loss2) <= 1e-6 * abs(loss2), (loss3, loss2)
+    K2 = Kh.clone()
+    K2[0, 2] += 3.0
+    loss4 = float(gs.step(K=K2))
+    assert abs(loss4 - loss2) > 1e-4 * abs(loss2), (loss4, loss2)
+    cam4, _, _ = ib.Camera(512, 512, K2, Wh).crop_region(32, 32, ul_corner=ul)
+    for _, p in names(sdf, nets):
+        p.grad = None
+    l_ref4, _ = ib.stage2_step(sdf, nets, ib.RayTracer(), ib.make_render_fn(ib.GGXColocatedRenderer(use_cuda=True)), cam4,
+                               target2.to(DEV), eik.to(DEV), eik_weight=0.1, dense_shading=True)
+    assert abs(loss4 - float(l_ref4)) <= 1e-6 * abs(loss4), (loss4, float(l_ref4))
