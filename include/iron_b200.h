@@ -194,6 +194,23 @@ int ironb_depth_closing(const float* depth, int H, int W, float* tmp, float* out
 /* Depth-edge detector of raytrace_camera (models/raytracer.py:569): kornia.filters.sobel magnitude of the [H,W] depth map. */
 int ironb_sobel_depth(const float* depth, int H, int W, float* out, void* stream);
 
+/* ---------------------------------------------------------------- optimiser
+ * Multi-tensor Adam with torch.optim.Adam's arithmetic (amsgrad = False): replaces the six torch.optim.Adam instances the
+ * stage-2 loop steps (render_surface.py:112-113, 651-653; models/network_conf.py:707-716) with one launch.
+ * tensors_dev: DEVICE array of n_tensors descriptors (grad == NULL: tensor skipped); max_numel: largest numel (grid sizing);
+ * step_dev: device int32 holding the number of steps taken so far (read as t = *step + 1, then advanced by one). */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+  float lr;
+  float weight_decay;
+} ironb_adam_tensor;
+int ironb_adam_step(const ironb_adam_tensor* tensors_dev, int n_tensors, int64_t max_numel, double beta1, double beta2,
+                    double eps, int* step_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,11 +10,12 @@ from .render_fn import make_render_fn
 from .renderer_ggx import GGXColocatedRenderer
 from .rendering_func import get_materials
 from .embedder import get_embedder
+from .optim import FusedAdam
 from .step import GraphedStage2Step, stage2_step
 
 __all__ = [
     "SDFNetwork", "RenderingNetwork", "PointLightNetwork", "GGXColocatedRenderer", "RayTracer", "Camera",
     "intersect_sphere", "raytrace_pixels", "raytrace_camera", "render_camera", "render_normal_and_color",
-    "reparam_points", "locate_edge_points", "render_edge_pixels", "get_materials", "get_embedder", "make_render_fn", "stage2_step", "GraphedStage2Step",
+    "reparam_points", "locate_edge_points", "render_edge_pixels", "get_materials", "get_embedder", "make_render_fn", "stage2_step", "GraphedStage2Step", "FusedAdam",
     "init_sdf_network_dict", "init_rendering_network_dict", "choose_renderer",
 ]

@@ -68,6 +68,7 @@ _PROTOS = {
     "ironb_compact_mask": (_INT, [_P, _I64, _P, _P, _P]),
     "ironb_gather_rows": (_INT, [_P, _P, _I64, _INT, _P, _P]),
     "ironb_scatter_rows": (_INT, [_P, _P, _I64, _INT, _P, _P]),
+    "ironb_adam_step": (_INT, [_P, _INT, _I64, C.c_double, C.c_double, C.c_double, _P, _P]),
     "ironb_depth_closing": (_INT, [_P, _INT, _INT, _P, _P, _P]),
     "ironb_sobel_depth": (_INT, [_P, _INT, _INT, _P, _P]),
 }

@@ -68,10 +68,11 @@ class GraphedStage2Step:
     Limits: fixed patch size / eikonal count / tracer settings; no fill_holes / edge sampling (both read counts back)."""
 
     def __init__(self, sdf_network, color_network_dict, raytracer, render_fn, K, W2C, target_shape, n_eik, crop_ul=None,
-                 full_size=(512, 512), eik_weight=0.1, warmup=3, time_tracer=False, overlap_eikonal=True):
+                 full_size=(512, 512), eik_weight=0.1, warmup=3, time_tracer=False, overlap_eikonal=True, optimizer=None):
         import torch.cuda
         self.sdf, self.nets, self.raytracer, self.render_fn = sdf_network, color_network_dict, raytracer, render_fn
         self.eik_weight = eik_weight
+        self.optimizer = optimizer          # e.g. iron_b200.FusedAdam: its step() becomes the tail of the graph
         self.full_size, self.crop_ul = full_size, crop_ul
         H, W = target_shape
         dev = sdf_network.lin0.bias.device
@@ -103,7 +104,7 @@ class GraphedStage2Step:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                        # warm-up off the capture: lazy initialisation, allocator state
             for _ in range(max(warmup, 1)):
-                self._eager()
+                self._eager(run_optimizer=False)            # the warm-up must not move the parameters
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         if getattr(raytracer, "collect_stats", False):
@@ -154,15 +155,18 @@ class GraphedStage2Step:
         assert (cam.H, cam.W) == (H, W), "target_shape must match the (cropped) camera"
         return cam
 
-    def _eager(self):
+    def _eager(self, run_optimizer=True):
         for p in self.params:
             p.grad = None
         if self._mat_streams is not None:
             self.nets["_ironb_streams"] = self._mat_streams       # get_materials forks the three material MLPs
         try:
-            return self._eager_step()
+            out = self._eager_step()
         finally:
             self.nets.pop("_ironb_streams", None)
+        if self.optimizer is not None and run_optimizer:
+            self.optimizer.step()
+        return out
 
     def _eager_step(self):
         return stage2_step(self.sdf, self.nets, self.raytracer, self.render_fn, self.camera, self.target, self.eik,

@@ -901,3 +901,24 @@ def stage2_step(sdf_p: Params, nets: Dict[str, Params], light: Tensor, cam: OCam
     loss = img + eik / eik_cnt * eik_weight
     loss.backward()
     return loss.detach(), res
+
+
+# ---------------------------------------------------------------------------------------------- optimiser
+def adam_step(p, g, m, v, t, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
+    """One Adam update of one tensor, restated from torch/optim/adam.py::_single_tensor_adam (amsgrad=False, maximize=False),
+    the optimiser every network of the reference's stage-2 loop uses (render_surface.py:112-113, 651-653;
+    models/network_conf.py:707-716; third-party: PyTorch, pinned torch==1.11 in create_env.sh, same update rule in 2.x).
+    numpy float32 arrays in, (p, m, v) out; t = 1 for the first step.  Pinned against torch.optim.Adam in
+    tests/test_oracle_golden.py."""
+    import numpy as np
+    p, g, m, v = (np.asarray(a, dtype=np.float32) for a in (p, g, m, v))
+    if weight_decay != 0.0:
+        g = g + np.float32(weight_decay) * p
+    m = m + np.float32(1.0 - beta1) * (g - m)                      # exp_avg.lerp_(grad, 1 - beta1)
+    v = np.float32(beta2) * v + np.float32(1.0 - beta2) * g * g     # exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+    bc1 = 1.0 - beta1 ** t                                        # Python doubles, like the reference
+    bc2 = 1.0 - beta2 ** t
+    step_size = np.float32(lr / bc1)
+    denom = np.sqrt(v) / np.float32(bc2 ** 0.5) + np.float32(eps)
+    p = p - step_size * (m / denom)
+    return p.astype(np.float32), m.astype(np.float32), v.astype(np.float32)

@@ -232,3 +232,24 @@ def test_step_with_edges_golden(golden):
         got = v.grad.double().pow(2).sum().sqrt().item()
         assert abs(got - ref[2]) <= 2e-3 * ref[2] + 1e-9, (k, got, ref[2])
     assert abs(light.grad.item() - g["g.point_light_network.light"]) <= 1e-4 * abs(g["g.point_light_network.light"])
+
+
+def test_oracle_adam_matches_torch_optim_adam():
+    """The optimiser restatement against the reference's own optimiser (torch.optim.Adam on CPU), ragged tensors, 6 steps,
+    with and without weight decay."""
+    import torch
+    from oracle import iron_oracle as O
+    for wd in (0.0, 0.01):
+        gen = torch.Generator().manual_seed(3)
+        ps = [torch.randn(n, generator=gen) for n in (1, 7, 1000, 257 * 33)]
+        ref = [p.clone().requires_grad_(True) for p in ps]
+        opt = torch.optim.Adam(ref, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+        mine = [(p.numpy().copy(), np.zeros(p.numel(), np.float32), np.zeros(p.numel(), np.float32)) for p in ps]
+        for t in range(1, 7):
+            grads = [torch.randn(p.shape, generator=gen) * (10.0 ** (t - 4)) for p in ps]
+            for r, g in zip(ref, grads):
+                r.grad = g.clone()
+            opt.step()
+            mine = [O.adam_step(p, g.numpy(), m, v, t, 1e-2, 0.9, 0.999, 1e-8, wd) for (p, m, v), g in zip(mine, grads)]
+            for r, (p, m, v) in zip(ref, mine):
+                assert np.allclose(p, r.detach().numpy(), rtol=2e-6, atol=1e-7), (wd, t, np.abs(p - r.detach().numpy()).max())

@@ -233,3 +233,56 @@ def test_graphed_step_matches_eager_step(golden):
     l_ref4, _ = ib.stage2_step(sdf, nets, ib.RayTracer(), ib.make_render_fn(ib.GGXColocatedRenderer(use_cuda=True)), cam4,
                                target2.to(DEV), eik.to(DEV), eik_weight=0.1, dense_shading=True)
     assert abs(loss4 - float(l_ref4)) <= 1e-6 * abs(loss4), (loss4, float(l_ref4))
+
+
+def test_graphed_training_iterations_with_fused_adam_match_eager_torch_adam(golden):
+    """Three complete training iterations (step + optimiser) as graph replays with FusedAdam inside the graph, against the
+    eager loop with the reference's per-network torch.optim.Adam instances (lr 1e-5 / 1e-4 / 1e-2)."""
+    g = golden("step_h256")
+    ul = tuple(int(v) for v in g["ul"])
+    target, eik = T(g["target"]), T(g["eik_points"])
+    Kh = torch.tensor(O.FIXTURE_K, dtype=torch.float64).reshape(4, 4).float()
+    Wh = torch.tensor(O.FIXTURE_W2C, dtype=torch.float64).reshape(4, 4).float()
+    mat = ("diffuse_albedo_network", "specular_albedo_network", "specular_roughness_network")
+
+    def groups(sdf, nets):
+        return ([{"params": list(sdf.parameters()), "lr": 1e-5}] + [{"params": list(nets[nm].parameters()), "lr": 1e-4} for nm in mat]
+                + [{"params": list(nets["point_light_network"].parameters()), "lr": 1e-2}])
+
+    ib, sdf, nets, _ = build()
+    opt = ib.FusedAdam(groups(sdf, nets))
+    rf = ib.make_render_fn(ib.GGXColocatedRenderer(use_cuda=True))
+    start = {k: v.clone() for k, v in sdf.state_dict().items()}
+    gs = ib.GraphedStage2Step(sdf, nets, ib.RayTracer(), rf, Kh, Wh, (32, 32), eik.shape[0], crop_ul=ul, eik_weight=0.1,
+                              optimizer=opt)
+    for k, v in sdf.state_dict().items():
+        assert torch.equal(v, start[k]), f"warm-up / capture moved {k}"
+    losses = []
+    for _ in range(3):
+        losses.append(float(gs.step(target=target.pin_memory(), eik_points=eik.pin_memory())))
+    torch.cuda.synchronize()
+    assert opt.steps_taken == 3
+
+    ib2, sdf2, nets2, _ = build()
+    opts = [torch.optim.Adam(gr["params"], lr=gr["lr"]) for gr in groups(sdf2, nets2)]
+    cam, _, _ = ib2.Camera(512, 512, Kh, Wh).crop_region(32, 32, ul_corner=ul)
+    ref_losses = []
+    for _ in range(3):
+        for o in opts:
+            o.zero_grad()
+        loss, _ = ib2.stage2_step(sdf2, nets2, ib2.RayTracer(), rf, cam, target.to(DEV), eik.to(DEV), eik_weight=0.1,
+                                  dense_shading=True)
+        ref_losses.append(float(loss))
+        for o in opts:
+            o.step()
+    print("graph + FusedAdam losses", losses, "eager + torch.optim.Adam losses", ref_losses)
+    assert losses[0] != losses[2]
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) <= 1e-5 * abs(b), (losses, ref_losses)
+    worst = 0.0
+    for (k, p), (_, q) in zip(list(sdf.named_parameters()) + [x for nm in mat for x in nets[nm].named_parameters()],
+                              list(sdf2.named_parameters()) + [x for nm in mat for x in nets2[nm].named_parameters()]):
+        worst = max(worst, rel_l2(p.detach().cpu().numpy(), q.detach().cpu().numpy()))
+    # Adam's first steps move every element by ~lr * sign(g): elements whose gradient is ~0 (zero-initialised biases) turn the
+    # atomic-order noise of the weight gradients into O(lr) differences, so the bound is loose in relative terms
+    assert worst <= 5e-4, worst
