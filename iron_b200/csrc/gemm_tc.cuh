@@ -378,11 +378,20 @@ struct EpiAtomicAdd {
   }
 };
 
-// dst[c][m] = src[m][c] for c < cols, m < M; dst row pitch ldt >= round4(M), columns m in [M, ldt) zeroed
-static __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, int lds, int M, int cols,
-                                                               float* __restrict__ dst, int ldt) {
+// Both operands of a weight gradient in one launch (blockIdx.z = 0: A, 1: B):  dst[c][m] = src[m][c] for c < cols, m < M;
+// dst row pitch ldt >= round4(M), columns m in [M, ldt) zeroed.  Optionally the column sums of A (the bias gradient of the
+// same layer: csum[c] += scale * sum_m A[m][c], c < csum_cols) are taken from the tile while it sits in shared memory.
+static __global__ void __launch_bounds__(256) transpose2_kernel(const float* __restrict__ A, int lda, int colsA,
+                                                                float* __restrict__ At, const float* __restrict__ B, int ldb,
+                                                                int colsB, float* __restrict__ Bt, int M, int ldt,
+                                                                float* __restrict__ csum, int csum_cols, float csum_scale) {
   __shared__ float tile[32][33];
+  const bool second = blockIdx.z != 0;
+  const float* __restrict__ src = second ? B : A;
+  float* __restrict__ dst = second ? Bt : At;
+  const int lds = second ? ldb : lda, cols = second ? colsB : colsA;
   const int m0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  if (c0 >= cols) return;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -395,22 +404,27 @@ static __global__ void __launch_bounds__(256) transpose_kernel(const float* __re
     const int c = c0 + ty + i * 8, m = m0 + tx;
     if (c < cols && m < ldt) dst[(size_t)c * ldt + m] = tile[tx][ty + i * 8];
   }
+  if (!second && csum != nullptr && ty == 0 && c0 + tx < csum_cols && m0 < M) {
+    float t = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) t += tile[r][tx];
+    atomicAdd(csum + c0 + tx, t * csum_scale);
+  }
 }
 
 inline int64_t wgrad_scratch_floats(int64_t M, int max_cols) { return 2 * (int64_t)max_cols * ((M + 3) / 4 * 4); }
 
 // scratch: wgrad_scratch_floats(M, max(Nd, Kd)) floats
 inline int launch_wgrad_tc(const float* A, int lda, const float* B, int ldb, int M, int Nd, int Kd, float* C, int ldc,
-                           float* scratch, cudaStream_t st, const char* what) {
+                           float* scratch, cudaStream_t st, const char* what, float* csum = nullptr, int csum_cols = 0,
+                           float csum_scale = 1.f) {
   if (M <= 0 || Nd <= 0 || Kd <= 0) return IRONB_OK;
   const int ldt = (M + 3) / 4 * 4;
   float* At = scratch;
   float* Bt = scratch + (size_t)(Nd > Kd ? Nd : Kd) * ldt;
-  dim3 ga((unsigned)ceil_div64(ldt, 32), (unsigned)ceil_div64(Nd, 32)), gb((unsigned)ceil_div64(ldt, 32), (unsigned)ceil_div64(Kd, 32));
-  transpose_kernel<<<ga, 256, 0, st>>>(A, lda, M, Nd, At, ldt);
-  IRONB_CHECK_LAUNCH("transpose_kernel");
-  transpose_kernel<<<gb, 256, 0, st>>>(B, ldb, M, Kd, Bt, ldt);
-  IRONB_CHECK_LAUNCH("transpose_kernel");
+  dim3 g2((unsigned)ceil_div64(ldt, 32), (unsigned)ceil_div64(Nd > Kd ? Nd : Kd, 32), 2);
+  transpose2_kernel<<<g2, 256, 0, st>>>(A, lda, Nd, At, B, ldb, Kd, Bt, M, ldt, csum, csum_cols, csum_scale);
+  IRONB_CHECK_LAUNCH("transpose2_kernel");
   tc::CUtensorMapAlias mA, mB;
   int rc = tc::make_map(&mA, At, Nd, ldt, ldt);
   if (rc) return rc;
@@ -426,10 +440,15 @@ inline int launch_wgrad_tc(const float* A, int lda, const float* B, int ldb, int
   return tc::launch_gemm_nt_tc_maps(mA, mB, Nd, Kd, ldt, ep, nullptr, 1, st, what, -1, k_chunk);
 }
 
+// csum (optional): the bias gradient of the same layer, csum[c] += csum_scale * sum_m A[m][c] for c < csum_cols
 inline int launch_wgrad_auto(const float* A, int lda, const float* B, int ldb, int M, int Nd, int Kd, float* C, int ldc,
-                             float* scratch, cudaStream_t st, const char* what) {
-  if (tc::tc_enabled() && scratch != nullptr) return launch_wgrad_tc(A, lda, B, ldb, M, Nd, Kd, C, ldc, scratch, st, what);
-  return launch_gemm_tn(A, lda, B, ldb, M, Nd, Kd, C, ldc, st, what);
+                             float* scratch, cudaStream_t st, const char* what, float* csum = nullptr, int csum_cols = 0,
+                             float csum_scale = 1.f) {
+  if (tc::tc_enabled() && scratch != nullptr)
+    return launch_wgrad_tc(A, lda, B, ldb, M, Nd, Kd, C, ldc, scratch, st, what, csum, csum_cols, csum_scale);
+  int rc = launch_gemm_tn(A, lda, B, ldb, M, Nd, Kd, C, ldc, st, what);
+  if (rc || csum == nullptr) return rc;
+  return launch_colsum(A, lda, M, csum_cols, csum_scale, csum, st, what);
 }
 
 template <class Epi>

@@ -259,9 +259,8 @@ extern "C" int ironb_matnet_bwd(const ironb_mlp_layout* lay, const ironb_matnet_
   const bool need_in = d_points || d_normals || d_view || d_feats;
   for (int l = last; l >= 0; --l) {
     int rc = launch_wgrad_auto(D, lay->out_pad[l], w.U[l], lay->in_pad[l], (int)M, lay->out_pad[l], lay->in_pad[l],
-                               dpacked + lay->off_w[l], lay->in_pad[l], w.wg, st, "matnet wgrad");
-    if (rc) return rc;
-    rc = launch_colsum(D, lay->out_pad[l], (int)M, lay->out_dim[l], 1.f, dpacked + lay->off_b[l], st, "matnet bias grad");
+                               dpacked + lay->off_w[l], lay->in_pad[l], w.wg, st, "matnet wgrad (+ bias grad)",
+                               dpacked + lay->off_b[l], lay->out_dim[l], 1.f);
     if (rc) return rc;
     float* Dn = w.D[(l + 1) & 1];
     if (l > 0) {

@@ -432,11 +432,10 @@ extern "C" int ironb_sdf_getall_bwd(const ironb_mlp_layout* lay, const float* pa
     D = w.R[lstart];
   }
   for (int l = lstart; l >= 0; --l) {
+    // dW_l += delta_l^T u_l, and db_l += column sums of delta_l (taken from the transposed tiles of the same launch)
     int rc = launch_wgrad_auto(D, lay->out_pad[l], w.U[l], lay->in_pad[l], (int)M, lay->out_pad[l], lay->in_pad[l],
-                               dpacked + lay->off_w[l], lay->in_pad[l], w.wg, st, "sdf bwd A wgrad");
-    if (rc) return rc;
-    rc = launch_colsum(D, lay->out_pad[l], (int)M, lay->out_dim[l], 1.f, dpacked + lay->off_b[l], st,
-                       "sdf bwd A bias");
+                               dpacked + lay->off_w[l], lay->in_pad[l], w.wg, st, "sdf bwd A wgrad",
+                               dpacked + lay->off_b[l], lay->out_dim[l], 1.f);
     if (rc) return rc;
     if (l == 0) break;
     EpiA ep;
