@@ -71,6 +71,17 @@ bool tc_enabled() {
   }
   return m == 1;
 }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    // measured (bench.py, graph replay with three parallel streams): 5.12 ms/step with PDL, 4.99 without -- the early CTAs of
+    // a dependent GEMM hold whole SMs (192 KiB of shared memory each) while they wait, which costs the other streams more
+    // than the hidden prologue gains.  Off unless IRONB_PDL=1 (isolated eager chains do gain: wgrad 40 -> 36 us).
+    const char* e = getenv("IRONB_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 static std::atomic<int> g_write_hi{-1};
 bool split_writes_hi() {
   int m = g_write_hi.load(std::memory_order_relaxed);

@@ -158,7 +158,11 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                   Epi epi, const int* __restrict__ m_dev, int m_mul, int write_hi, int k_chunk, long long* dbg) {
   const bool stamp = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   if (stamp && threadIdx.x == 0) dbg[0] = clock64();
-  if (m_dev != nullptr) {   // row count produced on the device (compacted ray lists): whole CTAs beyond it leave at once
+  // Programmatic dependent launch: the next kernel of the stream may start its prologue now; this kernel touches global
+  // memory only after griddepcontrol.wait (the predecessor has completed and its writes are visible).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (m_dev != nullptr) {   // the device-side row count is produced by a predecessor
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // row count produced on the device (compacted ray lists): whole CTAs beyond it leave at once
     const int md = *m_dev * m_mul;
     if (md < M) M = md;
   }
@@ -202,6 +206,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot_ptr;
+  asm volatile("griddepcontrol.wait;" ::: "memory");        // barriers, TMEM and tensor maps are set up: now wait for the data
   if (stamp && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
@@ -329,6 +334,7 @@ EncodeTiledFn encode_fn();
 int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld);
 int make_map_h(CUtensorMap* map, const void* ptr, int rows, int K, int ld);   // fp16, 64 x 128 box
 bool tc_enabled();
+bool pdl_enabled();       // programmatic dependent launch of the GEMM kernels (IRONB_PDL=1 switches it on; see gemm_tc.cu)
 bool split_writes_hi();   // 0 (default): raw fp32 stays as the hi operand; 1 (IRONB_SPLIT_WRITE_HI=1): store the truncated hi back
 
 template <class Epi>
@@ -344,8 +350,20 @@ int launch_gemm_nt_tc_maps(const CUtensorMap& mA, const CUtensorMap& mB, int M, 
     configured = true;
   }
   dim3 grid((unsigned)ceil_div64(N, BN), (unsigned)ceil_div64(M, BM), (unsigned)(k_chunk > 0 ? ceil_div64(K, k_chunk) : 1));
-  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mB, M, N, K, epi, m_dev, m_mul, write_hi, k_chunk,
-                                           g_mlp_dbg ? g_mlp_dbg + 256 : nullptr);   // IRONB debug timeline (last launch wins)
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NTHREADS, 1, 1);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  long long* dbg = g_mlp_dbg ? g_mlp_dbg + 256 : nullptr;   // IRONB debug timeline (last launch wins)
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mA, mB, M, N, K, epi, m_dev, m_mul, write_hi, k_chunk, dbg);
+  if (le != cudaSuccess) { (void)cudaGetLastError(); note_launch(); set_error("%s: %s", what, cudaGetErrorString(le)); return (int)le; }
   IRONB_CHECK_LAUNCH(what);
   return IRONB_OK;
 }
@@ -386,6 +404,7 @@ static __global__ void __launch_bounds__(256) transpose2_kernel(const float* __r
                                                                 int colsB, float* __restrict__ Bt, int M, int ldt,
                                                                 float* __restrict__ csum, int csum_cols, float csum_scale) {
   __shared__ float tile[32][33];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the split-K GEMM that follows may set itself up
   const bool second = blockIdx.z != 0;
   const float* __restrict__ src = second ? B : A;
   float* __restrict__ dst = second ? Bt : At;
