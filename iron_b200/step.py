@@ -94,7 +94,8 @@ class GraphedStage2Step:
         self._cam_pin = torch.empty(21, dtype=torch.float32).pin_memory()
         self.graph = torch.cuda.CUDAGraph()
         self.loss, self.results = None, None
-        side = torch.cuda.Stream(device=dev)
+        prio = int(__import__("os").environ.get("IRONB_GRAPH_MAIN_PRIORITY", "0"))
+        side = torch.cuda.Stream(device=dev, priority=prio)   # the critical path (tracer -> shading -> backward)
         self._eik_stream = torch.cuda.Stream(device=dev) if overlap_eikonal else None
         self._mat_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if overlap_eikonal else None
         # two streams feed the same parameters' AccumulateGrad nodes on purpose (eikonal_stream): silence the hint
