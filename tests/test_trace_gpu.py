@@ -162,3 +162,33 @@ def test_camera_from_host_matrices_matches_device_camera():
     cd2, _ = iron_b200.Camera(512, 512, Kh.to(DEV), Wh.to(DEV)).resize(0.5)
     for a, b in zip(cd2.get_rays(cd2.get_uv()), ch2.get_rays(ch2.get_uv())):
         assert_close(a.cpu().numpy(), b.cpu().numpy(), 3e-7, what="host-built resized camera rays")
+
+
+@pytest.mark.parametrize("H,n_layers,multires", [(128, 8, 6), (128, 4, 4), (256, 6, 6)])
+def test_trace_other_widths_depths_vs_oracle(H, n_layers, multires, trace_mode):
+    """Cluster sizes 1 and 2 of the fused MLP kernels (H = 128, 256), fewer layers and a shorter encoding: 40x40 silhouette
+    crop and a ragged ray count (N = 1,531: not a multiple of the 128-row tile) against the oracle on the same weights."""
+    import iron_b200
+    torch.manual_seed(0)
+    skip = [n_layers // 2]
+    net = iron_b200.SDFNetwork(d_in=3, d_out=33, d_hidden=H, n_layers=n_layers, skip_in=skip, multires=multires, bias=0.5,
+                               scale=1.0, geometric_init=True, weight_norm=True)
+    p = oracle_params(net)
+    net = net.to(DEV)
+    cam = O.OCamera.fixture().crop(40, 40, (335, 236))
+    uv = cam.pixel_uv()
+    ref = O.trace_pixels(p, cam, uv, multires=multires, skip_in=tuple(skip))
+    cam_g, _, _ = fixture_camera().crop_region(40, 40, ul_corner=(335, 236))
+    res = iron_b200.raytrace_pixels(net, iron_b200.RayTracer(), cam_g.get_uv(), cam_g)
+    m, mr = res["convergent_mask"].cpu().numpy(), ref["convergent_mask"].numpy()
+    assert mr.sum() > 0
+    assert (m == mr).mean() >= 0.998, f"H={H} L={n_layers}: mask agreement {(m == mr).mean()}"
+    both = m & mr
+    assert_close(res["distance"].cpu().numpy()[both], ref["distance"].numpy()[both], TOL_DEPTH, what="distance", frac=0.998)
+    # ragged N through RayTracer.forward directly
+    o, d, _ = cam_g.get_rays(cam_g.get_uv())
+    o, d = o.reshape(-1, 3)[:1531].contiguous(), d.reshape(-1, 3)[:1531].contiguous()
+    hit, t0, t1 = iron_b200.intersect_sphere(o, d, 1.0)
+    r2 = iron_b200.RayTracer()(net, o, d, t0, t1, hit)
+    assert torch.equal(r2["convergent_mask"], res["convergent_mask"].reshape(-1)[:1531]) or \
+        float((r2["convergent_mask"] == res["convergent_mask"].reshape(-1)[:1531]).float().mean()) >= 0.999
