@@ -326,8 +326,9 @@ def run_ours(args):
     use_graph = args.exec_mode == "graph" and args.shading == "dense" and not args.driver_defaults
     gs = None
     if use_graph:
-        tracer.collect_stats = True
-        gs = ib.GraphedStage2Step(sdf, nets, tracer, render_fn, K_h, W2C_h, (S, S), S * S // 2, crop_ul=ul, time_tracer=True)
+        tracer.collect_stats = os.environ.get("IRONB_BENCH_STATS", "1") != "0"
+        gs = ib.GraphedStage2Step(sdf, nets, tracer, render_fn, K_h, W2C_h, (S, S), S * S // 2, crop_ul=ul,
+                                  time_tracer=os.environ.get("IRONB_BENCH_TIME_TRACER", "1") != "0")
         gs.step(target=target_h, eik_points=eik_h)
         torch.cuda.synchronize()
 

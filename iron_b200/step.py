@@ -96,8 +96,16 @@ class GraphedStage2Step:
         self.loss, self.results = None, None
         prio = int(__import__("os").environ.get("IRONB_GRAPH_MAIN_PRIORITY", "0"))
         side = torch.cuda.Stream(device=dev, priority=prio)   # the critical path (tracer -> shading -> backward)
-        self._eik_stream = torch.cuda.Stream(device=dev) if overlap_eikonal else None
-        self._mat_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if overlap_eikonal else None
+        _env = __import__("os").environ
+        # KNOWN ISSUE (unresolved): with the eikonal branch on its own stream, replays at 65,536 rays /
+        # 32,768 eikonal points fault intermittently ("unspecified launch failure"; both tensor-core tracers; not with the
+        # material streams alone).  At 4,096 rays thousands of replays ran clean.  The overlap only pays when the tracer
+        # leaves SMs idle, i.e. for small patches, so it is limited to those (IRONB_GRAPH_EIK_STREAM=1 forces it on).
+        small = H * W <= 16384
+        want_eik = _env.get("IRONB_GRAPH_EIK_STREAM", "1" if small else "0") != "0"
+        self._eik_stream = torch.cuda.Stream(device=dev) if overlap_eikonal and want_eik else None
+        self._mat_streams = ([torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+                             if overlap_eikonal and _env.get("IRONB_GRAPH_MAT_STREAMS", "1") != "0" else None)
         # two streams feed the same parameters' AccumulateGrad nodes on purpose (eikonal_stream): silence the hint
         warn = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
         if warn is not None and overlap_eikonal:
@@ -105,7 +113,10 @@ class GraphedStage2Step:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                        # warm-up off the capture: lazy initialisation, allocator state
             for _ in range(max(warmup, 1)):
-                self._eager(run_optimizer=False)            # the warm-up must not move the parameters
+                # the warm-up must not move the parameters, and it runs single-stream: the eager caching allocator hands
+                # a block freed on one stream to the next request on that stream at once, which is only safe for the
+                # cross-stream consumers of the forked branches inside a capture (static memory, explicit graph edges)
+                self._eager(run_optimizer=False, multi_stream=False)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         if getattr(raytracer, "collect_stats", False):
@@ -113,15 +124,17 @@ class GraphedStage2Step:
         self._tracer_events = None
         orig_forward = raytracer.forward
         if time_tracer:                                      # external events become event-record nodes of the graph
-            ev = (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
+            pairs = []                                       # one pair per tracer call (render_camera traces <= 50,000 rays per call)
 
             def timed(*a, **k):
-                ev[0].record()
+                e0, e1 = (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
+                e0.record()
                 r = orig_forward(*a, **k)
-                ev[1].record()
+                e1.record()
+                pairs.append((e0, e1))
                 return r
             raytracer.forward = timed
-            self._tracer_events = ev
+            self._tracer_events = pairs
         from . import _lib
         n0 = _lib.load().ironb_launch_count()
         folded_nets = [sdf_network] + [m for m in color_network_dict.values() if hasattr(m, "folded")]
@@ -144,9 +157,9 @@ class GraphedStage2Step:
 
     def tracer_ms(self):
         """Device time of the tracer call inside the LAST replay (needs time_tracer=True and a synchronize before)."""
-        if self._tracer_events is None:
+        if not self._tracer_events:
             return None
-        return self._tracer_events[0].elapsed_time(self._tracer_events[1])
+        return sum(a.elapsed_time(b) for a, b in self._tracer_events)
 
     def _host_camera(self, K, W2C, H, W):
         self._K_full, self._W2C_full = K.detach().cpu().float().clone(), W2C.detach().cpu().float().clone()
@@ -156,22 +169,23 @@ class GraphedStage2Step:
         assert (cam.H, cam.W) == (H, W), "target_shape must match the (cropped) camera"
         return cam
 
-    def _eager(self, run_optimizer=True):
+    def _eager(self, run_optimizer=True, multi_stream=True):
         for p in self.params:
             p.grad = None
-        if self._mat_streams is not None:
+        if self._mat_streams is not None and multi_stream:
             self.nets["_ironb_streams"] = self._mat_streams       # get_materials forks the three material MLPs
         try:
-            out = self._eager_step()
+            out = self._eager_step(multi_stream)
         finally:
             self.nets.pop("_ironb_streams", None)
         if self.optimizer is not None and run_optimizer:
             self.optimizer.step()
         return out
 
-    def _eager_step(self):
+    def _eager_step(self, multi_stream=True):
         return stage2_step(self.sdf, self.nets, self.raytracer, self.render_fn, self.camera, self.target, self.eik,
-                           eik_weight=self.eik_weight, dense_shading=True, eikonal_stream=self._eik_stream)
+                           eik_weight=self.eik_weight, dense_shading=True,
+                           eikonal_stream=self._eik_stream if multi_stream else None)
 
     def step(self, target=None, eik_points=None, K=None, W2C=None):
         """Copies the given inputs (host tensors: pinned memory makes the copies asynchronous) into the static buffers,
