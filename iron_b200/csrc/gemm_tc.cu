@@ -76,7 +76,8 @@ bool pdl_enabled() {
   if (v < 0) {
     // measured (bench.py, graph replay with three parallel streams): 5.12 ms/step with PDL, 4.99 without -- the early CTAs of
     // a dependent GEMM hold whole SMs (192 KiB of shared memory each) while they wait, which costs the other streams more
-    // than the hidden prologue gains.  Off unless IRONB_PDL=1 (isolated eager chains do gain: wgrad 40 -> 36 us).
+    // than the hidden prologue gains.  Off unless IRONB_PDL=1 AND the library is built with -DIRONB_ENABLE_PDL (the
+    // griddepcontrol instructions are compiled out otherwise); isolated eager chains do gain: wgrad 40 -> 36 us.
     const char* e = getenv("IRONB_PDL");
     v = (e && e[0] == '1') ? 1 : 0;
   }

@@ -19,6 +19,15 @@
 #include "common.cuh"
 #include "gemm.cuh"
 
+// programmatic-dependent-launch hooks (no-ops unless built with -DIRONB_ENABLE_PDL; see gemm_tc.cu: measured slower)
+#ifdef IRONB_ENABLE_PDL
+#define IRONB_GDC_LAUNCH() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define IRONB_GDC_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#else
+#define IRONB_GDC_LAUNCH() ((void)0)
+#define IRONB_GDC_WAIT() ((void)0)
+#endif
+
 namespace ironb {
 extern long long* g_mlp_dbg;   // mlp_tc.cu: optional clock64 stamp buffer (ironb_debug_mlp_timeline)
 namespace tc {
@@ -160,9 +169,9 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   if (stamp && threadIdx.x == 0) dbg[0] = clock64();
   // Programmatic dependent launch: the next kernel of the stream may start its prologue now; this kernel touches global
   // memory only after griddepcontrol.wait (the predecessor has completed and its writes are visible).
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  IRONB_GDC_LAUNCH();
   if (m_dev != nullptr) {   // the device-side row count is produced by a predecessor
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // row count produced on the device (compacted ray lists): whole CTAs beyond it leave at once
+    IRONB_GDC_WAIT();   // row count produced on the device (compacted ray lists): whole CTAs beyond it leave at once
     const int md = *m_dev * m_mul;
     if (md < M) M = md;
   }
@@ -206,7 +215,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot_ptr;
-  asm volatile("griddepcontrol.wait;" ::: "memory");        // barriers, TMEM and tensor maps are set up: now wait for the data
+  IRONB_GDC_WAIT();        // barriers, TMEM and tensor maps are set up: now wait for the data
   if (stamp && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
@@ -360,7 +369,7 @@ int launch_gemm_nt_tc_maps(const CUtensorMap& mA, const CUtensorMap& mB, int M, 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;          // no attribute at all unless PDL is switched on
   long long* dbg = g_mlp_dbg ? g_mlp_dbg + 256 : nullptr;   // IRONB debug timeline (last launch wins)
   cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mA, mB, M, N, K, epi, m_dev, m_mul, write_hi, k_chunk, dbg);
   if (le != cudaSuccess) { (void)cudaGetLastError(); note_launch(); set_error("%s: %s", what, cudaGetErrorString(le)); return (int)le; }
@@ -404,7 +413,7 @@ static __global__ void __launch_bounds__(256) transpose2_kernel(const float* __r
                                                                 int colsB, float* __restrict__ Bt, int M, int ldt,
                                                                 float* __restrict__ csum, int csum_cols, float csum_scale) {
   __shared__ float tile[32][33];
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the split-K GEMM that follows may set itself up
+  IRONB_GDC_LAUNCH();   // the split-K GEMM that follows may set itself up
   const bool second = blockIdx.z != 0;
   const float* __restrict__ src = second ? B : A;
   float* __restrict__ dst = second ? Bt : At;
