@@ -556,8 +556,26 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    else:
-        run_ours(args)
+        return
+    single = int(os.environ.get("WORLD_SIZE", "1")) == 1
+    if args.exec_mode == "graph" and single and not os.environ.get("IRONB_BENCH_CHILD"):
+        # Safety net (single process only): the measurement runs in a child; if the graph-replay path dies (a CUDA fault
+        # kills the context, nothing can be measured in this process afterwards) the same step is measured with eager
+        # execution in a fresh child and the line says so.  The child's JSON line is relayed unchanged otherwise.
+        env = dict(os.environ, IRONB_BENCH_CHILD="1")
+        for attempt, extra in enumerate(([], ["--exec", "eager"])):
+            r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + extra, env=env,
+                               stdout=subprocess.PIPE, stderr=None)
+            lines = [ln for ln in r.stdout.decode("utf-8", "replace").splitlines() if ln.startswith("{")]
+            if r.returncode == 0 and lines:
+                line = json.loads(lines[-1])
+                if attempt == 1:
+                    line["config"]["execution"] += " -- FALLBACK: the CUDA-graph child exited with an error"
+                emit(line)
+                return
+            sys.stderr.write(f"bench.py: child (attempt {attempt}) exited with code {r.returncode}\n")
+        sys.exit(1)
+    run_ours(args)
 
 
 if __name__ == "__main__":
