@@ -15,6 +15,7 @@
 // tiles that is ~84 B/clk/SM of L2 traffic, above the measured L2 slice throughput, while one fp32 copy is 42 B/clk.
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm.cuh"
@@ -472,7 +473,8 @@ inline int launch_wgrad_tc(const float* A, int lda, const float* B, int ldb, int
 inline int launch_wgrad_auto(const float* A, int lda, const float* B, int ldb, int M, int Nd, int Kd, float* C, int ldc,
                              float* scratch, cudaStream_t st, const char* what, float* csum = nullptr, int csum_cols = 0,
                              float csum_scale = 1.f) {
-  if (tc::tc_enabled() && scratch != nullptr)
+  static const bool wgrad_simt = [] { const char* e = getenv("IRONB_WGRAD"); return e && (e[0] == 's' || e[0] == 'S'); }();   // diagnostic
+  if (tc::tc_enabled() && scratch != nullptr && !wgrad_simt)
     return launch_wgrad_tc(A, lda, B, ldb, M, Nd, Kd, C, ldc, scratch, st, what, csum, csum_cols, csum_scale);
   int rc = launch_gemm_tn(A, lda, B, ldb, M, Nd, Kd, C, ldc, st, what);
   if (rc || csum == nullptr) return rc;
