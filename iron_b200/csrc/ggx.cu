@@ -24,27 +24,34 @@ struct GgxCommon {   // everything both directions need
   float L, d2, c_raw, c, a, c2, a2e, root, D, sin_t, cpe, tan_t, rt, h, G1, G, q, S, Kc;
 };
 
+// FAST = false: IEEE divisions (the forward pass: results within ~1e-6 of the reference).  FAST = true: the backward
+// pass recomputes the same quantities with __fdividef (2 ulp, one MUFU.RCP + multiply instead of a ~10-instruction
+// sequence with a slow-path call): gradients are asserted to 1e-4 relative, and the kernel drops under 128 registers.
+template <bool FAST>
+__device__ __forceinline__ float qdiv(float a, float b) { return FAST ? __fdividef(a, b) : a / b; }
+
+template <bool FAST = false>
 __device__ __forceinline__ GgxCommon ggx_common(const GgxIn& p, float light, const float* __restrict__ trans,
                                                 const float* __restrict__ diff_trans) {
   GgxCommon s;
   s.d2 = p.dist * p.dist + 1e-10f;
-  s.L = light / s.d2;                                            // :88
+  s.L = qdiv<FAST>(light, s.d2);                                            // :88
   s.c_raw = p.v[0] * p.n[0] + p.v[1] * p.n[1] + p.v[2] * p.n[2];
   s.c = fminf(fmaxf(s.c_raw, 0.00001f), 0.99999f);               // :90-91
   s.a = fmaxf(p.alpha, 0.0001f);                                 // :103
   s.c2 = s.c * s.c;
   s.a2e = s.a * s.a + 1e-10f;
-  s.root = s.c2 + (1.0f - s.c2) / s.a2e;                         // :107
-  s.D = 1.0f / (kPi * s.a * s.a * s.root * s.root + 1e-10f);     // :108
+  s.root = s.c2 + qdiv<FAST>(1.0f - s.c2, s.a2e);                         // :107
+  s.D = qdiv<FAST>(1.0f, kPi * s.a * s.a * s.root * s.root + 1e-10f);     // :108
   s.sin_t = sqrtf(1.0f - s.c * s.c);                             // smithG1 :12-16
   s.cpe = s.c + 1e-10f;
-  s.tan_t = s.sin_t / s.cpe;
+  s.tan_t = qdiv<FAST>(s.sin_t, s.cpe);
   s.rt = s.a * s.tan_t;
   s.h = hypotf(s.rt, 1.0f);
-  s.G1 = 2.0f / (1.0f + s.h);
+  s.G1 = qdiv<FAST>(2.0f, 1.0f + s.h);
   s.G = s.G1 * s.G1;                                             // :111
   s.q = 4.0f * s.c + 1e-10f;
-  s.S = kF * s.D * s.G / s.q;                                    // :113-115 without light / albedo
+  s.S = qdiv<FAST>(kF * s.D * s.G, s.q);                                    // :113-115 without light / albedo
   // table lookups, floor indexed                                  :121-137
   float wc = sqrtf(sqrtf(s.c));                                  // c ** 0.25
   float wa = sqrtf(sqrtf(s.a * 0.25f));                          // ((alpha - 0)/(4 - 0)) ** 0.25
@@ -54,7 +61,7 @@ __device__ __forceinline__ GgxCommon ggx_common(const GgxIn& p, float light, con
   float T12 = fminf(fmaxf(__ldg(trans + idx), 0.0f), 1.0f);
   int idy = min(max(ty, 0), 49);
   float Fdr = fminf(fmaxf(1.0f - __ldg(diff_trans + idy), 0.0f), 1.0f);
-  s.Kc = T12 * T12 * kInvEta2 / (kPi * (1.0f - Fdr + 1e-10f));   // :139-144 without light / albedo / cos
+  s.Kc = qdiv<FAST>(T12 * T12 * kInvEta2, kPi * (1.0f - Fdr + 1e-10f));   // :139-144 without light / albedo / cos
   return s;
 }
 
@@ -174,7 +181,7 @@ __device__ __forceinline__ void load_up(const float* base, int64_t g, int64_t M,
   }
 }
 
-__global__ void __launch_bounds__(256) ggx_bwd_kernel(GgxPtrs P, GgxGradPtrs Gp, int64_t M) {
+__global__ void __launch_bounds__(256, 2) ggx_bwd_kernel(GgxPtrs P, GgxGradPtrs Gp, int64_t M) {
   const float light = __ldg(P.light);
   const int64_t groups = (M + 3) / 4;
   float light_acc = 0.f;
@@ -190,7 +197,7 @@ __global__ void __launch_bounds__(256) ggx_bwd_kernel(GgxPtrs P, GgxGradPtrs Gp,
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const GgxIn& p = in[i];
-      GgxCommon s = ggx_common(p, light, P.trans, P.diff_trans);
+      GgxCommon s = ggx_common<true>(p, light, P.trans, P.diff_trans);
       float Ad = 0.f, As = 0.f;
       float dsc = s.L * s.Kc * s.c, ssc = s.L * s.S;
 #pragma unroll
@@ -204,28 +211,31 @@ __global__ void __launch_bounds__(256) ggx_bwd_kernel(GgxPtrs P, GgxGradPtrs Gp,
       }
       float dL = Ad * s.Kc * s.c + As * s.S;                     // d/dL of (diff + spec)
       bool valid = (g * 4 + i) < M;
-      if (valid) light_acc += dL / s.d2;
-      o_dist[i] = dL * light * (-2.0f * p.dist) / (s.d2 * s.d2);
+      if (valid) light_acc += __fdividef(dL, s.d2);
+      o_dist[i] = __fdividef(dL * light * (-2.0f * p.dist), s.d2 * s.d2);
       float dc = Ad * s.L * s.Kc;                                // diffuse cosine
       float dS = As * s.L;
-      float dD = dS * kF * s.G / s.q;
-      float dG = dS * kF * s.D / s.q;
-      dc += dS * kF * s.D * s.G * (-4.0f) / (s.q * s.q);
+      const float rq = __fdividef(1.0f, s.q);
+      float dD = dS * kF * s.G * rq;
+      float dG = dS * kF * s.D * rq;
+      dc += dS * kF * s.D * s.G * (-4.0f) * rq * rq;
       float dden = -dD * s.D * s.D;                              // D = 1/den
       float da = dden * kPi * 2.0f * s.a * s.root * s.root;
       float droot = dden * kPi * s.a * s.a * 2.0f * s.root;
-      float dc2 = droot * (1.0f - 1.0f / s.a2e);
-      float da2e = droot * (-(1.0f - s.c2) / (s.a2e * s.a2e));
+      const float ra2e = __fdividef(1.0f, s.a2e);
+      float dc2 = droot * (1.0f - ra2e);
+      float da2e = droot * (-(1.0f - s.c2) * ra2e * ra2e);
       da += da2e * 2.0f * s.a;
       dc += dc2 * 2.0f * s.c;
       float dG1 = dG * 2.0f * s.G1;
       float dh = -dG1 * s.G1 * s.G1 * 0.5f;                      // G1 = 2/(1+h)
-      float drt = dh * s.rt / s.h;
+      float drt = __fdividef(dh * s.rt, s.h);
       da += drt * s.tan_t;
       float dtan = drt * s.a;
-      float dsin = dtan / s.cpe;
-      dc -= dtan * s.sin_t / (s.cpe * s.cpe);
-      dc += dsin * (-s.c / s.sin_t);
+      const float rcpe = __fdividef(1.0f, s.cpe);
+      float dsin = dtan * rcpe;
+      dc -= dtan * s.sin_t * rcpe * rcpe;
+      dc += dsin * __fdividef(-s.c, s.sin_t);
       bool pass = (s.c_raw >= 0.00001f) && (s.c_raw <= 0.99999f);  // clamp backward
       float dcr = pass ? dc : 0.f;
 #pragma unroll
