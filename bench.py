@@ -490,7 +490,13 @@ def run_ours(args):
                     "ms_per_step": float(te.item()) * 1e3 / e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"kernel": roof_kernel, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE mlp_h16 launch of this workload (4,096 rows,
+                         # H = 512) from the committed ncu --set full capture (profiles/r1l_mlp_h16_ncu.md, launch 0,
+                         # cold cache: the fp16 weight copies, 7.3 MB, and the encoded points are read once from HBM; the
+                         # activations live in L2).  The kernel's operand stream is L2 -> SM: 0.48 GB per launch.
+                         "traffic": (8.18e6 if (_prev == 2 and H == 512 and S == 64) else None),
+                         "traffic_unit": "bytes of DRAM traffic per launch (ncu, profiles/r1l_mlp_h16_ncu.md)",
                          "mode": roof_mode + "; achieved = ALGORITHMIC fp32 FLOPs of the evaluations executed / tracer time "
                                  "(whole tracer call incl. its state-machine kernels); peak = bf16 dense tensor, sustained, of "
                                  + pk["source"],
