@@ -104,10 +104,18 @@ def load() -> C.CDLL:
     return lib
 
 
+_DEBUG_SYNC = bool(os.environ.get("IRONB_DEBUG_SYNC"))
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().ironb_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"iron_b200 {what} failed (code {rc}): {msg}")
+    if _DEBUG_SYNC:      # diagnostic: wait for the calling stream after every library call and name the call that faulted
+        try:
+            torch.cuda.current_stream().synchronize()
+        except Exception as e:
+            raise RuntimeError(f"iron_b200 {what}: device fault surfaced after this call: {e}") from None
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:

@@ -11,6 +11,7 @@ is not produced (the reference never uses it: the query points are detached trac
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -128,6 +129,8 @@ class _SDFEval(torch.autograd.Function):
         dev = x.device
         packed = net.folded()
         save = any(ctx.needs_input_grad[4:])
+        ctx.simt = bool(os.environ.get("IRONB_EIK_SIMT")) and not want_yf      # diagnostic: FFMA GEMMs for gradient-only calls
+        prev_mode = lib.ironb_set_gemm_mode(0) if ctx.simt else None
         lay = net.layout
         y = torch.empty(M, 1, dtype=torch.float32, device=dev) if want_yf else None
         feat = torch.empty(M, lay.d_out - 1, dtype=torch.float32, device=dev) if want_yf else None
@@ -138,6 +141,8 @@ class _SDFEval(torch.autograd.Function):
             _lib.check(lib.ironb_sdf_getall_fwd(C.byref(lay), _lib.ptr(packed), _lib.ptr(x), M, _lib.ptr(y), _lib.ptr(feat),
                                                 _lib.ptr(grad), int(save), _lib.ptr(ws), ws.numel(), _lib.stream()),
                        "sdf_getall_fwd")
+        if prev_mode is not None:
+            lib.ironb_set_gemm_mode(prev_mode)
         ctx.net, ctx.M, ctx.x = net, M, x
         ctx.ws = ws if save else None
         ctx.packed = packed if save else None
@@ -161,10 +166,13 @@ class _SDFEval(torch.autograd.Function):
         ggrad = _lib.f32c(ggrad) if (want_grad and ggrad is not None) else None
         dev = ctx.x.device
         dpacked = torch.zeros(int(lay.packed_floats), dtype=torch.float32, device=dev)
+        prev_mode = lib.ironb_set_gemm_mode(0) if ctx.simt else None
         with torch.cuda.device(dev):
             _lib.check(lib.ironb_sdf_getall_bwd(C.byref(lay), _lib.ptr(ctx.packed), _lib.ptr(ctx.x), M, _lib.ptr(gy),
                                                 _lib.ptr(gfeat), _lib.ptr(ggrad), _lib.ptr(ctx.ws), ctx.ws.numel(),
                                                 _lib.ptr(dpacked), _lib.stream()), "sdf_getall_bwd")
+        if prev_mode is not None:
+            lib.ironb_set_gemm_mode(prev_mode)
         grads = net.unfold_grads(dpacked)
         ctx.ws = None
         return (None, None, None, None, *grads)
