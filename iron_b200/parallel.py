@@ -47,12 +47,16 @@ def allreduce_gradients(params: Sequence[torch.nn.Parameter], world: int, averag
     if average:
         flat.div_(world)
     off = 0
+    dsts, srcs = [], []
     for p in params:
         n = p.numel()
         g = flat[off:off + n].view_as(p)
         if p.grad is None:
             p.grad = g.clone()
         else:
-            p.grad.copy_(g)
+            dsts.append(p.grad)
+            srcs.append(g)
         off += n
+    if dsts:
+        torch._foreach_copy_(dsts, srcs)     # one multi-tensor kernel instead of one copy launch per parameter
     return int(flat.numel())
