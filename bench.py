@@ -569,6 +569,12 @@ def main():
         # kills the context, nothing can be measured in this process afterwards) the same step is measured with eager
         # execution in a fresh child and the line says so.  The child's JSON line is relayed unchanged otherwise.
         env = dict(os.environ, IRONB_BENCH_CHILD="1")
+        try:    # the C-ABI library is loaded here too (fails loudly if it is missing), although the child does the GPU work
+            from iron_b200 import _lib as _parent_lib
+            _parent_lib.load()
+        except Exception as e:
+            sys.stderr.write(f"bench.py: cannot load libiron_b200.so: {e}\n")
+            sys.exit(1)
         for attempt, extra in enumerate(([], ["--exec", "eager"])):
             r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + extra, env=env,
                                stdout=subprocess.PIPE, stderr=None)
