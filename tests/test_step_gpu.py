@@ -286,3 +286,43 @@ def test_graphed_training_iterations_with_fused_adam_match_eager_torch_adam(gold
     # Adam's first steps move every element by ~lr * sign(g): elements whose gradient is ~0 (zero-initialised biases) turn the
     # atomic-order noise of the weight gradients into O(lr) differences, so the bound is loose in relative terms
     assert worst <= 5e-4, worst
+
+
+def test_graphed_step_bench_configuration_matches_eager():
+    """The bench workload itself (BASELINE configs[1]: H = 512, 64 x 64 centre crop, 2,048 eikonal points): the graph replay
+    with its parallel streams (eikonal branch, three material MLPs) against the eager single-stream step -- loss and every
+    parameter gradient -- over several replays."""
+    import iron_b200 as ib
+    torch.manual_seed(0)
+    nets = ib.init_rendering_network_dict("ggx")
+    torch.manual_seed(0)
+    sdf = ib.SDFNetwork(d_in=3, d_out=257, d_hidden=512, n_layers=8, skip_in=[4], multires=6, bias=0.5, scale=1.0,
+                        geometric_init=True, weight_norm=True).to(DEV)
+    nets["point_light_network"].set_light(32.0)
+    Kh = torch.tensor(O.FIXTURE_K, dtype=torch.float64).reshape(4, 4).float()
+    Wh = torch.tensor(O.FIXTURE_W2C, dtype=torch.float64).reshape(4, 4).float()
+    S, ul = 64, (224, 224)
+    gen = torch.Generator().manual_seed(11)
+    target = (torch.rand(S, S, 3, generator=gen) * 0.5)
+    eik = torch.empty(S * S // 2, 3).uniform_(-1.0, 1.0, generator=gen)
+    rf = ib.make_render_fn(ib.GGXColocatedRenderer(use_cuda=True))
+    params = [("sdf." + k, p) for k, p in sdf.named_parameters()]
+    for nm in ("diffuse_albedo_network", "specular_albedo_network", "specular_roughness_network", "point_light_network"):
+        params += [(nm + "." + k, p) for k, p in nets[nm].named_parameters()]
+    gs = ib.GraphedStage2Step(sdf, nets, ib.RayTracer(), rf, Kh, Wh, (S, S), eik.shape[0], crop_ul=ul)
+    assert gs._eik_stream is not None and gs._mat_streams is not None       # the overlapped configuration is what is tested
+    graph_runs = []
+    for _ in range(5):
+        loss = gs.step(target=target.pin_memory(), eik_points=eik.pin_memory())
+        torch.cuda.synchronize()
+        graph_runs.append((float(loss), {k: p.grad.clone() for k, p in params}))
+    cam, _, _ = ib.Camera(512, 512, Kh, Wh).crop_region(S, S, ul_corner=ul)
+    for _, p in params:
+        p.grad = None
+    l_ref, _ = ib.stage2_step(sdf, nets, ib.RayTracer(), rf, cam, target.to(DEV), eik.to(DEV), dense_shading=True)
+    g_ref = {k: p.grad.clone() for k, p in params}
+    for lg, gg in graph_runs:
+        assert abs(lg - float(l_ref)) <= 1e-6 * abs(float(l_ref)), (lg, float(l_ref))
+        worst = max(rel_l2(gg[k].cpu().numpy(), g_ref[k].cpu().numpy()) for k in g_ref)
+        assert worst <= 1e-5, worst
+    print(f"bench configuration: loss {graph_runs[0][0]:.7f} / {float(l_ref):.7f}, 5 replays, gradients within 1e-5")
