@@ -192,3 +192,39 @@ def test_trace_other_widths_depths_vs_oracle(H, n_layers, multires, trace_mode):
     r2 = iron_b200.RayTracer()(net, o, d, t0, t1, hit)
     assert torch.equal(r2["convergent_mask"], res["convergent_mask"].reshape(-1)[:1531]) or \
         float((r2["convergent_mask"] == res["convergent_mask"].reshape(-1)[:1531]).float().mean()) >= 0.999
+
+
+@pytest.mark.parametrize("gain", [0.1, 10.0])
+def test_fp16x2_mlp_with_rescaled_layers_matches_ffma(gain):
+    """The fp16x2-split operands must not depend on the O(1) scale of the seed initialisation: rescale two hidden layers by
+    `gain` (activations and weights move by 10x up / down; the function changes, which does not matter here) and compare ONE
+    MLP evaluation per point (work_mask = False finalises every ray after the first evaluation) of the tensor-core tracer with
+    the exact fp32 FFMA tracer on the same weights."""
+    import iron_b200
+    from iron_b200 import _lib
+    torch.manual_seed(0)
+    net = iron_b200.SDFNetwork(d_in=3, d_out=257, d_hidden=256, n_layers=8, skip_in=[4], multires=6, bias=0.5, scale=1.0,
+                               geometric_init=True, weight_norm=True)
+    perturb(net, 0.005, seed=1)
+    with torch.no_grad():
+        net.lin1.weight_g.mul_(gain); net.lin1.bias.mul_(gain)
+        net.lin5.weight_g.mul_(gain); net.lin5.bias.mul_(gain)
+    net = net.to(DEV)
+    gen = torch.Generator().manual_seed(9)
+    x = ((torch.rand(5000, 3, generator=gen) - 0.5) * 1.8).to(DEV)
+    d = torch.zeros_like(x); d[:, 2] = 1.0
+    z = torch.zeros(x.shape[0], device=DEV)
+    wm = torch.zeros(x.shape[0], dtype=torch.bool, device=DEV)
+    lib = _lib.load()
+    out = {}
+    for mode in (0, 2):
+        prev = lib.ironb_set_trace_mode(mode)
+        try:
+            out[mode] = iron_b200.RayTracer()(net, x, d, z, z + 1.0, wm)["sdf"]
+        finally:
+            lib.ironb_set_trace_mode(prev)
+    assert torch.isfinite(out[2]).all()
+    scale = float(out[0].abs().max().clamp_min(1.0))
+    err = float((out[0] - out[2]).abs().max())
+    print(f"gain {gain}: |sdf| up to {float(out[0].abs().max()):.3f}, max |fp16x2 - ffma| = {err:.2e}")
+    assert err <= 2e-5 * scale, (err, scale)
