@@ -65,7 +65,10 @@ class GraphedStage2Step:
         # is part of the graph); their storage must not be reallocated.  Build it before any eager backward through the
         # same parameters (their AccumulateGrad nodes remember the stream they were created on).
 
-    Limits: fixed patch size / eikonal count / tracer settings; no fill_holes / edge sampling (both read counts back)."""
+    Limits: fixed patch size / eikonal count / tracer settings; no fill_holes / edge sampling (both read counts back).
+    `optimizer=` puts the optimiser step at the tail of the graph: single-GPU only -- with several ranks the gradient
+    all-reduce (iron_b200.parallel.allreduce_gradients) has to run between the replay and the optimiser step, so pass
+    optimizer=None there and step the optimiser after the all-reduce."""
 
     def __init__(self, sdf_network, color_network_dict, raytracer, render_fn, K, W2C, target_shape, n_eik, crop_ul=None,
                  full_size=(512, 512), eik_weight=0.1, warmup=3, time_tracer=False, overlap_eikonal=True, optimizer=None):
