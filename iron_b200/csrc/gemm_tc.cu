@@ -72,16 +72,21 @@ bool tc_enabled() {
   return m == 1;
 }
 bool pdl_enabled() {
+#ifdef IRONB_ENABLE_PDL
+  // measured (bench.py, graph replay with three parallel streams): 5.12 ms/step with PDL, 4.99 without -- the early CTAs of
+  // a dependent GEMM hold whole SMs (192 KiB of shared memory each) while they wait, which costs the other streams more
+  // than the hidden prologue gains; isolated eager chains do gain (wgrad 40 -> 36 us).  Needs the build flag (the
+  // griddepcontrol instructions are compiled out otherwise, and the launch attribute without them would be a race) AND
+  // IRONB_PDL=1.
   static int v = -1;
   if (v < 0) {
-    // measured (bench.py, graph replay with three parallel streams): 5.12 ms/step with PDL, 4.99 without -- the early CTAs of
-    // a dependent GEMM hold whole SMs (192 KiB of shared memory each) while they wait, which costs the other streams more
-    // than the hidden prologue gains.  Off unless IRONB_PDL=1 AND the library is built with -DIRONB_ENABLE_PDL (the
-    // griddepcontrol instructions are compiled out otherwise); isolated eager chains do gain: wgrad 40 -> 36 us.
     const char* e = getenv("IRONB_PDL");
     v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
+#else
+  return false;
+#endif
 }
 static std::atomic<int> g_write_hi{-1};
 bool split_writes_hi() {
