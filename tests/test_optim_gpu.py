@@ -44,7 +44,7 @@ def test_fused_adam_matches_torch_adam(wd):
     torch.cuda.synchronize()
     assert mine.steps_taken == 20
     for i, (x, y) in enumerate(zip(a, b)):
-        err = float((x - y).abs().max() / x.abs().max().clamp_min(1e-30))
+        err = float((x.detach() - y.detach()).abs().max() / x.detach().abs().max().clamp_min(1e-30))
         assert err <= 2e-6, (i, err)
         # moments too (torch keeps them in optimizer.state)
         for k in ("exp_avg", "exp_avg_sq"):
