@@ -265,6 +265,9 @@ def workload_config(args, patch):
 
 # ------------------------------------------------------------------------------------------ CUDA arm
 def run_ours(args):
+    import faulthandler
+    # a stuck run prints where every thread is and exits, so that a driver (or the parent's eager fallback) is not left waiting
+    faulthandler.dump_traceback_later(float(os.environ.get("IRONB_BENCH_WATCHDOG_S", "180")), exit=True)
     import torch
     import torch.distributed as dist
 
@@ -516,6 +519,7 @@ def run_ours(args):
             line["ggx_roofline"] = ggx_microbench(dev, pk)
             line["cpu_baseline"] = cpu_baseline(H, S)
         emit(line)
+    faulthandler.cancel_dump_traceback_later()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -576,8 +580,12 @@ def main():
             sys.stderr.write(f"bench.py: cannot load libiron_b200.so: {e}\n")
             sys.exit(1)
         for attempt, extra in enumerate(([], ["--exec", "eager"])):
-            r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + extra, env=env,
-                               stdout=subprocess.PIPE, stderr=None)
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + extra, env=env,
+                                   stdout=subprocess.PIPE, stderr=None, timeout=float(os.environ.get("IRONB_BENCH_CHILD_TIMEOUT", "240")))
+            except subprocess.TimeoutExpired as te:
+                sys.stderr.write(f"bench.py: child (attempt {attempt}) did not finish in {te.timeout:.0f} s; killed\n")
+                continue
             lines = [ln for ln in r.stdout.decode("utf-8", "replace").splitlines() if ln.startswith("{")]
             if r.returncode == 0 and lines:
                 line = json.loads(lines[-1])
