@@ -267,6 +267,7 @@ def workload_config(args, patch):
 def run_ours(args):
     import faulthandler
     # a stuck run prints where every thread is and exits, so that a driver (or the parent's eager fallback) is not left waiting
+    faulthandler.enable()          # a host-side crash (SIGSEGV ...) prints the Python stacks to stderr
     faulthandler.dump_traceback_later(float(os.environ.get("IRONB_BENCH_WATCHDOG_S", "180")), exit=True)
     import torch
     import torch.distributed as dist
@@ -523,6 +524,12 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    # The measurement is complete and the line is out.  Leave without running the interpreter's teardown: destroying the
+    # captured graph, its private memory pool, the side streams and the external events in arbitrary order at exit crashed
+    # one soak run in three (SIGSEGV after the last replay) -- nothing of value happens after this point.
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 _REAL_STDOUT = None
@@ -587,7 +594,9 @@ def main():
                 sys.stderr.write(f"bench.py: child (attempt {attempt}) did not finish in {te.timeout:.0f} s; killed\n")
                 continue
             lines = [ln for ln in r.stdout.decode("utf-8", "replace").splitlines() if ln.startswith("{")]
-            if r.returncode == 0 and lines:
+            if lines and r.returncode != 0:
+                sys.stderr.write(f"bench.py: child exited with code {r.returncode} AFTER printing its result line (teardown)\n")
+            if lines:
                 line = json.loads(lines[-1])
                 if attempt == 1:
                     line["config"]["execution"] += " -- FALLBACK: the CUDA-graph child exited with an error"

@@ -153,6 +153,17 @@ class GraphedStage2Step:
         self._grads = {id(p): p.grad for p in self.params}    # the graph's static gradient tensors
         self.kernels_per_replay = int(_lib.load().ironb_launch_count() - n0)   # this library's kernel nodes in the graph
 
+    def close(self):
+        """Releases the captured graph, its memory pool and the events while the CUDA context is still alive (leaving that to
+        the interpreter's teardown order crashed a long soak run once).  The object is unusable afterwards."""
+        torch.cuda.synchronize(self.device)
+        self._tracer_events = None
+        self.loss, self.results = None, None
+        self._grads = {}
+        if self.graph is not None:
+            self.graph.reset()
+            self.graph = None
+
     def grads(self):
         """{id(parameter): static gradient tensor}: rewritten by every replay.  `step` re-attaches them as `.grad`, so an
         optimiser's `zero_grad(set_to_none=True)` between steps is harmless."""

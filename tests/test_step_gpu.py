@@ -233,6 +233,7 @@ def test_graphed_step_matches_eager_step(golden):
     l_ref4, _ = ib.stage2_step(sdf, nets, ib.RayTracer(), ib.make_render_fn(ib.GGXColocatedRenderer(use_cuda=True)), cam4,
                                target2.to(DEV), eik.to(DEV), eik_weight=0.1, dense_shading=True)
     assert abs(loss4 - float(l_ref4)) <= 1e-6 * abs(loss4), (loss4, float(l_ref4))
+    gs.close()
 
 
 def test_graphed_training_iterations_with_fused_adam_match_eager_torch_adam(golden):
@@ -286,6 +287,7 @@ def test_graphed_training_iterations_with_fused_adam_match_eager_torch_adam(gold
     # Adam's first steps move every element by ~lr * sign(g): elements whose gradient is ~0 (zero-initialised biases) turn the
     # atomic-order noise of the weight gradients into O(lr) differences, so the bound is loose in relative terms
     assert worst <= 5e-4, worst
+    gs.close()
 
 
 def test_graphed_step_bench_configuration_matches_eager():
@@ -326,3 +328,4 @@ def test_graphed_step_bench_configuration_matches_eager():
         worst = max(rel_l2(gg[k].cpu().numpy(), g_ref[k].cpu().numpy()) for k in g_ref)
         assert worst <= 1e-5, worst
     print(f"bench configuration: loss {graph_runs[0][0]:.7f} / {float(l_ref):.7f}, 5 replays, gradients within 1e-5")
+    gs.close()
