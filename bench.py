@@ -486,7 +486,8 @@ def run_ours(args):
                          "arithmetic is peak/6 (tf32 = 1/2 bf16 rate, x3 MMAs)")
             split_cost = 6.0
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "warmup_steps_run": n_warm,      # W steps, extended to >= 0.5 s of continuous load (see the warm-up loop)
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, S),
             "clocks": clocks,
