@@ -118,33 +118,84 @@ def crop_corner(rank: int, patch: int):
 
 
 # ------------------------------------------------------------------------------------------ CPU oracle arm
-def oracle_setup(hidden: int, patch: int, rank: int = 0):
+def oracle_setup(hidden: int, patch: int, rank: int = 0, device=None):
+    """The oracle's state for one step: seed-0 weights, the rank's crop, the rank's target / eikonal samples (the same
+    seeds run_ours uses).  device: None = CPU (the reference arm / cpu_baseline); a CUDA device = the reference path as
+    eager PyTorch on the GPU (cuda_eager_baseline)."""
     import torch
     from oracle import iron_oracle as O
     torch.manual_seed(0)
     mats = O.make_material_dict()
     torch.manual_seed(0)
     sdf = O.make_sdf_params(d_hidden=hidden)
+    light = torch.tensor(32.0)
+    fx = O.OCamera.fixture()
+    K, W2C = fx.K, fx.W2C
+    target = torch.rand(patch, patch, 3, generator=torch.Generator().manual_seed(11 + rank)) * 0.5
+    eik = torch.empty(patch * patch // 2, 3).uniform_(-1.0, 1.0, generator=torch.Generator().manual_seed(12 + rank))
+    if device is not None:
+        sdf = {k: v.detach().to(device) for k, v in sdf.items()}
+        mats = {n: {k: v.detach().to(device) for k, v in d.items()} for n, d in mats.items()}
+        light, K, W2C, target, eik = (t.to(device) for t in (light, K, W2C, target, eik))
     for d in [sdf] + list(mats.values()):
         for v in d.values():
             v.requires_grad_(True)
-    light = torch.tensor(32.0, requires_grad=True)
-    cam = O.OCamera.fixture().crop(patch, patch, crop_corner(rank, patch))
-    target = torch.rand(patch, patch, 3, generator=torch.Generator().manual_seed(11)) * 0.5
-    eik = torch.empty(patch * patch // 2, 3).uniform_(-1.0, 1.0, generator=torch.Generator().manual_seed(12))
+    light.requires_grad_(True)
+    cam = O.OCamera(512, 512, K, W2C).crop(patch, patch, crop_corner(rank, patch))
     return O, sdf, mats, light, cam, target, eik
 
 
 def oracle_step(state):
+    """One oracle step; returns (seconds, loss).  On a CUDA state the time is the host wall time around a synchronised
+    step (cuda_eager_baseline additionally takes CUDA events)."""
     import torch
     O, sdf, mats, light, cam, target, eik = state
     for d in [sdf] + list(mats.values()):
         for v in d.values():
             v.grad = None
     light.grad = None
+    cuda = light.is_cuda
+    if cuda:
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
-    O.stage2_step(sdf, mats, light, cam, target, eik.clone())
-    return time.perf_counter() - t0
+    if cuda:
+        with torch.device(light.device):       # the oracle's factory calls (linspace, zeros ...) follow its inputs
+            loss, _ = O.stage2_step(sdf, mats, light, cam, target, eik.clone())
+        torch.cuda.synchronize()
+    else:
+        loss, _ = O.stage2_step(sdf, mats, light, cam, target, eik.clone())
+    return time.perf_counter() - t0, float(loss)
+
+
+def cuda_eager_baseline(hidden: int, patch: int, dev, steps: int = 5, warmup: int = 2):
+    """SURVEY 8(d) / BASELINE.md section 3, last bullet: the reference path (models/raytracer.py:778-814 ->
+    models/fields.py:120-137 -> models/renderer_ggx.py:82-146, restated by the oracle and pinned to the reference by
+    tests/golden) executed as EAGER PyTorch on this B200, fp32 with TF32 off, CUDA-event timed, same weights / crop /
+    target / eikonal samples as the hand-written path.  This is the competitor on equal hardware."""
+    import torch
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        st = oracle_setup(hidden, patch, 0, device=dev)
+        for _ in range(warmup):
+            oracle_step(st)
+        ms, loss = [], None
+        for _ in range(steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _, loss = oracle_step(st)
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    t = statistics.median(ms)
+    return {"value": patch * patch / (t * 1e-3), "unit": UNIT, "ms_per_step": t, "steps": steps, "warmup": warmup,
+            "loss": loss, "rays": patch * patch,
+            "what": "the reference path (oracle restatement, torch.autograd incl. the double backward) as eager PyTorch on "
+                    "cuda:0, fp32, allow_tf32=False, CUDA events around the step (host syncs of the reference's control "
+                    "flow included), same weights / crop / target / eikonal samples"}
 
 
 def cpu_baseline(hidden: int, patch: int, budget_s: float = 20.0):
@@ -155,19 +206,20 @@ def cpu_baseline(hidden: int, patch: int, budget_s: float = 20.0):
     torch.set_num_threads(cores)
     # calibrate on a 16x16 crop, then pick the sample size
     st = oracle_setup(hidden, 16)
-    t16 = oracle_step(st)
-    t16 = min(t16, oracle_step(st))
+    t16 = oracle_step(st)[0]
+    t16 = min(t16, oracle_step(st)[0])
     per_ray = t16 / 256.0
     size = patch
     while size > 16 and per_ray * size * size * 2 > budget_s:
         size //= 2
     st = oracle_setup(hidden, size)
     oracle_step(st)                      # warm-up
-    ts = [oracle_step(st)]
+    t1, loss = oracle_step(st)
+    ts = [t1]
     if sum(ts) * 2 < budget_s:
-        ts.append(oracle_step(st))
+        ts.append(oracle_step(st)[0])
     t = statistics.median(ts)
-    return {"value": size * size / t, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": size * size / t, "unit": UNIT, "cores": cores, "kind": "port", "loss": loss, "rays": size * size,
             "sample": f"{size}x{size} centre crop ({size * size} rays) of the same view/weights, {len(ts)} timed step(s) "
                       f"after 1 warm-up, torch CPU fp32 {torch.get_num_threads()} threads, {t:.2f} s/step"}
 
@@ -183,7 +235,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     st = oracle_setup(args.hidden, 16)
-    t16 = min(oracle_step(st), oracle_step(st))
+    t16 = min(oracle_step(st)[0], oracle_step(st)[0])
     per_ray = t16 / 256.0
     size = args.patch
     total = args.steps + args.warmup
@@ -192,7 +244,7 @@ def run_reference(args):
     st = oracle_setup(args.hidden, size)
     for _ in range(args.warmup):
         oracle_step(st)
-    ts = [oracle_step(st) for _ in range(args.steps)]
+    ts = [oracle_step(st)[0] for _ in range(args.steps)]
     t = sum(ts) / len(ts)
     v = size * size / t
     sample = (f"{size}x{size} centre crop ({size * size} rays/step) of the configs[1] view, oracle port of the reference "
@@ -266,21 +318,37 @@ def workload_config(args, patch):
 # ------------------------------------------------------------------------------------------ CUDA arm
 def run_ours(args):
     import faulthandler
-    # a stuck run prints where every thread is and exits, so that a driver (or the parent's eager fallback) is not left waiting
-    faulthandler.enable()          # a host-side crash (SIGSEGV ...) prints the Python stacks to stderr
-    faulthandler.dump_traceback_later(float(os.environ.get("IRONB_BENCH_WATCHDOG_S", "180")), exit=True)
-    import torch
-    import torch.distributed as dist
-
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # a stuck run prints where every thread is and exits, so that a driver is not left waiting; the stage log says how far
+    # the rank came (stderr with IRONB_BENCH_VERBOSE=1, and gpurun_out/bench_rank<r>.log when that directory exists)
+    faulthandler.enable()          # a host-side crash (SIGSEGV ...) prints the Python stacks to stderr
+    faulthandler.dump_traceback_later(float(os.environ.get("IRONB_BENCH_WATCHDOG_S", "180")), exit=True)
+    _t_start = time.perf_counter()
+    _logf = None
+    if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        _logf = open(os.path.join(ROOT, "gpurun_out", f"bench_rank{rank}.log"), "a", buffering=1)
+
+    def stage(msg):
+        STAGE[0] = msg
+        line_ = f"[bench rank {rank} +{time.perf_counter() - _t_start:7.2f}s] {msg}\n"
+        if _logf is not None:
+            _logf.write(line_)
+        if os.environ.get("IRONB_BENCH_VERBOSE"):
+            sys.stderr.write(line_)
+
+    stage("start")
+    import torch
+    import torch.distributed as dist
+    stage("torch imported")
     # NVML is initialised before anything else (its start-up is slow and must not run next to the timed loop)
     sampler = ClockSampler(local) if (rank == 0 and not args.no_clocks) else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    stage("process group up" if world > 1 else "device set")
 
     import iron_b200 as ib
     from iron_b200 import _lib
@@ -333,8 +401,10 @@ def run_ours(args):
         tracer.collect_stats = os.environ.get("IRONB_BENCH_STATS", "1") != "0"
         gs = ib.GraphedStage2Step(sdf, nets, tracer, render_fn, K_h, W2C_h, (S, S), S * S // 2, crop_ul=ul,
                                   time_tracer=os.environ.get("IRONB_BENCH_TIME_TRACER", "1") != "0")
+        stage("graph captured")
         gs.step(target=target_h, eik_points=eik_h)
         torch.cuda.synchronize()
+        stage("first replay done")
 
     def step(cam_, target_, eik_, time_trace=False):
         if gs is not None:           # inputs are already in the graph's static buffers (cam_/target_/eik_ are those values)
@@ -387,6 +457,7 @@ def run_ours(args):
         if n_warm % 4 == 0:
             torch.cuda.synchronize()
     barrier()
+    stage(f"warm-up done ({n_warm} steps)")
 
     # ---- timed: K steps, per-step CUDA events, L2 flushed between steps
     if gs is None:
@@ -413,6 +484,7 @@ def run_ours(args):
             if world > 1:
                 barrier()
     barrier()
+    stage("timed loop done")
     wall = time.perf_counter() - wall0
     epoch1 = time.time()
     launches = lib.ironb_launch_count() - l0
@@ -464,6 +536,7 @@ def run_ours(args):
     h2d = 2 * 4 * 16 * 4 + target_h.numel() * 4 + eik_h.numel() * 4   # two cameras (full view + crop) x 4 matrices, patch, samples
     d2h = 4 + (0 if args.shading == "dense" else 4)   # loss (+ the hit count the shading chunk reads back when compacting)
 
+    stage("e2e loop done")
     gc.enable()
     clocks = sampler.stop(epoch0, epoch1) if sampler else None
     if rank == 0:
@@ -519,7 +592,16 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             line["ggx_roofline"] = ggx_microbench(dev, pk)
+            # the reference path as eager PyTorch on this GPU (the competitor on equal hardware), then on the host cores
+            line["cuda_eager_baseline"] = cuda_eager_baseline(H, S, dev)
             line["cpu_baseline"] = cpu_baseline(H, S)
+            ce, cb = line["cuda_eager_baseline"], line["cpu_baseline"]
+            ce["speedup_of_this_library"] = {"device_timed": value / ce["value"], "e2e": e2e_value / ce["value"]}
+            rel = lambda a, b: abs(a - b) / max(abs(b), 1e-30)
+            line["loss_check"] = {      # same weights, crop, target and eikonal samples in all three
+                "loss_gpu": loss_host, "loss_reference_cuda_eager": ce["loss"], "rel_err_vs_cuda_eager": rel(loss_host, ce["loss"]),
+                "loss_oracle_cpu": cb["loss"] if cb["rays"] == S * S else None,
+                "rel_err_vs_oracle_cpu": rel(loss_host, cb["loss"]) if cb["rays"] == S * S else None}
         emit(line)
     faulthandler.cancel_dump_traceback_later()
     if world > 1:
@@ -534,6 +616,7 @@ def run_ours(args):
 
 
 _REAL_STDOUT = None
+STAGE = ["not started"]      # the last stage run_ours reached (named in the failure message)
 
 
 def emit(line: dict):
@@ -605,7 +688,38 @@ def main():
                 return
             sys.stderr.write(f"bench.py: child (attempt {attempt}) exited with code {r.returncode}\n")
         sys.exit(1)
-    run_ours(args)
+    guarded_run_ours(args)
+
+
+def guarded_run_ours(args):
+    """run_ours with its failure made visible: the traceback goes to stderr (and to gpurun_out/bench_rank<r>.err when that
+    directory exists), then the process leaves at once with a non-zero code.  A rank that raised must not enter the
+    interpreter's teardown: destroying a NCCL process group whose peers are still inside a collective blocks, the rank
+    lingers with an idle GPU until the watchdog fires, and the launcher's summary then hides which rank failed first and
+    why (SCALE_r01 N=8).  With an immediate exit torchrun sees the first failure, names it, and stops the peers."""
+    import traceback
+    rank = os.environ.get("RANK", "0")
+    try:
+        run_ours(args)
+    except BaseException as e:      # noqa: BLE001 -- includes KeyboardInterrupt / SystemExit from the watchdog
+        if isinstance(e, SystemExit) and e.code in (0, None):
+            raise
+        msg = f"bench.py: rank {rank} FAILED after stage '{STAGE[0]}'\n{traceback.format_exc()}"
+        sys.stderr.write(msg)
+        sys.stderr.flush()
+        try:
+            d = os.path.join(ROOT, "gpurun_out")
+            if os.path.isdir(d):
+                with open(os.path.join(d, f"bench_rank{rank}.err"), "a") as f:
+                    f.write(msg)
+            ef = os.environ.get("TORCHELASTIC_ERROR_FILE")      # torchrun prints this under "Root Cause"
+            if ef:
+                with open(ef, "w") as f:
+                    json.dump({"message": {"message": f"{type(e).__name__}: {e}", "extraInfo":
+                                           {"py_callstack": traceback.format_exc(), "timestamp": str(int(time.time()))}}}, f)
+        except Exception:
+            pass
+        os._exit(1)
 
 
 if __name__ == "__main__":

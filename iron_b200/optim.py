@@ -47,26 +47,88 @@ class FusedAdam(torch.optim.Optimizer):
         self._table_dev = torch.empty(n * C.sizeof(_AdamTensor), dtype=torch.uint8, device=self._dev)
         self._table = (_AdamTensor * n).from_address(self._table_host.data_ptr())
         self._max_numel = max(p.numel() for p, _ in self._flat)
+        self._rows = None            # what the pinned table currently holds
+        self._table_event = None     # recorded after the last eager H2D copy of the table
 
     @property
     def steps_taken(self) -> int:
         return int(self._step_dev.item())
 
-    @torch.no_grad()
-    def step(self, closure=None):
-        loss = closure() if closure is not None else None
-        for i, (p, g) in enumerate(self._flat):
+    # -- the pointer / hyper-parameter table ---------------------------------------------------------------------------
+    def _table_rows(self):
+        rows = []
+        for p, g in self._flat:
             st = self.state[p]
-            t = self._table[i]
             grad = p.grad
             if grad is not None and not (grad.is_contiguous() and grad.dtype == torch.float32):
                 raise RuntimeError("FusedAdam: gradients must be contiguous fp32")
-            t.param, t.grad = p.data_ptr(), (grad.data_ptr() if grad is not None else None)
-            t.exp_avg, t.exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
-            t.numel, t.lr, t.weight_decay = p.numel(), float(g["lr"]), float(g["weight_decay"])
+            rows.append((p.data_ptr(), grad.data_ptr() if grad is not None else None, st["exp_avg"].data_ptr(),
+                         st["exp_avg_sq"].data_ptr(), p.numel(), float(g["lr"]), float(g["weight_decay"])))
+        return rows
+
+    def refresh_table(self) -> bool:
+        """Rewrites the pinned host table from the CURRENT param_groups (lr schedules), gradients and moments; returns
+        whether anything changed.  step() calls it; GraphedStage2Step.step() calls it before every replay, because the
+        captured step() never runs again and the graph's copy node re-reads this pinned table at replay time.  An
+        unchanged table is not rewritten; a changed one waits for the copy that may still be reading the old content."""
+        rows = self._table_rows()
+        if rows == self._rows:
+            return False
+        if self._table_event is not None and not torch.cuda.is_current_stream_capturing():
+            self._table_event.synchronize()
+        for t, r in zip(self._table, rows):
+            t.param, t.grad, t.exp_avg, t.exp_avg_sq, t.numel, t.lr, t.weight_decay = r
+        self._rows = rows
+        return True
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        self.refresh_table()
+        capturing = torch.cuda.is_current_stream_capturing()
         with torch.cuda.device(self._dev):
             self._table_dev.copy_(self._table_host, non_blocking=True)      # pinned -> device, stream ordered
+            if not capturing:
+                if self._table_event is None:
+                    self._table_event = torch.cuda.Event()
+                self._table_event.record()
             _lib.check(_lib.load().ironb_adam_step(_lib.ptr(self._table_dev), len(self._flat), self._max_numel,
                                                    float(self._betas[0]), float(self._betas[1]), float(self._eps),
                                                    _lib.ptr(self._step_dev), _lib.stream()), "adam_step")
+        self.mark_parameters_updated()
         return loss
+
+    def mark_parameters_updated(self) -> None:
+        """The kernel writes the parameters through raw pointers, which torch's version counters do not see; everything
+        keyed on `p._version` (the folded-weight cache of SDFNetwork / RenderingNetwork, autograd's saved-tensor checks)
+        must learn that the values moved.  No kernel is launched.  GraphedStage2Step calls this after every replay whose
+        graph contains the optimiser step."""
+        bump = torch.autograd.graph.increment_version
+        for p, _ in self._flat:
+            bump(p)
+
+    # -- checkpoint / resume -------------------------------------------------------------------------------------------
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["ironb_step"] = self.steps_taken        # the shared device-side step count (bias correction)
+        return sd
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        """Keeps the moment STORAGE (a captured graph holds pointers to it) and copies the loaded values in; restores the
+        step count ("ironb_step", or the largest per-parameter `step` of a torch.optim.Adam state dict)."""
+        sd = dict(state_dict)
+        step = sd.pop("ironb_step", None)
+        keep = {p: (self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"]) for p, _ in self._flat}
+        super().load_state_dict(sd)
+        for p, (m, v) in keep.items():
+            st = self.state[p]
+            if "exp_avg" in st:
+                m.copy_(st["exp_avg"])
+                v.copy_(st["exp_avg_sq"])
+            if step is None and "step" in st:
+                step = max(int(step or 0), int(float(st["step"])))
+            st["exp_avg"], st["exp_avg_sq"] = m, v
+        if step is not None:
+            self._step_dev.fill_(int(step))
+        self._rows = None                           # param_groups were replaced: rebuild the table at the next step

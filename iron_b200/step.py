@@ -226,7 +226,12 @@ class GraphedStage2Step:
             buf[9:18] = C2W[:3, :3].reshape(-1)
             buf[18:21] = C2W[:3, 3]
             self._cam_dev.copy_(self._cam_pin, non_blocking=True)
+        opt = self.optimizer
+        if opt is not None and hasattr(opt, "refresh_table"):
+            opt.refresh_table()          # lr schedules / reloaded state: the graph's copy node re-reads the pinned table
         self.graph.replay()
         for p in self.params:
             p.grad = self._grads[id(p)]
+        if opt is not None and hasattr(opt, "mark_parameters_updated"):
+            opt.mark_parameters_updated()   # the in-graph optimiser moved the parameters: eager folds must refold
         return self.loss

@@ -391,12 +391,19 @@ def get_materials(nets: Dict[str, Params], points: Tensor, normals: Tensor, feat
 # --------------------------------------------------------------------------
 
 _TABLES = None
+_TABLES_DEV: Dict[str, Tuple[Tensor, Tensor]] = {}
 
 
-def ggx_tables() -> Tuple[Tensor, Tensor]:
+def ggx_tables(device=None) -> Tuple[Tensor, Tensor]:
     """MTS_TRANS[5000], MTS_DIFF_TRANS[50] (models/renderer_ggx.py:65-74); the repo ships the
-    same numbers as iron_b200/data/ggx_tables.npz (float32)."""
+    same numbers as iron_b200/data/ggx_tables.npz (float32).  `device`: where the caller's tensors live (the
+    reference's use_cuda flag, :75-78); bench.py's cuda-eager leg runs this file on the GPU."""
     global _TABLES
+    if device is not None and torch.device(device).type != "cpu":
+        key = str(torch.device(device))
+        if key not in _TABLES_DEV:
+            _TABLES_DEV[key] = tuple(t.to(device) for t in ggx_tables())
+        return _TABLES_DEV[key]
     if _TABLES is None:
         import os
         f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "iron_b200", "data",
@@ -408,7 +415,7 @@ def ggx_tables() -> Tuple[Tensor, Tensor]:
 def ggx_shade(light: Tensor, distance: Tensor, normal: Tensor, viewdir: Tensor,
               kd: Tensor, ks: Tensor, alpha: Tensor) -> Dict[str, Tensor]:
     """models/renderer_ggx.py:82-146.  Table lookups are floor-indexed (no gradient)."""
-    trans, diff_trans = ggx_tables()
+    trans, diff_trans = ggx_tables(normal.device)
     L = light / (distance * distance + 1e-10)
     c = torch.sum(viewdir * normal, dim=-1, keepdim=True)
     c = torch.clamp(c, min=0.00001, max=0.99999)
@@ -467,7 +474,7 @@ class OCamera:
 
     def pixel_uv(self) -> Tensor:  # :300-303
         u, v = np.meshgrid(np.arange(self.W), np.arange(self.H))
-        return torch.from_numpy(np.stack((u, v), axis=-1).astype(np.float32)) + 0.5
+        return torch.from_numpy(np.stack((u, v), axis=-1).astype(np.float32)).to(self.K.device) + 0.5
 
     def rays(self, uv: Tensor):  # :254-286
         sh = list(uv.shape[:-1])
@@ -645,7 +652,8 @@ def trace_pixels(p: Params, cam: OCamera, uv: Tensor, max_num_rays: int = 200000
 def morph_closing3(depth: Tensor) -> Tensor:
     """kornia.morphology.closing(depth[None,None], ones(3,3)) restated: flat 3x3 dilation then erosion with the
     'geodesic' border (borders never win), models/raytracer.py:555-557.  kornia is not installable in the build
-    container, so this row is restated from kornia's documentation: PARITY UNPINNED for this function."""
+    container, so this row is restated from kornia's documentation and pinned against an independent implementation:
+    cv2.morphologyEx(MORPH_CLOSE), bit-exact on tests/golden/morph_cv2.npz (oracle/make_golden_cv2.py)."""
     x = depth[None, None]
     dil = torch.nn.functional.max_pool2d(x, 3, stride=1, padding=1)            # implicit -inf padding
     ero = -torch.nn.functional.max_pool2d(-dil, 3, stride=1, padding=1)
@@ -654,8 +662,9 @@ def morph_closing3(depth: Tensor) -> Tensor:
 
 def sobel_magnitude(depth: Tensor) -> Tensor:
     """kornia.filters.sobel(depth[None,None]) restated (normalized=True, eps=1e-6): 3x3 Sobel derivatives / 8 on a
-    replicate-padded image, magnitude sqrt(gx^2 + gy^2 + eps).  models/raytracer.py:569.  PARITY UNPINNED (kornia is not
-    installable in the build container; restated from its documentation)."""
+    replicate-padded image, magnitude sqrt(gx^2 + gy^2 + eps).  models/raytracer.py:569.  kornia is not installable in the
+    build container; restated from its documentation and pinned against cv2.Sobel (scale 1/8, BORDER_REPLICATE) within
+    5e-7 on tests/golden/morph_cv2.npz (oracle/make_golden_cv2.py)."""
     x = torch.nn.functional.pad(depth[None, None], (1, 1, 1, 1), mode="replicate")
     kx = torch.tensor([[-1.0, 0.0, 1.0], [-2.0, 0.0, 2.0], [-1.0, 0.0, 1.0]]) / 8.0
     gx = torch.nn.functional.conv2d(x, kx[None, None])

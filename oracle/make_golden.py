@@ -33,7 +33,7 @@ def import_reference():
             if name == "kornia":
                 # kornia cannot be installed here.  The two calls the hot path's "next" rows make are restated from
                 # kornia's documentation (oracle/iron_oracle.py: morph_closing3, sobel_magnitude) -- those two functions are
-                # therefore UNPINNED; everything around them (edge walk, sub-pixel blending, hole update) is the reference's.
+                # pinned independently against OpenCV (oracle/make_golden_cv2.py); everything around them (edge walk, sub-pixel blending, hole update) is the reference's.
                 sys.path.insert(0, os.path.join(HERE, ".."))
                 from oracle import iron_oracle as _O
                 m.morphology = types.SimpleNamespace(closing=lambda x, kernel: _O.morph_closing3(x[0, 0])[None, None])

@@ -1,5 +1,6 @@
 """fill_holes (row f-4): 3x3 depth closing kernel and the mask / depth / points update of raytrace_camera, against the
-oracle's restatement (models/raytracer.py:552-564).  kornia's closing is restated from its documentation (unpinned)."""
+oracle's restatement (models/raytracer.py:552-564), and against tests/golden/morph_cv2.npz: OpenCV's closing / Sobel of the
+same depth maps (oracle/make_golden_cv2.py), the independent pin for the two kornia calls (models/raytracer.py:557, 569)."""
 import numpy as np
 import pytest
 import torch
@@ -19,6 +20,16 @@ def test_depth_closing_kernel(H, W):
     d[torch.rand(H, W, generator=g) < 0.2] = 0.0            # holes
     got = depth_closing(d.to(DEV)).cpu()
     assert torch.equal(got, O.morph_closing3(d))
+
+
+def test_closing_and_sobel_kernels_match_opencv(golden):
+    """ironb_depth_closing bit-exact, ironb_sobel_depth within 5e-7, against cv2.morphologyEx(MORPH_CLOSE) / cv2.Sobel."""
+    from iron_b200.raytracer import depth_closing, sobel_depth
+    g = golden("morph_cv2")
+    for i in range(int(g["n"])):
+        d = torch.from_numpy(g[f"depth{i}"]).to(DEV)
+        assert np.array_equal(depth_closing(d).cpu().numpy(), g[f"closing{i}"]), f"closing, image {i}"
+        assert_close(sobel_depth(d).cpu().numpy(), g[f"sobel{i}"], 5e-7, what=f"sobel, image {i}")
 
 
 def test_raytrace_camera_fill_holes(trace_mode):

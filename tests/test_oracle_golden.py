@@ -202,7 +202,7 @@ def test_full_step(golden):
 
 def test_step_with_edges_golden(golden):
     """The drivers' default step (fill_holes + edge sampling): oracle vs the real reference's render_camera.  The two kornia
-    calls are shared restatements (unpinned); the edge walk, uniqueness, sub-pixel blending and their gradients are pinned."""
+    calls are shared restatements (pinned against OpenCV below); the edge walk, uniqueness, sub-pixel blending and their gradients are pinned."""
     import torch
     g = golden("step_edges_h256")
     torch.manual_seed(0)
@@ -253,3 +253,14 @@ def test_oracle_adam_matches_torch_optim_adam():
             mine = [O.adam_step(p, g.numpy(), m, v, t, 1e-2, 0.9, 0.999, 1e-8, wd) for (p, m, v), g in zip(mine, grads)]
             for r, (p, m, v) in zip(ref, mine):
                 assert np.allclose(p, r.detach().numpy(), rtol=2e-6, atol=1e-7), (wd, t, np.abs(p - r.detach().numpy()).max())
+
+
+def test_closing_and_sobel_restatements_match_opencv(golden):
+    """The oracle's restatement of kornia.morphology.closing / kornia.filters.sobel (models/raytracer.py:557, 569) against an
+    independent implementation: OpenCV (oracle/make_golden_cv2.py).  Closing bit-exact, Sobel magnitude within 5e-7."""
+    g = golden("morph_cv2")
+    assert int(g["n"]) >= 8
+    for i in range(int(g["n"])):
+        d = torch.from_numpy(g[f"depth{i}"])
+        assert np.array_equal(O.morph_closing3(d).numpy(), g[f"closing{i}"]), f"closing, image {i}"
+        assert np.abs(O.sobel_magnitude(d).numpy() - g[f"sobel{i}"]).max() <= 5e-7, f"sobel, image {i}"
