@@ -451,11 +451,23 @@ def run_ours(args):
     n_warm = 0
     t_w = time.perf_counter()
     min_warm_s = float(os.environ.get("IRONB_BENCH_MIN_WARMUP_S", "0.5"))    # 0 for ncu launch lists
-    while n_warm < max(args.warmup, 3) or time.perf_counter() - t_w < min_warm_s:
-        step(cam, target, eik)
-        n_warm += 1
-        if n_warm % 4 == 0:
-            torch.cuda.synchronize()
+    # Every step contains a collective (the gradient all-reduce), so ALL ranks must run the same number of warm-up steps:
+    # the "is 0.5 s over?" decision is taken in chunks of 4 steps and agreed on by an all-reduce(MAX).  (Round 1 let every
+    # rank consult its own clock: ranks left the loop after different step counts, the stragglers' all-reduce met the
+    # others' barrier, and the 8-GPU run dead-locked in 2 of 3 launches -- SCALE_r01 N=8.)
+    more = torch.zeros(1, dtype=torch.int32, device=dev)
+    while True:
+        for _ in range(4):
+            step(cam, target, eik)
+            n_warm += 1
+        torch.cuda.synchronize()
+        again = n_warm < max(args.warmup, 3) or time.perf_counter() - t_w < min_warm_s
+        if world > 1:
+            more.fill_(1 if again else 0)
+            dist.all_reduce(more, op=dist.ReduceOp.MAX)
+            again = bool(more.item())
+        if not again:
+            break
     barrier()
     stage(f"warm-up done ({n_warm} steps)")
 

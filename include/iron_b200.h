@@ -75,6 +75,9 @@ int ironb_set_gemm_mode(int mode);
  * 3xTF32 operands; 0 = fused persistent fp32-FFMA kernels.  Returns the previous mode.
  * IRONB_TRACE=fused / tf32 selects 0 / 1 at start-up. */
 int ironb_set_trace_mode(int mode);
+/* Truncation de-bias factor of the default tracer's tcgen05 accumulators (csrc/mlp_h16.cu: mlp16_debias); g < 0 only
+ * queries.  Returns the previous factor.  IRONB_MLP_DEBIAS sets it at start-up; 0 switches the correction off. */
+float ironb_set_mlp_debias(float g);
 /* C[M][ldc] = A[M][lda] * B[N][ldb]^T (fp32, K-major operands, N/K/ld multiples of 4): unit-test entry of both GEMMs. */
 int ironb_gemm_nt(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float* C, int ldc,
                   int mode, void* stream);

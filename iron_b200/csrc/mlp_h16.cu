@@ -67,6 +67,7 @@ struct Args {
   float* Fpart;              // [4C][cap] partial sdf sums
   int n_true[MAXH];
   int kpad[MAXH];
+  float gam[MAXH];           // truncation de-bias of the hi*hi accumulator, per layer (see mlp16_debias)
   int n_hidden, skip_layer, Epad, Edim, H, C;
   float nbl2e, ln2_ib;       // -beta * log2(e),  ln(2) / beta
   const int* m_dev;
@@ -144,6 +145,7 @@ __device__ __forceinline__ void epi_unit(const Args& a, const EpiCtx& c, int l, 
                                          uint32_t tfree, uint32_t& se_n) {
   const int m = m0 + c.row;
   const int n_true = a.n_true[l];
+  const float gam = a.gam[l];
   float dot = 0.f;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -175,7 +177,8 @@ __device__ __forceinline__ void epi_unit(const Args& a, const EpiCtx& c, int l, 
       for (int jj = 0; jj < 2; ++jj) {
         const int i = g * 2 + jj;
         const float b = __shfl_sync(0xffffffffu, mybias, h * 16 + i);
-        const float z = fmaf(__uint_as_float(rl[i]), LO_INV, __uint_as_float(r0[i])) + b;
+        const float hh = __uint_as_float(r0[i]);
+        const float z = fmaf(__uint_as_float(rl[i]), LO_INV, fmaf(hh, gam, hh)) + b;
         u[jj] = softplus_fast(z, a.nbl2e, a.ln2_ib);
       }
       if (PRE_SKIP) {   // cat(h, PE)/sqrt(2)
@@ -471,6 +474,32 @@ int split_weights_h(const float* src, int64_t n, void* hi, void* lo, cudaStream_
   return IRONB_OK;
 }
 
+// The tensor core adds into its TMEM accumulator with TRUNCATION (measured: tests/probe_precision.py, probe_mlp_h16.py --
+// the error of one evaluation is a pure bias, signed mean == -mean |err|, proportional to the chain length: -0.99e-6 at
+// H = 256, -2.12e-6 at H = 512), i.e. every one of the K/16 accumulation steps of the hi*hi chain drops on average half
+// an ulp of the running sum, always towards zero.  A round-to-nearest accumulator would drop +-half an ulp with zero
+// mean, so the expected loss is added back: acc *= 1 + g * n_steps * 2^-24.  Calibrated on the box
+// (tests/probe_debias.py, profiles/r2_mlp_h16_debias.md): g = 0.25 takes the signed mean error of one evaluation from
+// -2.10e-6 to -1.4e-8 (H = 512) and from -0.99e-6 to -1.2e-7 (H = 256), on the seed-0 init and on perturbed weights alike,
+// and the mean |error| from 2.1e-6 to 8.9e-8 -- the level of the exact-fp32 FFMA tracer (9.1e-8): the loss was almost
+// entirely the deterministic bias.  IRONB_MLP_DEBIAS / ironb_set_mlp_debias override it, 0 switches it off.  The
+// correction is ~5e-7 relative at H = 512, so a network whose statistics differ from the calibration stays fp32-grade.
+static float g_debias = -1.f;
+float mlp16_debias() {
+  if (g_debias < 0.f) {
+    const char* e = getenv("IRONB_MLP_DEBIAS");
+    g_debias = e ? (float)atof(e) : 0.25f;
+    if (!(g_debias >= 0.f && g_debias <= 4.f)) g_debias = 0.f;
+  }
+  return g_debias;
+}
+
+float mlp16_set_debias(float g) {
+  const float prev = mlp16_debias();
+  if (g >= 0.f && g <= 4.f) g_debias = g;
+  return prev;
+}
+
 static int g_nhh = -1;
 int mlp16_nhh() {
   if (g_nhh < 0) {
@@ -507,6 +536,8 @@ int launch_trace_mlp_h16(const ironb_mlp_layout* lay, const float* packed, const
   a.nbl2e = (float)(-(double)lay->beta * 1.4426950408889634); a.ln2_ib = (float)(0.6931471805599453 / (double)lay->beta);
   a.m_dev = m_dev; a.m_mul = m_mul; a.rows_cap = rows_cap; a.cap = cap;
   a.nhh = mlp16_nhh();
+  for (int l = 0; l < last; ++l)
+    a.gam[l] = mlp16_debias() * (float)((lay->in_pad[l] + 15) / 16) / (float)a.nhh * 5.9604645e-8f;   // g * n_steps * 2^-24
   { static int preb = -1; if (preb < 0) { const char* e = getenv("IRONB_MLP_PREB"); preb = (e && atoi(e) >= 1 && atoi(e) <= NSTAGE) ? atoi(e) : NSTAGE; } a.preb = preb; }
   a.dbg = g_mlp_dbg;
 
@@ -541,3 +572,5 @@ int launch_trace_mlp_h16(const ironb_mlp_layout* lay, const float* packed, const
 }
 
 }  // namespace ironb
+
+extern "C" float ironb_set_mlp_debias(float g) { return ironb::mlp16_set_debias(g); }

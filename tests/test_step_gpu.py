@@ -10,6 +10,18 @@ from util import T, TOL_GRAD_REL, TOL_NORMAL, TOL_RGB, assert_close, perturb, re
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
+# The reference's own reproducibility floor (oracle/measure_floor.py -> tests/golden/floor.json): the fraction of hit normals
+# on which the reference algorithm in fp32 agrees with itself in fp64 within 1e-4.  Two fp32-grade evaluations (the CUDA path
+# and the reference's fp32) each deviate from the exact result, so the CUDA path is held to 2.5x the floor's outlier rate --
+# for EVERY tracer mode, no per-mode slack.
+import json as _json
+import os as _os
+FLOOR = _json.load(open(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "floor.json")))
+
+
+def normal_need(key):
+    return 1.0 - 2.5 * (1.0 - FLOOR[key]["normals_within_1e-4"])
+
 
 def build():
     import iron_b200
@@ -50,7 +62,7 @@ def test_step_golden(golden, gemm_mode, trace_mode):
           f"{100 * (nerr <= 1e-4).mean():.2f}% (max {nerr.max():.2e})  distance within 1e-4: {100 * (derr <= 1e-4).mean():.2f}% "
           f"(max {derr.max():.2e})")
     assert_close(res["normal"].detach().cpu().numpy()[both], g["res.normal"][both], TOL_NORMAL, what="normal",
-                 frac=0.99 if trace_mode == "fused-ffma" else 0.97)
+                 frac=normal_need("h256_golden_crop"))
     assert_close(res["normal"].detach().cpu().numpy()[both], g["res.normal"][both], 2e-3, what="normal (all)")
     for k in ("color", "diffuse_color", "specular_color"):
         assert_close(res[k].detach().cpu().numpy()[both], g["res." + k][both], TOL_RGB, 1e-3, what=k, frac=0.995)
@@ -329,3 +341,149 @@ def test_graphed_step_bench_configuration_matches_eager():
         assert worst <= 1e-5, worst
     print(f"bench configuration: loss {graph_runs[0][0]:.7f} / {float(l_ref):.7f}, 5 replays, gradients within 1e-5")
     gs.close()
+
+
+def test_eager_steps_with_fused_adam_match_torch_adam(golden):
+    """The advertised drop-in: an EAGER training loop with iron_b200.FusedAdam against the same loop with the reference's
+    torch.optim.Adam instances.  FusedAdam writes the parameters through raw pointers; unless it bumps their version counters
+    the weight-norm fold cache (keyed on p._version) keeps serving the initial weights and the losses never move."""
+    g = golden("step_h256")
+    ul = tuple(int(v) for v in g["ul"])
+    target, eik = T(g["target"]).to(DEV), T(g["eik_points"]).to(DEV)
+    mat = ("diffuse_albedo_network", "specular_albedo_network", "specular_roughness_network")
+
+    def groups(sdf, nets):
+        return ([{"params": list(sdf.parameters()), "lr": 1e-4}] + [{"params": list(nets[nm].parameters()), "lr": 1e-3} for nm in mat]
+                + [{"params": list(nets["point_light_network"].parameters()), "lr": 1e-2}])
+
+    def run(make_opts):
+        ib, sdf, nets, cam512 = build()
+        cam, _, _ = cam512.crop_region(32, 32, ul_corner=ul)
+        opts = make_opts(ib, groups(sdf, nets))
+        rf = ib.make_render_fn(ib.GGXColocatedRenderer(use_cuda=True))
+        losses = []
+        for _ in range(4):
+            for o in opts:
+                o.zero_grad()
+            loss, _ = ib.stage2_step(sdf, nets, ib.RayTracer(), rf, cam, target, eik, eik_weight=0.1, dense_shading=True)
+            losses.append(float(loss))
+            for o in opts:
+                o.step()
+        probe = sdf.sdf(eik[:64]).detach().cpu().numpy()        # an eager forward AFTER the last optimiser step
+        return losses, probe
+
+    fused, probe_f = run(lambda ib, gr: [ib.FusedAdam(gr)])
+    ref, probe_r = run(lambda ib, gr: [torch.optim.Adam(x["params"], lr=x["lr"]) for x in gr])
+    print("eager + FusedAdam", fused, "eager + torch.optim.Adam", ref)
+    assert abs(ref[0] - ref[3]) > 1e-4 * abs(ref[0]), "the reference loop itself did not move"
+    for a, b in zip(fused, ref):
+        assert abs(a - b) <= 2e-5 * abs(b), (fused, ref)
+    assert np.abs(probe_f - probe_r).max() <= 1e-5
+
+
+def test_graph_with_fused_adam_sees_lr_changes_and_invalidates_eager_folds(golden):
+    """A captured optimiser step never runs its Python again: GraphedStage2Step.step() has to refresh the pinned
+    pointer / hyper-parameter table (lr schedules) before the replay and bump the parameter versions after it."""
+    g = golden("step_h256")
+    ul = tuple(int(v) for v in g["ul"])
+    target, eik = T(g["target"]), T(g["eik_points"])
+    Kh = torch.tensor(O.FIXTURE_K, dtype=torch.float64).reshape(4, 4).float()
+    Wh = torch.tensor(O.FIXTURE_W2C, dtype=torch.float64).reshape(4, 4).float()
+    ib, sdf, nets, _ = build()
+    opt = ib.FusedAdam([{"params": list(sdf.parameters()), "lr": 1e-4}])
+    rf = ib.make_render_fn(ib.GGXColocatedRenderer(use_cuda=True))
+    gs = ib.GraphedStage2Step(sdf, nets, ib.RayTracer(), rf, Kh, Wh, (32, 32), eik.shape[0], crop_ul=ul, eik_weight=0.1,
+                              optimizer=opt)
+    x = eik[:128].to(DEV)
+    f0 = sdf.sdf(x).detach().clone()
+    w0 = sdf.lin3.weight_v.detach().clone()
+    gs.step(target=target.pin_memory(), eik_points=eik.pin_memory())
+    torch.cuda.synchronize()
+    d1 = float((sdf.lin3.weight_v.detach() - w0).abs().max())
+    f1 = sdf.sdf(x).detach().clone()                               # eager call after a replay: must see the new weights
+    assert d1 > 0 and float((f1 - f0).abs().max()) > 0, "eager forward after a replay still used the pre-step fold"
+    opt.param_groups[0]["lr"] = 0.0                                # a scheduler sets lr: the next replay must not move anything
+    w1 = sdf.lin3.weight_v.detach().clone()
+    gs.step()
+    torch.cuda.synchronize()
+    assert float((sdf.lin3.weight_v.detach() - w1).abs().max()) == 0.0, "the replay ignored the new learning rate"
+    # checkpoint / resume: the moments keep their storage (the graph holds pointers to it), values and step count come back
+    import copy
+    sd = copy.deepcopy(opt.state_dict())
+    assert sd["ironb_step"] == 2
+    m_ptr = opt.state[sdf.lin3.weight_v]["exp_avg"].data_ptr()
+    m_val = opt.state[sdf.lin3.weight_v]["exp_avg"].clone()
+    opt.state[sdf.lin3.weight_v]["exp_avg"].zero_()
+    opt._step_dev.zero_()
+    opt.load_state_dict(sd)
+    assert opt.state[sdf.lin3.weight_v]["exp_avg"].data_ptr() == m_ptr
+    assert torch.equal(opt.state[sdf.lin3.weight_v]["exp_avg"], m_val) and opt.steps_taken == 2
+    gs.close()
+
+
+H512_CROPS = {"centre": (224, 224), "silhouette": (342, 224)}
+
+
+@pytest.mark.parametrize("crop", list(H512_CROPS))
+def test_step_bench_configuration_against_oracle(crop, trace_mode):
+    """The configuration bench.py times (BASELINE configs[1]: H = 512, 64 x 64 crop, 2,048 eikonal points, seed-0 weights),
+    full step against the CPU oracle's stage2_step (the restated reference, pinned by tests/golden): hit mask, distance,
+    normal, RGB, loss and every parameter-gradient tensor at the BASELINE tolerances.  `silhouette` straddles the object's
+    outline (r ~ 0.287 -> ~118 px from the image centre), where rays graze and the sampler / bisection do the work."""
+    import iron_b200 as ib
+    S, ul = 64, H512_CROPS[crop]
+    torch.manual_seed(0)
+    nets = ib.init_rendering_network_dict("ggx")
+    torch.manual_seed(0)
+    sdf = ib.SDFNetwork(d_in=3, d_out=257, d_hidden=512, n_layers=8, skip_in=[4], multires=6, bias=0.5, scale=1.0,
+                        geometric_init=True, weight_norm=True)
+    sdf_p = {k: v.detach().clone().requires_grad_(True) for k, v in sdf.state_dict().items()}
+    mat = ("diffuse_albedo_network", "specular_albedo_network", "specular_roughness_network")
+    mats_p = {nm: {k: v.detach().cpu().clone().requires_grad_(True) for k, v in nets[nm].state_dict().items()} for nm in mat}
+    light_p = torch.tensor(32.0, requires_grad=True)
+    sdf = sdf.to(DEV)
+    nets["point_light_network"].set_light(32.0)
+    target = torch.rand(S, S, 3, generator=torch.Generator().manual_seed(11)) * 0.5
+    eik = torch.empty(S * S // 2, 3).uniform_(-1.0, 1.0, generator=torch.Generator().manual_seed(12))
+    K = torch.tensor(O.FIXTURE_K, dtype=torch.float64).reshape(4, 4).float()
+    W2C = torch.tensor(O.FIXTURE_W2C, dtype=torch.float64).reshape(4, 4).float()
+    cam, _, _ = ib.Camera(512, 512, K.to(DEV), W2C.to(DEV)).crop_region(S, S, ul_corner=ul)
+    rf = ib.make_render_fn(ib.GGXColocatedRenderer(use_cuda=True))
+    loss, res = ib.stage2_step(sdf, nets, ib.RayTracer(), rf, cam, target.to(DEV), eik.to(DEV), dense_shading=True)
+    torch.cuda.synchronize()
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    oloss, ores = O.stage2_step(sdf_p, mats_p, light_p, O.OCamera.fixture().crop(S, S, ul), target, eik.clone())
+    m, mr = res["convergent_mask"].cpu().numpy(), ores["convergent_mask"].numpy()
+    agree = (m == mr).mean()
+    both = m & mr
+    assert both.sum() > 500, f"crop {crop}: only {both.sum()} common hits"
+    if crop == "silhouette":
+        assert (~mr).sum() > 500, "the silhouette crop must contain misses"
+    nerr = np.abs(res["normal"].detach().cpu().numpy()[both] - ores["normal"].detach().numpy()[both]).max(axis=-1)
+    derr = np.abs(res["distance"].cpu().numpy()[both] - ores["distance"].numpy()[both])
+    cerr = np.abs(res["color"].detach().cpu().numpy()[both] - ores["color"].detach().numpy()[both]).max(axis=-1)
+    same_mask = bool((m == mr).all())
+    print(f"[H512 {crop} / {trace_mode}] hits {int(m.sum())}/{int(mr.sum())} mask-agree {agree:.5f}  normals<=1e-4: "
+          f"{100 * (nerr <= 1e-4).mean():.2f}% (max {nerr.max():.2e})  dist<=1e-4: {100 * (derr <= 1e-4).mean():.2f}% "
+          f"(max {derr.max():.2e})  rgb max {cerr.max():.2e}  loss {float(loss):.7f} / {float(oloss):.7f}")
+    assert agree >= 0.9995, f"hit mask agreement {agree:.5f}"                     # <= 2 of 4,096 rays (pooled check: test_trace_gpu)
+    assert (derr <= 1e-4).mean() >= 0.995 and derr.max() <= 2.0 / 127, "distance"
+    need = normal_need("h512_" + crop)
+    assert (nerr <= TOL_NORMAL).mean() >= need, f"normals within 1e-4: {(nerr <= 1e-4).mean():.4f}, need {need:.4f}"
+    assert nerr.max() <= 2e-3
+    assert (cerr <= TOL_RGB).mean() >= 0.995, "rgb"
+    assert abs(float(loss) - float(oloss)) <= (1e-3 if same_mask else 2e-2) * abs(float(oloss)), (float(loss), float(oloss))
+    tol = TOL_GRAD_REL if same_mask else 5e-2
+    named = [("sdf." + k, p, sdf_p[k]) for k, p in sdf.named_parameters()]
+    for nm in mat:
+        named += [(nm + "." + k, p, mats_p[nm][k]) for k, p in nets[nm].named_parameters()]
+    worst = 0.0
+    for k, p, q in named:
+        assert p.grad is not None and q.grad is not None, k
+        r = rel_l2(p.grad.cpu().numpy(), q.grad.numpy())
+        worst = max(worst, r)
+        assert r <= tol, (k, r, "same_mask", same_mask)
+    gl = float(nets["point_light_network"].light.grad) if hasattr(nets["point_light_network"], "light") else None
+    if gl is not None:
+        assert abs(gl - float(light_p.grad)) <= tol * abs(float(light_p.grad)), (gl, float(light_p.grad))
+    print(f"[H512 {crop} / {trace_mode}] same_mask={same_mask} worst relative gradient error {worst:.2e}")
