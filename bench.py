@@ -356,12 +356,12 @@ def run_ours(args):
     from oracle import iron_oracle as O   # fixture constants only (camera K / W2C); nothing is computed with it here
     lib = _lib.load()
     if args.tracer != "default":
-        lib.ironb_set_trace_mode({"batched": 2, "tf32": 1, "fused": 0}[args.tracer])
+        lib.ironb_set_trace_mode({"batched": 2, "fused": 0}[args.tracer])
     if args.gemm != "default":
         lib.ironb_set_gemm_mode(1 if args.gemm == "tcgen05" else 0)
     _prev = lib.ironb_set_trace_mode(2)
     lib.ironb_set_trace_mode(_prev)
-    tracer_impl = {2: "batched tcgen05 (fp16x2 split)", 1: "batched tcgen05 (3xTF32)", 0: "fused persistent fp32 FFMA"}[_prev]
+    tracer_impl = {2: "batched tcgen05 (fp16x2 split)", 0: "fused persistent fp32 FFMA"}[_prev]
 
     H, S = args.hidden, args.patch
     torch.manual_seed(0)
@@ -564,12 +564,10 @@ def run_ours(args):
             roof_mode = ("fp16x2 split on tcgen05 (3 kind::f16 MMAs per product, fp32-grade accuracy): the ceiling of this "
                          "arithmetic is peak/3")
             split_cost = 3.0
-        else:
-            roof_kernel = ("mlp_fused_kernel (batched tcgen05 tracer: all 8 hidden SDF-MLP layers + sdf row per 128-row tile, "
-                           "cluster of H/128 CTAs)")
-            roof_mode = ("3xTF32 split on tcgen05 (3 tf32 MMAs per product, fp32-grade accuracy): the ceiling of this "
-                         "arithmetic is peak/6 (tf32 = 1/2 bf16 rate, x3 MMAs)")
-            split_cost = 6.0
+        else:   # --tracer fused: the persistent fp32-FFMA tracer; same FLOP count, reported against the same peak
+            roof_kernel = "trace_kernel (fused persistent fp32-FFMA tracer, exact fp32 association)"
+            roof_mode = "fp32 FFMA on the CUDA cores (diagnostic mode): the tensor peak is not attainable by this arithmetic"
+            split_cost = 1.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "warmup_steps_run": n_warm,      # W steps, extended to >= 0.5 s of continuous load (see the warm-up loop)
@@ -664,7 +662,7 @@ def main():
     ap.add_argument("--shading", default="dense", choices=["dense", "compact"],
                     help="dense: shade every ray and mask (no hit-count read-back, host runs ahead of the tracer); compact: the "
                          "reference's order (compact the hits first: one host sync per step)")
-    ap.add_argument("--tracer", default="default", choices=["default", "batched", "tf32", "fused"])
+    ap.add_argument("--tracer", default="default", choices=["default", "batched", "fused"])
     ap.add_argument("--gemm", default="default", choices=["default", "tcgen05", "ffma"])
     args = ap.parse_args()
     if args.impl == "reference":

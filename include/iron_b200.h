@@ -59,7 +59,11 @@ typedef struct ironb_mlp_layout {
   int64_t off_w[IRONB_MAX_LIN];    /* W_l  [out_pad][in_pad] row-major, float offset into the packed buffer */
   int64_t off_wt[IRONB_MAX_LIN];   /* W_l^T [in_pad][out_pad] */
   int64_t off_b[IRONB_MAX_LIN];    /* b_l  [out_pad] */
-  int64_t packed_floats;           /* total size of the packed buffer, in floats */
+  int64_t packed_floats;           /* size of the fp32 part (W, W^T, b of every layer): the size of a dpacked buffer */
+  int64_t off_h16[IRONB_MAX_LIN];  /* SDF nets, hidden layers: fp16x2-split copy of W_l written by ironb_mlp_fold -- hi
+                                      [out_pad][in_pad] halfs, then lo = fp16((w - hi) * 2^11), same shape; float offset.
+                                      The default tracer's tcgen05 operands (csrc/mlp_h16.cu); 0 = absent */
+  int64_t packed_total_floats;     /* size of the packed buffer ironb_mlp_fold writes (fp32 part + fp16 copies), in floats */
 } ironb_mlp_layout;
 
 const char* ironb_last_error(void);
@@ -71,9 +75,9 @@ int64_t ironb_launch_count(void);
  * 1 = tcgen05 3xTF32 split (tensor cores, fp32-grade accuracy; the default), 0 = fp32 FFMA tiles.
  * Returns the previous mode.  The environment variable IRONB_GEMM=simt selects 0 at start-up. */
 int ironb_set_gemm_mode(int mode);
-/* Tracer implementation: 2 = batched tcgen05 rounds, fp16x2-split operands (default); 1 = batched tcgen05 rounds,
- * 3xTF32 operands; 0 = fused persistent fp32-FFMA kernels.  Returns the previous mode.
- * IRONB_TRACE=fused / tf32 selects 0 / 1 at start-up. */
+/* Tracer implementation: 2 = batched tcgen05 rounds, fp16x2-split operands (default); 0 = fused persistent fp32-FFMA
+ * kernels (exact fp32 association).  Returns the previous mode.  IRONB_TRACE=fused selects 0 at start-up.
+ * (Mode 1, the 3xTF32 predecessor of mode 2, was retired in round 2; 1 is accepted and means 2.) */
 int ironb_set_trace_mode(int mode);
 /* Truncation de-bias factor of the default tracer's tcgen05 accumulators (csrc/mlp_h16.cu: mlp16_debias); g < 0 only
  * queries.  Returns the previous factor.  IRONB_MLP_DEBIAS sets it at start-up; 0 switches the correction off. */

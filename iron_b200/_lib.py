@@ -21,6 +21,7 @@ class MlpLayout(C.Structure):
         ("in_pad", C.c_int32 * MAX_LIN), ("out_pad", C.c_int32 * MAX_LIN),
         ("off_w", C.c_int64 * MAX_LIN), ("off_wt", C.c_int64 * MAX_LIN), ("off_b", C.c_int64 * MAX_LIN),
         ("packed_floats", C.c_int64),
+        ("off_h16", C.c_int64 * MAX_LIN), ("packed_total_floats", C.c_int64),
     ]
 
 

@@ -3,6 +3,8 @@
 // both as W [out_pad][in_pad] and transposed W^T [in_pad][out_pad] into the packed buffer (pads stay
 // zero), so every GEMM of the path is a K-major x K-major ("NT") product.  The unfold is the chain rule
 //   dg = sum_k dW * v/||v||,   dv = (g/||v||) * (dW - dg * v/||v||).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ironb {
@@ -43,10 +45,18 @@ __global__ void __launch_bounds__(256) fold_kernel(ironb_mlp_layout L, FoldArgs 
   }
   float* W = packed + L.off_w[l] + (int64_t)n * Kp;
   float* WT = packed + L.off_wt[l] + n;
+  // fp16x2-split copy for the tracer's tensor cores (SDF hidden layers): hi = fp16(w), lo = fp16((w - hi) * 2^11)
+  __half* Whi = L.off_h16[l] > 0 ? reinterpret_cast<__half*>(packed + L.off_h16[l]) + (int64_t)n * Kp : nullptr;
+  __half* Wlo = Whi ? Whi + (int64_t)Np * Kp : nullptr;   // the lo block follows the hi block
   for (int k = lane; k < K; k += 32) {
     float w = v[k] * sc;
     W[k] = w;
     WT[(int64_t)k * Np] = w;
+    if (Whi) {
+      const __half h = __float2half_rn(w);
+      Whi[k] = h;
+      Wlo[k] = __float2half_rn((w - __half2float(h)) * 2048.f);
+    }
   }
   if (lane == 0) packed[L.off_b[l] + n] = A.b[l] ? A.b[l][n] : 0.f;
 }

@@ -1,8 +1,8 @@
 // Fused SDF-MLP evaluation for the batched tracer, fp16x2-split arithmetic, two row tiles in flight per cluster.
 //
-// Same decomposition as mlp_tc.cu (a cluster of C = H/128 CTAs owns 128-row tiles, CTA rank r computes output features
-// [128 r, 128 r + 128) of every hidden layer, activations are exchanged through L2), with two changes that roughly
-// triple its throughput:
+// Decomposition: a cluster of C = H/128 CTAs owns 128-row tiles, CTA rank r computes output features
+// [128 r, 128 r + 128) of every hidden layer, activations are exchanged through L2.  Against round 1's 3xTF32 predecessor
+// (mlp_tc.cu, retired in round 2) two changes roughly triple the throughput:
 //
 //   * ARITHMETIC.  Every fp32 operand x is split into hi = fp16_rn(x) and lo = fp16_rn((x - hi) * 2^11): two 11-bit
 //     mantissas, the same 22 significant bits as the 3xTF32 split, but as 16-bit operands.  Three
@@ -453,25 +453,13 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
   }
 }
 
-// fp32 -> fp16 hi / scaled lo copies (weights: once per trace call)
-__global__ void __launch_bounds__(256) split_array_h_kernel(const float* __restrict__ src, int64_t n, __half* __restrict__ hi,
-                                                            __half* __restrict__ lo) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  __half h, l;
-  split_h(src[i], h, l);
-  hi[i] = h;
-  lo[i] = l;
-}
-
 }  // namespace mlp16
 
+long long* g_mlp_dbg = nullptr;   // optional clock64 stamp buffer (ironb_debug_mlp_timeline), shared with gemm_tc.cuh
 
-int split_weights_h(const float* src, int64_t n, void* hi, void* lo, cudaStream_t st) {
-  mlp16::split_array_h_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(src, n, reinterpret_cast<__half*>(hi),
-                                                                           reinterpret_cast<__half*>(lo));
-  IRONB_CHECK_LAUNCH("split_array_h_kernel");
-  return IRONB_OK;
+bool trace_mlp_fused_supported(const ironb_mlp_layout* lay) {
+  const int H = lay->d_hidden, C = H / 128;
+  return H % 128 == 0 && (C == 1 || C == 2 || C == 4) && lay->n_lin - 1 <= mlp16::MAXH && lay->n_lin >= 2;
 }
 
 // The tensor core adds into its TMEM accumulator with TRUNCATION (measured: tests/probe_precision.py, probe_mlp_h16.py --
@@ -574,3 +562,14 @@ int launch_trace_mlp_h16(const ironb_mlp_layout* lay, const float* packed, const
 }  // namespace ironb
 
 extern "C" float ironb_set_mlp_debias(float g) { return ironb::mlp16_set_debias(g); }
+
+// debugging aid: IRONB_MLP_DBG timeline of the fused MLP kernel (cluster 0, rank 0, first tile), 8 stamps per layer
+extern "C" int ironb_debug_mlp_timeline(long long* host_out, int n) {
+  if (ironb::g_mlp_dbg == nullptr) {
+    if (cudaMalloc(&ironb::g_mlp_dbg, 64 * 8 * sizeof(long long)) != cudaSuccess) return -1;
+    cudaMemset(ironb::g_mlp_dbg, 0, 64 * 8 * sizeof(long long));
+    return 0;
+  }
+  if (host_out && n > 0) cudaMemcpy(host_out, ironb::g_mlp_dbg, (size_t)(n < 512 ? n : 512) * sizeof(long long), cudaMemcpyDeviceToHost);
+  return 1;
+}

@@ -25,12 +25,7 @@
 namespace ironb {
 
 bool trace_mlp_fused_supported(const ironb_mlp_layout* lay);
-int split_weights(const float* src, int64_t n, float* hi, float* lo, cudaStream_t st);
-int launch_trace_mlp_fused(const ironb_mlp_layout* lay, const float* packed, const CUtensorMap* mE, const CUtensorMap* mU,
-                           const CUtensorMap* mW, const float* Ehi, const float* Elo, float* const* Uhi, float* const* Ulo,
-                           float* Fpart, int rows_cap, int cap, const int* m_dev, int m_mul, cudaStream_t st);
-// fp16x2-split version (mlp_h16.cu): operands are fp16 hi and fp16 (x - hi) * 2^11
-int split_weights_h(const float* src, int64_t n, void* hi, void* lo, cudaStream_t st);
+// the fused MLP evaluation (mlp_h16.cu): operands are fp16 hi and fp16 (x - hi) * 2^11
 int launch_trace_mlp_h16(const ironb_mlp_layout* lay, const float* packed, const CUtensorMap* mE, const CUtensorMap* mU,
                          const CUtensorMap* mW, const void* Ehi, const void* Elo, void* const* Uhi, void* const* Ulo,
                          float* Fpart, int rows_cap, int cap, const int* m_dev, int m_mul, cudaStream_t st);
@@ -58,8 +53,8 @@ struct BArgs {
   int* unf_list; float *smin, *smax, *prev_f, *prev_t;   // per unfinished ray
   int* glist[2];                // sampler group -> unfinished-ray index
   int* root_ray; float *root_lo, *root_hi, *root_mid; int* root_work;
-  float* Ehi; float* Elo;       // [CAP][Epad] encoded points, already split into hi / lo (the MLP's A operand):
-  int f16;                      // 0: tf32-exact fp32 pairs (mlp_tc.cu); 1: fp16 hi and fp16 (x - hi) * 2^11 (mlp_h16.cu)
+  float* Ehi; float* Elo;       // [CAP][Epad] encoded points, already split (the MLP's A operand): fp16 hi and
+                                // fp16 (x - hi) * 2^11 (mlp_h16.cu)
   const float* Fpart;           // [nparts][cap] partial sums of the sdf row, written by the fused MLP kernel
   const float* b_last;
   int nparts, cap;
@@ -72,18 +67,10 @@ constexpr int C_SG = 8;      // 8..10 rotating group counts (sampler)
 constexpr int C_BR = 16;     // 16.. row count of bisection round j (0 = nobody works any more)
 constexpr int NCOUNTERS = 64;
 
-template <bool F16>
-__device__ __forceinline__ void put_split(float* __restrict__ ehi, float* __restrict__ elo, int i, float v) {
-  if (F16) {
-    const __half h = __float2half_rn(v);
-    reinterpret_cast<__half*>(ehi)[i] = h;
-    reinterpret_cast<__half*>(elo)[i] = __float2half_rn((v - __half2float(h)) * 2048.f);
-  } else {
-    float h, l;
-    tc::split1(v, h, l);
-    ehi[i] = h;
-    elo[i] = l;
-  }
+__device__ __forceinline__ void put_split(__half* __restrict__ ehi, __half* __restrict__ elo, int i, float v) {
+  const __half h = __float2half_rn(v);
+  ehi[i] = h;
+  elo[i] = __float2half_rn((v - __half2float(h)) * 2048.f);
 }
 struct BArgs;
 __device__ __forceinline__ void write_pe(const BArgs& A, size_t row, const float x[3], int part);
@@ -96,15 +83,15 @@ __device__ __forceinline__ float read_f(const BArgs& A, size_t i) {
 }
 
 // encoded point of work item `row`, written as the split A operand of the MLP's first layer
-template <bool F16>
-__device__ __forceinline__ void write_pe_t(const BArgs& A, size_t row, const float x[3], int part) {
-  // row pitch: Epad elements of 4 (fp32 pairs) or 2 (fp16 pairs) bytes
-  float* __restrict__ ehi = F16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(A.Ehi) + row * A.Epad) : A.Ehi + row * A.Epad;
-  float* __restrict__ elo = F16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(A.Elo) + row * A.Epad) : A.Elo + row * A.Epad;
+// part < 0: the whole encoding by one thread; part in [0, 8): thread `part` of the 8 that share a work item writes
+// frequency `part` (part == multires: the raw coordinates + padding), so the dependent sincos chain per thread is 3 long
+__device__ __forceinline__ void write_pe(const BArgs& A, size_t row, const float x[3], int part = -1) {
+  __half* __restrict__ ehi = reinterpret_cast<__half*>(A.Ehi) + row * A.Epad;     // row pitch: Epad halfs
+  __half* __restrict__ elo = reinterpret_cast<__half*>(A.Elo) + row * A.Epad;
   const float xs[3] = {x[0] * A.scale, x[1] * A.scale, x[2] * A.scale};
   if (part < 0 || part == A.multires) {                 // the raw coordinates and the zero padding
-    put_split<F16>(ehi, elo, 0, xs[0]); put_split<F16>(ehi, elo, 1, xs[1]); put_split<F16>(ehi, elo, 2, xs[2]);
-    for (int w = 3 + 6 * A.multires; w < A.Epad; ++w) put_split<F16>(ehi, elo, w, 0.f);
+    put_split(ehi, elo, 0, xs[0]); put_split(ehi, elo, 1, xs[1]); put_split(ehi, elo, 2, xs[2]);
+    for (int w = 3 + 6 * A.multires; w < A.Epad; ++w) put_split(ehi, elo, w, 0.f);
   }
   const int k0 = part < 0 ? 0 : part, k1 = part < 0 ? A.multires : min(part + 1, A.multires);
   for (int k = k0; k < k1; ++k) {                       // frequency 2^k: sin block then cos block (embedder.py:25-33)
@@ -114,16 +101,10 @@ __device__ __forceinline__ void write_pe_t(const BArgs& A, size_t row, const flo
     for (int c = 0; c < 3; ++c) {
       float sn, co;
       sincosf(xs[c] * f, &sn, &co);
-      put_split<F16>(ehi, elo, w + c, sn);
-      put_split<F16>(ehi, elo, w + 3 + c, co);
+      put_split(ehi, elo, w + c, sn);
+      put_split(ehi, elo, w + 3 + c, co);
     }
   }
-}
-// part < 0: the whole encoding by one thread; part in [0, 8): thread `part` of the 8 that share a work item writes
-// frequency `part` (part == multires: the raw coordinates + padding), so the dependent sincos chain per thread is 3 long
-__device__ __forceinline__ void write_pe(const BArgs& A, size_t row, const float x[3], int part = -1) {
-  if (A.f16) write_pe_t<true>(A, row, x, part);
-  else write_pe_t<false>(A, row, x, part);
 }
 __device__ __forceinline__ void ray_point(const BArgs& A, int r, float t, float x[3]) {
 #pragma unroll
@@ -333,7 +314,7 @@ __global__ void __launch_bounds__(256) bis_final_kernel(BArgs A) {
 struct BWs {
   int* c; float* t; int* k; int* flags; float* x; int* list[2]; int* unf_list; float *smin, *smax, *prev_f, *prev_t;
   int* glist[2]; int* root_ray; float *root_lo, *root_hi, *root_mid; int* root_work;
-  float *Ehi, *Elo, *Uhi[2], *Ulo[2], *Fpart, *Whi[IRONB_MAX_LIN], *Wlo[IRONB_MAX_LIN];
+  float *Ehi, *Elo, *Uhi[2], *Ulo[2], *Fpart;
   int64_t cap; int64_t bytes;
 };
 
@@ -360,10 +341,6 @@ BWs carve_b(const ironb_mlp_layout* lay, int64_t N, unsigned char* base) {
   w.Ehi = (float*)take(cap * Epad * 4); w.Elo = (float*)take(cap * Epad * 4);
   w.Fpart = (float*)take(cap * 4 * 16);
   for (int b = 0; b < 2; ++b) { w.Uhi[b] = (float*)take(cap * (int64_t)H * 4); w.Ulo[b] = (float*)take(cap * (int64_t)H * 4); }
-  for (int l = 0; l < last; ++l) {
-    int64_t n = (int64_t)lay->out_pad[l] * lay->in_pad[l];
-    w.Whi[l] = (float*)take(n * 4); w.Wlo[l] = (float*)take(n * 4);
-  }
   w.bytes = off;
   return w;
 }
@@ -376,15 +353,15 @@ int trace_mode() {
   int m = g_trace_mode.load(std::memory_order_relaxed);
   if (m < 0) {
     const char* e = getenv("IRONB_TRACE");
-    // IRONB_TRACE=fused: fp32 FFMA tracer; =tf32: batched tcgen05 3xTF32; default: batched tcgen05 fp16x2 split
-    m = (e && (e[0] == 'f' || e[0] == 'F' || e[0] == '0')) ? 0 : (e && (e[0] == 't' || e[0] == 'T' || e[0] == '1')) ? 1 : 2;
+    // IRONB_TRACE=fused: fp32 FFMA tracer; default: batched tcgen05 tracer, fp16x2-split operands
+    m = (e && (e[0] == 'f' || e[0] == 'F' || e[0] == '0')) ? 0 : 2;
     g_trace_mode.store(m, std::memory_order_relaxed);
   }
   return m;
 }
 int set_trace_mode(int mode) {
   int prev = trace_mode();
-  g_trace_mode.store(mode <= 0 ? 0 : (mode == 1 ? 1 : 2), std::memory_order_relaxed);
+  g_trace_mode.store(mode <= 0 ? 0 : 2, std::memory_order_relaxed);   // 1 (the retired 3xTF32 tracer) means 2
   return prev;
 }
 
@@ -421,23 +398,18 @@ int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float*
   A.unf_list = w.unf_list; A.smin = w.smin; A.smax = w.smax; A.prev_f = w.prev_f; A.prev_t = w.prev_t;
   A.glist[0] = w.glist[0]; A.glist[1] = w.glist[1];
   A.root_ray = w.root_ray; A.root_lo = w.root_lo; A.root_hi = w.root_hi; A.root_mid = w.root_mid; A.root_work = w.root_work;
-  const bool f16 = trace_mode() == 2;
-  A.Ehi = w.Ehi; A.Elo = w.Elo; A.f16 = f16 ? 1 : 0;
+  A.Ehi = w.Ehi; A.Elo = w.Elo;
   A.cap_groups = (int)(w.cap / 32);
   const int C = H / 128;
   A.Fpart = w.Fpart; A.b_last = packed + lay->off_b[last]; A.nparts = 4 * C; A.cap = (int)w.cap;
 
-  // weights -> tf32-exact hi / lo copies (once per call), then the tensor maps: operands are fixed for the whole call
+  // The fp16x2-split weight copies come with the packed buffer (ironb_mlp_fold writes them once per parameter update;
+  // round 1 re-split all hidden layers on every tracer call: 8 launches).  Tensor maps: operands are fixed for the call.
   int rc;
-  for (int l = 0; l < last; ++l) {
-    const int64_t n = (int64_t)lay->out_pad[l] * lay->in_pad[l];
-    if ((rc = f16 ? split_weights_h(packed + lay->off_w[l], n, w.Whi[l], w.Wlo[l], st)
-                  : split_weights(packed + lay->off_w[l], n, w.Whi[l], w.Wlo[l], st))) return rc;
-  }
+  for (int l = 0; l < last; ++l)
+    if (lay->off_h16[l] <= 0) { set_error("trace: the layout carries no fp16 weight copies (layer %d)", l); return IRONB_EINVAL; }
   CUtensorMap mE[2], mU[4], mW[2 * IRONB_MAX_LIN];
-  auto mk = [&](CUtensorMap* m, const float* p, int rows, int K, int ld) -> int {   // same buffers, element type per mode
-    return f16 ? tc::make_map_h(m, p, rows, K, ld) : tc::make_map(m, p, rows, K, ld);
-  };
+  auto mk = [&](CUtensorMap* m, const void* p, int rows, int K, int ld) -> int { return tc::make_map_h(m, p, rows, K, ld); };
   if ((rc = mk(&mE[0], w.Ehi, (int)w.cap, Epad, Epad))) return rc;
   if ((rc = mk(&mE[1], w.Elo, (int)w.cap, Epad, Epad))) return rc;
   for (int b = 0; b < 2; ++b) {
@@ -445,18 +417,17 @@ int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float*
     if ((rc = mk(&mU[b * 2 + 1], w.Ulo[b], (int)w.cap, H, H))) return rc;
   }
   for (int l = 0; l < last; ++l) {
-    if ((rc = mk(&mW[l * 2], w.Whi[l], lay->out_pad[l], lay->in_pad[l], lay->in_pad[l]))) return rc;
-    if ((rc = mk(&mW[l * 2 + 1], w.Wlo[l], lay->out_pad[l], lay->in_pad[l], lay->in_pad[l]))) return rc;
+    const __half* whi = reinterpret_cast<const __half*>(packed + lay->off_h16[l]);
+    const __half* wlo = whi + (int64_t)lay->out_pad[l] * lay->in_pad[l];
+    if ((rc = mk(&mW[l * 2], whi, lay->out_pad[l], lay->in_pad[l], lay->in_pad[l]))) return rc;
+    if ((rc = mk(&mW[l * 2 + 1], wlo, lay->out_pad[l], lay->in_pad[l], lay->in_pad[l]))) return rc;
   }
   // one MLP evaluation of the first (*m_dev x m_mul) rows: all hidden layers + the sdf row in one cluster launch
-  // (mlp_h16.cu: fp16x2 split, two tiles in flight; mlp_tc.cu: 3xTF32)
+  // (mlp_h16.cu: fp16x2 split, two tiles in flight)
   auto mlp = [&](int rows_cap, const int* m_dev, int m_mul) -> int {
-    if (f16) {
-      void* uh[2] = {w.Uhi[0], w.Uhi[1]};
-      void* ul[2] = {w.Ulo[0], w.Ulo[1]};
-      return launch_trace_mlp_h16(lay, packed, mE, mU, mW, w.Ehi, w.Elo, uh, ul, w.Fpart, rows_cap, (int)w.cap, m_dev, m_mul, st);
-    }
-    return launch_trace_mlp_fused(lay, packed, mE, mU, mW, w.Ehi, w.Elo, w.Uhi, w.Ulo, w.Fpart, rows_cap, (int)w.cap, m_dev, m_mul, st);
+    void* uh[2] = {w.Uhi[0], w.Uhi[1]};
+    void* ul[2] = {w.Ulo[0], w.Ulo[1]};
+    return launch_trace_mlp_h16(lay, packed, mE, mU, mW, w.Ehi, w.Elo, uh, ul, w.Fpart, rows_cap, (int)w.cap, m_dev, m_mul, st);
   };
   const int nb = (int)ceil_div64(N * PE_T, 256);    // st_* / bis_* kernels: PE_T threads per work item
   const int nb1 = (int)ceil_div64(N, 256);

@@ -91,7 +91,7 @@ class _FoldedMLP(nn.Module):
                 raise RuntimeError("iron_b200: parameters must be contiguous")
         buf = getattr(self, "_fold_buf", None)
         if buf is None or buf.device != dev:
-            buf = torch.zeros(int(self.layout.packed_floats), dtype=torch.float32, device=dev)
+            buf = torch.zeros(int(self.layout.packed_total_floats), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(_lib.load().ironb_mlp_fold(C.byref(self.layout), _lib.ptr_array(v), _lib.ptr_array(g),
                                                   _lib.ptr_array(b), _lib.ptr(buf), _lib.stream()), "mlp_fold")

@@ -912,6 +912,105 @@ def stage2_step(sdf_p: Params, nets: Dict[str, Params], light: Tensor, cam: OCam
     return loss.detach(), res
 
 
+# --------------------------------------------------------------------------
+# patch losses (row f-3)                   models/image_losses.py:13-158, render_surface.py:594-613
+# --------------------------------------------------------------------------
+
+_GAUSS7 = None
+
+
+def gauss7() -> Tensor:
+    """The 7x7 kernel of PyramidL2Loss (models/image_losses.py:17-20): scipy.ndimage.gaussian_filter(dirac 7x7, sigma=1)
+    = the outer product of the 1-D sigma-1 Gaussian truncated at 4 sigma (radius 4) and normalised, applied to a 7-wide
+    dirac with scipy's default 'reflect' border.  Restated without scipy: w[d], d = -4..4; the 7-sample response at offset
+    i from the centre collects w[i] plus the taps reflected at the array ends (half-sample symmetric)."""
+    global _GAUSS7
+    if _GAUSS7 is None:
+        r = 4
+        x = np.arange(-r, r + 1, dtype=np.float64)
+        w = np.exp(-0.5 * x * x)
+        w /= w.sum()
+        out = np.zeros(7, dtype=np.float64)
+        for j in range(7):                       # output sample j, dirac at index 3
+            for d in range(-r, r + 1):
+                i = j + d                        # input index read by tap d, reflected into [0, 6] (d c b a | a b c d)
+                while i < 0 or i > 6:
+                    i = -i - 1 if i < 0 else 2 * 7 - 1 - i
+                if i == 3:
+                    out[j] += w[d + r]
+        g1 = out.astype(np.float64)
+        _GAUSS7 = torch.from_numpy(np.outer(g1, g1).astype(np.float32))
+    return _GAUSS7
+
+
+def pyramid_l2_loss(pred: Tensor, trgt: Tensor) -> Tensor:
+    """PyramidL2Loss.forward, models/image_losses.py:29-48.  pred, trgt: [B, 3, H, W]."""
+    C = pred.shape[1]
+    f = torch.zeros(C, C, 7, 7, dtype=pred.dtype, device=pred.device)
+    g = gauss7().to(pred.device, pred.dtype)
+    for c in range(C):
+        f[c, c] = g
+    h, w = pred.shape[-2:]
+    d = pred - trgt
+    loss = d.pow(2).sum() / (h * w)
+    for k in range(1, 5):
+        d = torch.nn.functional.avg_pool2d(torch.nn.functional.conv2d(d, f, padding=3), 2)
+        loss = loss + d.pow(2).sum() / ((h / 2.0 ** k) * (w / 2.0 ** k))
+    return loss
+
+
+def erode_mask(mask: Tensor, k: int) -> Tensor:
+    """kornia.morphology.erosion(mask.float(), ones(k, k)) > 0.5 restated (models/image_losses.py:154): flat k x k erosion
+    with kornia's default 'geodesic' border (pixels outside the image never lose).  kornia is not installable here; pinned
+    against cv2.erode (default border) in tests/golden/morph_cv2.npz."""
+    x = mask.float()
+    return (-torch.nn.functional.max_pool2d(-x, k, stride=1, padding=k // 2)) > 0.5
+
+
+def ssim_loss(X: Tensor, Y: Tensor, mask: Optional[Tensor] = None, data_range: float = 1.0, win_size: int = 11,
+              win_sigma: float = 1.5, K=(0.01, 0.03)) -> Tensor:
+    """ssim_loss_fn, models/image_losses.py:97-158.  X, Y: [B, C, H, W]; mask: [B, 1, H, W] bool.  Valid (unpadded)
+    separable Gaussian filtering; with a mask the map is padded back with 1.0 and averaged over the ERODED mask."""
+    coords = torch.arange(win_size, dtype=torch.float, device=X.device) - win_size // 2
+    g = torch.exp(-(coords ** 2) / (2 * win_sigma ** 2))
+    g = g / g.sum()
+    C = X.shape[1]
+    wy = g.reshape(1, 1, win_size, 1).repeat(C, 1, 1, 1)
+    wx = g.reshape(1, 1, 1, win_size).repeat(C, 1, 1, 1)
+
+    def filt(t):
+        out = t
+        if t.shape[2] >= win_size:
+            out = torch.nn.functional.conv2d(out, wy, groups=C)
+        if t.shape[3] >= win_size:
+            out = torch.nn.functional.conv2d(out, wx, groups=C)
+        return out
+
+    C1, C2 = (K[0] * data_range) ** 2, (K[1] * data_range) ** 2
+    mu1, mu2 = filt(X), filt(Y)
+    mu1_sq, mu2_sq, mu12 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    s1 = filt(X * X) - mu1_sq
+    s2 = filt(Y * Y) - mu2_sq
+    s12 = filt(X * Y) - mu12
+    cs = (2 * s12 + C2) / (s1 + s2 + C2)
+    m = ((2 * mu12 + C1) / (mu1_sq + mu2_sq + C1)) * cs
+    m = m.mean(dim=1, keepdim=True)
+    if mask is not None:
+        r = win_size // 2
+        m = torch.nn.functional.pad(m, (r, r, r, r), mode="constant", value=1.0)
+        m = m[erode_mask(mask, win_size)]
+    return 1.0 - m.mean()
+
+
+def roughrange_loss(roughness: Tensor, mask: Tensor, weight: float = 0.1, value: float = 0.5) -> Tensor:
+    """render_surface.py:609-613: mean excess of the hit pixels' roughness over 0.5, times the weight (0 if none)."""
+    r = roughness[mask]
+    r = r[r > value]
+    if r.numel() > 0:
+        return (r - value).mean() * weight
+    return torch.zeros((), dtype=roughness.dtype, device=roughness.device)
+
+
 # ---------------------------------------------------------------------------------------------- optimiser (SURVEY 8f-3)
 def adam_step(p, g, m, v, t, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0):
     """One Adam update of one tensor, restated from torch/optim/adam.py::_single_tensor_adam (amsgrad=False, maximize=False),

@@ -26,7 +26,7 @@ ap.add_argument("--timeline-only", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 lib = _lib.load()
-MODES = ((0, "ffma"), (1, "3xTF32"), (2, "fp16x2"))
+MODES = ((0, "ffma"), (2, "fp16x2"))
 print("IRONB_MLP_NHH =", os.environ.get("IRONB_MLP_NHH", "1"))
 
 
