@@ -218,6 +218,24 @@ typedef struct {
 int ironb_adam_step(const ironb_adam_tensor* tensors_dev, int n_tensors, int64_t max_numel, double beta1, double beta2,
                     double eps, int* step_dev, void* stream);
 
+/* ---------------------------------------------------------------- patch losses
+ * One [C][H][W] image pair (C <= 4), addressed through ELEMENT strides {channel, row, column}, so the [1,3,H,W] view of
+ * the renderer's [H,W,3] buffer is read in place.  Value and gradient w.r.t. the first image in one call; `ws` from
+ * ironb_patch_loss_workspace_bytes (one per call in flight).  No host read-back: capturable into a CUDA graph.
+ *
+ * ironb_pyramid_l2: PyramidL2Loss.forward, models/image_losses.py:29-48 (7x7 sigma-1 Gaussian, 2x average pooling, five
+ * levels; H, W >= 16).  *loss is ACCUMULATED (the caller zeroes it).  grad may be NULL.
+ * ironb_ssim_loss: ssim_loss_fn, models/image_losses.py:97-158 (11-tap sigma-1.5 separable window without padding,
+ * channel mean, padded back with 1.0, mean over the 11x11-eroded mask; mask: H*W bytes or NULL = unmasked mean of the
+ * unpadded map).  *loss is WRITTEN.  grad may be NULL. */
+int64_t ironb_patch_loss_workspace_bytes(int C, int H, int W);
+int ironb_pyramid_l2(const float* pred, const int64_t* pred_strides, const float* trgt, const int64_t* trgt_strides, int C,
+                     int H, int W, float* loss, float* grad, const int64_t* grad_strides, void* ws, int64_t ws_bytes,
+                     void* stream);
+int ironb_ssim_loss(const float* X, const int64_t* x_strides, const float* Y, const int64_t* y_strides, const uint8_t* mask,
+                    int C, int H, int W, float data_range, int win_size, float win_sigma, float K1, float K2, float* loss,
+                    float* grad, const int64_t* grad_strides, void* ws, int64_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,11 +11,13 @@ from .renderer_ggx import GGXColocatedRenderer
 from .rendering_func import get_materials
 from .embedder import get_embedder
 from .optim import FusedAdam
+from .image_losses import PyramidL2Loss, ssim_loss_fn
 from .step import GraphedStage2Step, stage2_step
 
 __all__ = [
     "SDFNetwork", "RenderingNetwork", "PointLightNetwork", "GGXColocatedRenderer", "RayTracer", "Camera",
     "intersect_sphere", "raytrace_pixels", "raytrace_camera", "render_camera", "render_normal_and_color",
     "reparam_points", "locate_edge_points", "render_edge_pixels", "get_materials", "get_embedder", "make_render_fn", "stage2_step", "GraphedStage2Step", "FusedAdam",
+    "PyramidL2Loss", "ssim_loss_fn",
     "init_sdf_network_dict", "init_rendering_network_dict", "choose_renderer",
 ]

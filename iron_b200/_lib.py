@@ -39,6 +39,7 @@ _F = C.c_float
 _LAY = C.POINTER(MlpLayout)
 _CFG = C.POINTER(MatnetCfg)
 _PP = C.POINTER(C.c_void_p)
+_PI64 = C.POINTER(C.c_int64)
 
 _PROTOS = {
     "ironb_last_error": (C.c_char_p, []),
@@ -73,6 +74,9 @@ _PROTOS = {
     "ironb_adam_step": (_INT, [_P, _INT, _I64, C.c_double, C.c_double, C.c_double, _P, _P]),
     "ironb_depth_closing": (_INT, [_P, _INT, _INT, _P, _P, _P]),
     "ironb_sobel_depth": (_INT, [_P, _INT, _INT, _P, _P]),
+    "ironb_patch_loss_workspace_bytes": (_I64, [_INT, _INT, _INT]),
+    "ironb_pyramid_l2": (_INT, [_P, _PI64, _P, _PI64, _INT, _INT, _INT, _P, _P, _PI64, _P, _I64, _P]),
+    "ironb_ssim_loss": (_INT, [_P, _PI64, _P, _PI64, _P, _INT, _INT, _INT, _F, _INT, _F, _F, _F, _P, _P, _PI64, _P, _I64, _P]),
 }
 
 EXPORTS = tuple(_PROTOS)

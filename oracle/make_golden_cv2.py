@@ -8,6 +8,8 @@ ironb_depth_closing / ironb_sobel_depth) against an INDEPENDENT implementation, 
     sobel    = sqrt(gx^2 + gy^2 + 1e-6), gx/gy = cv2.Sobel(depth, CV_32F, 1/0, 0/1, ksize=3, scale=1/8, BORDER_REPLICATE)
                (kornia.filters.sobel: normalized=True divides the 3x3 kernels by 8, replicate padding, eps=1e-6)
 
+    erosion  = cv2.erode(mask, ones(11,11))   (kornia.morphology.erosion of the SSIM mask, models/image_losses.py:154)
+
     python oracle/make_golden_cv2.py        -> tests/golden/morph_cv2.npz   (TEST INFRASTRUCTURE ONLY)
 """
 import os
@@ -47,6 +49,20 @@ def main():
         data[f"depth{i}"] = d
         data[f"closing{i}"] = closed.reshape(d.shape).astype(np.float32)
         data[f"sobel{i}"] = np.sqrt(gx.astype(np.float32) ** 2 + gy.astype(np.float32) ** 2 + np.float32(1e-6)).reshape(d.shape)
+    # kornia.morphology.erosion(mask, ones(11, 11)) of ssim_loss_fn (models/image_losses.py:154): cv2.erode, default border
+    k11 = np.ones((11, 11), np.uint8)
+    rng = np.random.default_rng(9)
+    masks = []
+    for (h, w) in [(64, 64), (37, 53), (16, 16), (9, 30), (128, 128)]:
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        m = ((xx - 0.55 * w) ** 2 / (0.42 * w) ** 2 + (yy - 0.5 * h) ** 2 / (0.46 * h) ** 2) < 1.0
+        m &= ~(rng.random((h, w)) < 0.004)
+        masks.append(m)
+    masks.append(np.ones((32, 32), bool))
+    for i, m in enumerate(masks):
+        data[f"mask{i}"] = m
+        data[f"erode11_{i}"] = cv2.erode(m.astype(np.uint8), k11).reshape(m.shape).astype(bool)
+    data["n_masks"] = np.int64(len(masks))
     data["n"] = np.int64(len(depth_images()))
     data["cv2_version"] = np.array(cv2.__version__)
     path = os.path.join(ROOT, "tests", "golden", "morph_cv2.npz")

@@ -264,3 +264,31 @@ def test_closing_and_sobel_restatements_match_opencv(golden):
         d = torch.from_numpy(g[f"depth{i}"])
         assert np.array_equal(O.morph_closing3(d).numpy(), g[f"closing{i}"]), f"closing, image {i}"
         assert np.abs(O.sobel_magnitude(d).numpy() - g[f"sobel{i}"]).max() <= 5e-7, f"sobel, image {i}"
+
+
+def test_erosion_restatement_matches_opencv(golden):
+    """kornia.morphology.erosion(mask, ones(11, 11)) of ssim_loss_fn (models/image_losses.py:154) restated by
+    oracle.erode_mask, against cv2.erode (default border: outside pixels never lose) -- bit-exact."""
+    g = golden("morph_cv2")
+    for i in range(int(g["n_masks"])):
+        m = torch.from_numpy(g[f"mask{i}"])[None, None]
+        assert np.array_equal(O.erode_mask(m, 11)[0, 0].numpy(), g[f"erode11_{i}"]), f"mask {i}"
+
+
+def test_patch_losses_match_the_reference(golden):
+    """PyramidL2Loss / ssim_loss_fn (models/image_losses.py:13-158) restated by the oracle, against values and gradients the
+    real reference module produced (oracle/make_golden_losses.py), including odd sizes, a masked and an unmasked SSIM."""
+    g = golden("losses")
+    close(O.gauss7().numpy(), g["gauss7"], 1e-8)
+    for c in [str(x) for x in g["cases"]]:
+        pred = T(g[f"{c}.pred"]).requires_grad_(True)
+        gt = T(g[f"{c}.gt"])
+        mask = T(g[f"{c}.mask"]) if f"{c}.mask" in g else None
+        lp = O.pyramid_l2_loss(pred, gt)
+        gp, = torch.autograd.grad(lp, pred)
+        assert abs(float(lp) - float(g[f"{c}.pyr"])) <= 2e-6 * abs(float(g[f"{c}.pyr"])), c
+        close(gp.numpy(), g[f"{c}.pyr_grad"], 1e-8, 1e-5)
+        ls = O.ssim_loss(pred, gt, mask)
+        gs, = torch.autograd.grad(ls, pred)
+        assert abs(float(ls) - float(g[f"{c}.ssim"])) <= 2e-6, c
+        close(gs.numpy(), g[f"{c}.ssim_grad"], 2e-8, 1e-4)
