@@ -145,6 +145,9 @@ def oracle_setup(hidden: int, patch: int, rank: int = 0, device=None):
     return O, sdf, mats, light, cam, target, eik
 
 
+IMAGE_LOSS = ["reference"]     # set from --loss: "reference" = PyramidL2 + SSIM + roughness range (what the reference trains with)
+
+
 def oracle_step(state):
     """One oracle step; returns (seconds, loss).  On a CUDA state the time is the host wall time around a synchronised
     step (cuda_eager_baseline additionally takes CUDA events)."""
@@ -160,10 +163,10 @@ def oracle_step(state):
     t0 = time.perf_counter()
     if cuda:
         with torch.device(light.device):       # the oracle's factory calls (linspace, zeros ...) follow its inputs
-            loss, _ = O.stage2_step(sdf, mats, light, cam, target, eik.clone())
+            loss, _ = O.stage2_step(sdf, mats, light, cam, target, eik.clone(), image_loss=IMAGE_LOSS[0])
         torch.cuda.synchronize()
     else:
-        loss, _ = O.stage2_step(sdf, mats, light, cam, target, eik.clone())
+        loss, _ = O.stage2_step(sdf, mats, light, cam, target, eik.clone(), image_loss=IMAGE_LOSS[0])
     return time.perf_counter() - t0, float(loss)
 
 
@@ -304,9 +307,12 @@ def workload_config(args, patch):
                         f"colocated-flash fixture view, trace+shade+loss+backward",
             "sdf_mlp": f"8x{args.hidden}, PE L=6, skip@4, softplus(100), weight-norm", "material_mlps": "3 x (4x256, ReLU)",
             "rays_per_gpu": patch * patch, "eikonal_points": patch * patch // 2,
-            "sharding": "every rank traces/shades its own copy of the same crop (identical work per GPU), own target/eikonal seeds", "parallelism": f"dp{args.gpus} (rays sharded, weights replicated)",
+            "sharding": "every rank traces/shades its own crop of the view (rank 0: the centre crop, the others tile around it), own target/eikonal seeds", "parallelism": f"dp{args.gpus} (rays sharded, weights replicated)",
             "l2": "256 MiB flush between steps, outside the per-step CUDA-event pairs",
             "init": "seed-0 geometric init, light=32",
+            "loss": ("PyramidL2 + 1.0 * SSIM(masked) + 0.1 * roughness range + 0.1 * eikonal: the reference's training loss, "
+                     "render_surface.py:594-639" if getattr(args, "loss", "reference") == "reference"
+                     else "plain L2 on the patch + 0.1 * eikonal"),
             "fill_holes_and_edge_sampling": bool(getattr(args, "driver_defaults", False)),
             "execution": ("one CUDA-graph replay per step (iron_b200.GraphedStage2Step)" if getattr(args, "exec_mode", "graph") == "graph"
                           and getattr(args, "shading", "dense") == "dense" and not getattr(args, "driver_defaults", False)
@@ -377,7 +383,10 @@ def run_ours(args):
     tracer.collect_stats = True
     K_h = torch.tensor(O.FIXTURE_K, dtype=torch.float64).reshape(4, 4).float().pin_memory()
     W2C_h = torch.tensor(O.FIXTURE_W2C, dtype=torch.float64).reshape(4, 4).float().pin_memory()
-    ul = crop_corner(0, S)     # weak scaling: every rank does the SAME amount of work (the canonical centre crop)
+    # weak scaling over patches: every rank traces and shades ITS OWN crop of the view (rank 0 = the canonical
+    # centre crop, the others tile around it: parallel.crop_for_rank), so the ranks' work differs like it does in training;
+    # the per-rank step times are reported next to the max that defines `value`
+    ul = crop_corner(rank, S) if not os.environ.get("IRONB_BENCH_SAME_CROP") else crop_corner(0, S)
     target_h = (torch.rand(S, S, 3, generator=torch.Generator().manual_seed(11 + rank)) * 0.5).pin_memory()
     eik_h = torch.empty(S * S // 2, 3).uniform_(-1.0, 1.0, generator=torch.Generator().manual_seed(12 + rank)).pin_memory()
 
@@ -400,7 +409,7 @@ def run_ours(args):
     if use_graph:
         tracer.collect_stats = os.environ.get("IRONB_BENCH_STATS", "1") != "0"
         gs = ib.GraphedStage2Step(sdf, nets, tracer, render_fn, K_h, W2C_h, (S, S), S * S // 2, crop_ul=ul,
-                                  time_tracer=os.environ.get("IRONB_BENCH_TIME_TRACER", "1") != "0")
+                                  time_tracer=os.environ.get("IRONB_BENCH_TIME_TRACER", "1") != "0", image_loss=args.loss)
         stage("graph captured")
         gs.step(target=target_h, eik_points=eik_h)
         torch.cuda.synchronize()
@@ -427,7 +436,8 @@ def run_ours(args):
                 return r
             tracer.forward = timed
         loss, res = ib.stage2_step(sdf, nets, tracer, render_fn, cam_, target_, eik_, fill_holes=args.driver_defaults,
-                                   handle_edges=args.driver_defaults, dense_shading=(args.shading == "dense"))
+                                   handle_edges=args.driver_defaults, dense_shading=(args.shading == "dense"),
+                                   image_loss=args.loss)
         if time_trace:
             tracer.forward = orig
             trace_ms.append(evs)
@@ -515,7 +525,11 @@ def run_ours(args):
         stats = tracer.last_stats.cpu().tolist()
     hits = int(res["convergent_mask"].sum().item())
     t = torch.tensor([my_ms], dtype=torch.float64, device=dev)
+    rank_ms = [my_ms / args.steps]
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_ms = [float(x.item()) / args.steps for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     rays_total = S * S * world * args.steps
@@ -597,6 +611,7 @@ def run_ours(args):
                        "root_rays": stats[4] / args.steps, "k_max": stats[5], "hits": hits, "rays": S * S,
                        "implementation": tracer_impl},
             "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps, "grad_params": n_params,
+            "rank_ms_per_step": [round(x, 4) for x in rank_ms], "rank_crop_ul": [list(crop_corner(r, S)) for r in range(world)],
             "loss": loss_host,
             "step_ms": [round(x, 3) for x in step_ms], "tracer_ms": [round(x, 3) for x in tr_ms],
         }
@@ -652,6 +667,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--hidden", type=int, default=512)
     ap.add_argument("--patch", type=int, default=64)
+    ap.add_argument("--loss", default="reference", choices=["reference", "l2"],
+                    help="reference: PyramidL2 + SSIM + roughness range (render_surface.py:594-613), in every arm; l2: round 1's plain L2")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--driver-defaults", action="store_true",
                     help="also run hole filling + edge sampling (the reference drivers' fill_holes=True, handle_edges=True)")
@@ -665,6 +682,7 @@ def main():
     ap.add_argument("--tracer", default="default", choices=["default", "batched", "fused"])
     ap.add_argument("--gemm", default="default", choices=["default", "tcgen05", "ffma"])
     args = ap.parse_args()
+    IMAGE_LOSS[0] = args.loss
     if args.impl == "reference":
         run_reference(args)
         return

@@ -5,13 +5,20 @@ from __future__ import annotations
 
 import torch
 
+from .image_losses import PyramidL2Loss, ssim_loss_fn
 from .raytracer import Camera, render_camera
+
+_pyramid_l2 = PyramidL2Loss()
 
 
 def stage2_step(sdf_network, color_network_dict, raytracer, render_fn, camera, target, eik_points, eik_weight=0.1,
-                max_num_rays=50000, fill_holes=False, handle_edges=False, dense_shading=False, eikonal_stream=None):
+                max_num_rays=50000, fill_holes=False, handle_edges=False, dense_shading=False, eikonal_stream=None,
+                image_loss="l2", ssim_weight=1.0, roughrange_weight=0.1):
     """Leaves gradients in .grad of every parameter; returns (loss, results).  fill_holes / handle_edges = True is the
     reference drivers' default configuration (render_surface.py:521-549).
+
+    image_loss: "l2" (plain L2 on the patch: round 1's goldens) or "reference" (PyramidL2 + SSIM + roughness range, the loss
+    of render_surface.py:594-613; iron_b200.PyramidL2Loss / ssim_loss_fn kernels).
 
     eikonal_stream: a second CUDA stream for the eikonal query on the random points (render_surface.py:580-583).  It does
     not depend on the traced surface, so its forward can run next to the tracer (whose rounds leave most SMs idle once
@@ -35,7 +42,20 @@ def stage2_step(sdf_network, color_network_dict, raytracer, render_fn, camera, t
         torch.cuda.current_stream().wait_stream(eikonal_stream)
     else:
         eik_cnt, eik = eikonal_points_term()
-    img = ((results["color"] - target) ** 2).sum() / float(mask.numel())
+    if image_loss == "reference":
+        # the loss the reference trains with (render_surface.py:594-599, 609-613): PyramidL2 + ssim_weight * SSIM on the
+        # [1, 3, H, W] views of the rendered patch, + the roughness-range penalty; all guarded by `mask.any()` there --
+        # here by a device-side factor, so the step stays free of host read-backs
+        pred_img = results["color"].permute(2, 0, 1).unsqueeze(0)
+        gt_img = target.permute(2, 0, 1).unsqueeze(0)
+        img = _pyramid_l2(pred_img, gt_img) + ssim_weight * ssim_loss_fn(pred_img, gt_img, mask.unsqueeze(0).unsqueeze(0))
+        rough = results["specular_roughness"]
+        sel = (mask & (rough > 0.5)).to(rough.dtype)
+        n_sel = sel.sum()
+        img = img + ((rough - 0.5) * sel).sum() / n_sel.clamp_min(1.0) * roughrange_weight
+        img = img * mask.any().to(img.dtype)
+    else:
+        img = ((results["color"] - target) ** 2).sum() / float(mask.numel())
     hn = results["normal"].reshape(-1, 3)
     hm = mask.reshape(-1, 1).float()
     n_hit = mask.sum()
@@ -71,10 +91,12 @@ class GraphedStage2Step:
     optimizer=None there and step the optimiser after the all-reduce."""
 
     def __init__(self, sdf_network, color_network_dict, raytracer, render_fn, K, W2C, target_shape, n_eik, crop_ul=None,
-                 full_size=(512, 512), eik_weight=0.1, warmup=3, time_tracer=False, overlap_eikonal=True, optimizer=None):
+                 full_size=(512, 512), eik_weight=0.1, warmup=3, time_tracer=False, overlap_eikonal=True, optimizer=None,
+                 image_loss="l2", ssim_weight=1.0, roughrange_weight=0.1):
         import torch.cuda
         self.sdf, self.nets, self.raytracer, self.render_fn = sdf_network, color_network_dict, raytracer, render_fn
         self.eik_weight = eik_weight
+        self.loss_kw = dict(image_loss=image_loss, ssim_weight=ssim_weight, roughrange_weight=roughrange_weight)
         self.optimizer = optimizer          # e.g. iron_b200.FusedAdam: its step() becomes the tail of the graph
         self.full_size, self.crop_ul = full_size, crop_ul
         H, W = target_shape
@@ -199,7 +221,7 @@ class GraphedStage2Step:
     def _eager_step(self, multi_stream=True):
         return stage2_step(self.sdf, self.nets, self.raytracer, self.render_fn, self.camera, self.target, self.eik,
                            eik_weight=self.eik_weight, dense_shading=True,
-                           eikonal_stream=self._eik_stream if multi_stream else None)
+                           eikonal_stream=self._eik_stream if multi_stream else None, **self.loss_kw)
 
     def step(self, target=None, eik_points=None, K=None, W2C=None):
         """Copies the given inputs (host tensors: pinned memory makes the copies asynchronous) into the static buffers,

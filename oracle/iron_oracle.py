@@ -880,9 +880,11 @@ def render_camera(sdf_p: Params, nets: Dict[str, Params], light: Tensor, cam: OC
 
 def stage2_step(sdf_p: Params, nets: Dict[str, Params], light: Tensor, cam: OCamera, target: Tensor,
                 eik_points: Tensor, eik_weight: float = 0.1, stats: Optional[TraceStats] = None,
-                max_num_rays: int = 50000, do_fill_holes: bool = False, handle_edges: bool = False, **sdf_kw):
+                max_num_rays: int = 50000, do_fill_holes: bool = False, handle_edges: bool = False,
+                image_loss: str = "l2", ssim_weight: float = 1.0, roughrange_weight: float = 0.1, **sdf_kw):
     """render_camera(is_training) -> L2 image loss + eik_weight * eikonal(random pts + hit normals [+ edge normals])
-    -> backward.  SSIM / pyramid losses are outside the section-8 scope (row f-3).  With do_fill_holes / handle_edges the
+    -> backward.  image_loss="reference" is the loss the reference trains with (row f-3: PyramidL2 + SSIM + roughness range,
+    render_surface.py:594-613); "l2" is the plain L2 of round 1's goldens.  With do_fill_holes / handle_edges the
     step is the drivers' default configuration (render_surface.py:541-549, 566-567, 601-607).
 
     The `normal` buffer holds the *normalised* normal (render_surface.py:146), so the hit-normal eikonal
@@ -899,7 +901,13 @@ def stage2_step(sdf_p: Params, nets: Dict[str, Params], light: Tensor, cam: OCam
     eik = ((eg.norm(dim=-1) - 1) ** 2).sum()
     img = torch.zeros(())
     if mask.any():
-        img = ((res["color"] - target) ** 2).sum() / float(mask.numel())
+        if image_loss == "reference":            # render_surface.py:594-599, 609-613 (ssim_weight 1.0, roughrange_weight 0.1)
+            pred_img = res["color"].permute(2, 0, 1).unsqueeze(0)
+            gt_img = target.permute(2, 0, 1).unsqueeze(0)
+            img = pyramid_l2_loss(pred_img, gt_img) + ssim_weight * ssim_loss(pred_img, gt_img, mask.unsqueeze(0).unsqueeze(0))
+            img = img + roughrange_loss(res["specular_roughness"], mask, roughrange_weight)
+        else:
+            img = ((res["color"] - target) ** 2).sum() / float(mask.numel())
         hn = res["normal"][mask]
         eik_cnt += hn.shape[0]
         eik = eik + ((hn.norm(dim=-1) - 1) ** 2).sum()

@@ -78,5 +78,67 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def step_with_reference_loss(L):
+    """A full stage-2 step of the REAL reference modules (render_camera is_training=True) with the loss the reference trains
+    with (render_surface.py:594-613: PyramidL2 + 1.0 * SSIM + 0.1 * roughness range, + 0.1 * eikonal), on the 32x32
+    silhouette crop of tests/golden/step_h256.npz (same weights, target and eikonal samples) -> step_refloss_h256.npz"""
+    sys.path.insert(0, HERE)
+    import make_golden as MG
+    fields, raytracer, renderer_ggx, rendering_func, network_conf = MG.import_reference()
+    torch.set_num_threads(8)
+    torch.manual_seed(0)
+    nets = MG.build_ggx_nets(fields)
+    torch.manual_seed(0)
+    sdf_net = fields.SDFNetwork(d_in=3, d_out=257, d_hidden=256, n_layers=8, skip_in=[4], multires=6, bias=0.5,
+                                scale=1.0, geometric_init=True, weight_norm=True)
+    MG.perturb(sdf_net, 0.005, seed=1)
+    # make the roughness-range term live: shift the roughness head so that some hit pixels exceed 0.5 (:609-613)
+    with torch.no_grad():
+        nets["specular_roughness_network"].lin4.bias.add_(6.0)
+    nets["point_light_network"] = network_conf.PointLightNetwork()
+    nets["point_light_network"].set_light(32.0)
+    rt = raytracer.RayTracer()
+    render_fn = MG.make_render_fn(renderer_ggx.GGXColocatedRenderer(use_cuda=False), rendering_func.get_materials)
+    ul = (448, 230)
+    cam, _, _ = MG.fixture_camera(raytracer).crop_region(32, 32, ul_corner=ul)
+    results = raytracer.render_camera(cam, sdf_net, rt, nets, render_fn, fill_holes=False, handle_edges=False, is_training=True)
+    mask = results["convergent_mask"]
+    tgt = torch.rand(32, 32, 3, generator=torch.Generator().manual_seed(11)) * 0.5
+    eik_pts = torch.empty(32 * 32 // 2, 3).uniform_(-1.0, 1.0, generator=torch.Generator().manual_seed(12))
+    eg = sdf_net.gradient(eik_pts.clone()).view(-1, 3)
+    eik_cnt = eg.shape[0]
+    eik = ((eg.norm(dim=-1) - 1) ** 2).sum()
+    pred_img = results["color"].permute(2, 0, 1).unsqueeze(0)[:, :3]
+    gt_img = tgt.permute(2, 0, 1).unsqueeze(0)
+    l_pyr = L.PyramidL2Loss(use_cuda=False)(pred_img, gt_img)
+    l_ssim = 1.0 * L.ssim_loss_fn(pred_img, gt_img, mask.unsqueeze(0).unsqueeze(0))
+    hn = results["normal"][mask]
+    eik_cnt += hn.shape[0]
+    eik = eik + ((hn.norm(dim=-1) - 1) ** 2).sum()
+    rough = results["specular_roughness"][mask]
+    rough = rough[rough > 0.5]
+    l_rough = (rough - 0.5).mean() * 0.1 if rough.numel() > 0 else torch.zeros(())
+    loss = l_pyr + l_ssim + eik / eik_cnt * 0.1 + l_rough
+    loss.backward()
+    out = dict(ul=np.array(ul), target=tgt.numpy(), eik_points=eik_pts.numpy(), loss=loss.detach().numpy(), mask=mask.numpy(),
+               l_pyr=l_pyr.detach().numpy(), l_ssim=l_ssim.detach().numpy(), l_rough=np.float32(float(l_rough)),
+               n_rough=np.int64(rough.numel()), rough_bias_shift=np.float32(6.0))
+    out["res.color"] = results["color"].detach().numpy()
+    out["res.specular_roughness"] = results["specular_roughness"].detach().numpy()
+    allp = [("sdf." + k, p_) for k, p_ in sdf_net.named_parameters()]
+    for nm in ("diffuse_albedo_network", "specular_albedo_network", "specular_roughness_network", "point_light_network"):
+        allp += [(nm + "." + k, p_) for k, p_ in nets[nm].named_parameters()]
+    for k, p_ in allp:
+        gr_ = p_.grad
+        out["gsum." + k] = np.array([gr_.double().sum().item(), gr_.double().abs().sum().item(), gr_.double().pow(2).sum().sqrt().item()])
+        if gr_.numel() <= 1024 or k.endswith("lin8.weight_v") or k.endswith("lin0.weight_v"):
+            out["g." + k] = gr_.numpy()
+    path = os.path.join(HERE, "..", "tests", "golden", "step_refloss_h256.npz")
+    np.savez_compressed(path, **out)
+    print("step_refloss_h256.npz hits", int(mask.sum()), "loss", float(loss), "pyr", float(l_pyr), "ssim", float(l_ssim),
+          "rough", float(l_rough), "n_rough", int(rough.numel()), os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     main()
+    step_with_reference_loss(import_losses())

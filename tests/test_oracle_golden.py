@@ -292,3 +292,34 @@ def test_patch_losses_match_the_reference(golden):
         gs, = torch.autograd.grad(ls, pred)
         assert abs(float(ls) - float(g[f"{c}.ssim"])) <= 2e-6, c
         close(gs.numpy(), g[f"{c}.ssim_grad"], 2e-8, 1e-4)
+
+
+def test_full_step_with_the_reference_loss(golden):
+    """stage2_step(image_loss="reference"): PyramidL2 + SSIM + roughness range + eikonal, the loss the reference trains with
+    (render_surface.py:594-613), against a step of the real reference modules (oracle/make_golden_losses.py)."""
+    g = golden("step_refloss_h256")
+    p = _trace_net()
+    torch.manual_seed(0)
+    nets = O.make_material_dict()
+    with torch.no_grad():
+        nets["specular_roughness_network"]["lin4.bias"].add_(float(g["rough_bias_shift"]))
+    light = torch.tensor(32.0, requires_grad=True)
+    for d in [p] + list(nets.values()):
+        for v in d.values():
+            v.requires_grad_(True)
+    cam = O.OCamera.fixture().crop(32, 32, tuple(int(v) for v in g["ul"]))
+    loss, res = O.stage2_step(p, nets, light, cam, T(g["target"]), T(g["eik_points"]), image_loss="reference")
+    assert (res["convergent_mask"].numpy() == g["mask"]).all()
+    assert int(g["n_rough"]) > 0
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"])), (loss.item(), float(g["loss"]))
+    allp = [("sdf." + k, v) for k, v in p.items()]
+    for nm, d in nets.items():
+        allp += [(f"{nm}.{k}", v) for k, v in d.items()]
+    allp.append(("point_light_network.light", light))
+    for k, v in allp:
+        s = g["gsum." + k]
+        nrm = v.grad.double().pow(2).sum().sqrt().item()
+        assert abs(nrm - s[2]) <= 1e-3 * max(s[2], 1e-12), (k, nrm, s[2])
+        if "g." + k in g:
+            ref = g["g." + k]
+            close(v.grad.numpy(), ref, 1e-4 * np.abs(ref).max(), 1e-3)

@@ -487,3 +487,53 @@ def test_step_bench_configuration_against_oracle(crop, trace_mode):
     if gl is not None:
         assert abs(gl - float(light_p.grad)) <= tol * abs(float(light_p.grad)), (gl, float(light_p.grad))
     print(f"[H512 {crop} / {trace_mode}] same_mask={same_mask} worst relative gradient error {worst:.2e}")
+
+
+def test_step_with_the_reference_loss_golden(golden, trace_mode):
+    """The step with the loss the reference trains with (PyramidL2 + SSIM + roughness range + eikonal,
+    render_surface.py:594-613; stage2_step(image_loss="reference")) against a step of the real reference modules
+    (tests/golden/step_refloss_h256.npz), eager and as a graph replay."""
+    g = golden("step_refloss_h256")
+    ib, sdf, nets, cam512 = build()
+    with torch.no_grad():
+        nets["specular_roughness_network"].lin4.bias.add_(float(g["rough_bias_shift"]))
+    ul = tuple(int(v) for v in g["ul"])
+    cam, _, _ = cam512.crop_region(32, 32, ul_corner=ul)
+    rf = ib.make_render_fn(ib.GGXColocatedRenderer(use_cuda=True))
+    target, eik = T(g["target"]), T(g["eik_points"])
+    named = [("sdf." + k, p) for k, p in sdf.named_parameters()]
+    for nm in ("diffuse_albedo_network", "specular_albedo_network", "specular_roughness_network", "point_light_network"):
+        named += [(nm + "." + k, p) for k, p in nets[nm].named_parameters()]
+
+    def check(loss, res, what):
+        m = res["convergent_mask"].cpu().numpy()
+        same_mask = bool((m == g["mask"]).all())
+        assert (m == g["mask"]).mean() >= 0.998
+        assert abs(float(loss) - float(g["loss"])) <= (1e-3 if same_mask else 2e-2) * abs(float(g["loss"])), (what, float(loss), float(g["loss"]))
+        tol = TOL_GRAD_REL if same_mask else 5e-2
+        worst = 0.0
+        for k, p in named:
+            gr = p.grad.double().cpu()
+            ref = g["gsum." + k]
+            e = abs(gr.pow(2).sum().sqrt().item() - ref[2]) / max(ref[2], 1e-12)
+            worst = max(worst, e)
+            assert e <= tol, (what, k, gr.pow(2).sum().sqrt().item(), ref[2])
+            if "g." + k in g:
+                r = rel_l2(gr.numpy(), g["g." + k])
+                worst = max(worst, r)
+                assert r <= 2 * tol, (what, k, r)
+        print(f"[{trace_mode}] reference-loss step ({what}): loss {float(loss):.6f} / {float(g['loss']):.6f}, same_mask={same_mask}, "
+              f"worst relative gradient error {worst:.2e}")
+
+    loss, res = ib.stage2_step(sdf, nets, ib.RayTracer(), rf, cam, target.to(DEV), eik.to(DEV), eik_weight=0.1,
+                               image_loss="reference")
+    check(loss, res, "eager, compacted shading")
+    Kh = torch.tensor(O.FIXTURE_K, dtype=torch.float64).reshape(4, 4).float()
+    Wh = torch.tensor(O.FIXTURE_W2C, dtype=torch.float64).reshape(4, 4).float()
+    gs = ib.GraphedStage2Step(sdf, nets, ib.RayTracer(), rf, Kh, Wh, (32, 32), eik.shape[0], crop_ul=ul, eik_weight=0.1,
+                              image_loss="reference")
+    for _ in range(2):
+        loss = gs.step(target=target.pin_memory(), eik_points=eik.pin_memory())
+        torch.cuda.synchronize()
+    check(loss, gs.results, "graph replay")
+    gs.close()
