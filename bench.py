@@ -33,6 +33,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "traced+shaded rays/sec fwd+bwd (8x512 SDF MLP, GGX)"
+# DRAM bytes of one mlp_h16_kernel launch by (hidden width, patch edge), from the ncu capture named below (cold cache: the
+# fp16 weight copies and the encoded points are read once from HBM, the activations live in L2)
+MLP_H16_TRAFFIC = {(512, 64): 8.18e6}
+MLP_H16_TRAFFIC_SOURCE = "profiles/r1l_mlp_h16_ncu.md (ncu --set full, launch 0; a profile constant, not measured by this run)"
 UNIT = "rays/s"
 
 
@@ -516,8 +520,7 @@ def run_ours(args):
         # one graph replay per step: the library's kernels are graph nodes (counted at capture); the tracer's device time
         # comes from two external-event nodes inside the graph, readable for the last replay
         launches = gs.kernels_per_replay * args.steps
-        tms = gs.tracer_ms()
-        tr_ms = [tms] * args.steps
+        tr_ms = None            # per-replay tracer times are read in the e2e loop below (each of its steps ends in a sync)
         stats = [v * args.steps for v in tracer.last_stats.cpu().tolist()]
         stats[5] = stats[5] // args.steps
     else:
@@ -551,8 +554,13 @@ def run_ours(args):
     barrier()
     e2e_steps = args.steps
     t0 = time.perf_counter()
+    tr_e2e = []
     for _ in range(e2e_steps):
         loss_host = float(e2e_step().item())          # D2H of the step's result
+        if gs is not None and gs._tracer_events:      # the external event pair inside the graph: THIS replay's tracer time
+            tr_e2e.append(gs.tracer_ms())
+    if tr_ms is None:
+        tr_ms = tr_e2e if tr_e2e else [0.0] * args.steps
     barrier()
     e2e_t = time.perf_counter() - t0
     te = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
@@ -597,15 +605,17 @@ def run_ours(args):
                          # H = 512) from the committed ncu --set full capture (profiles/r1l_mlp_h16_ncu.md, launch 0,
                          # cold cache: the fp16 weight copies, 7.3 MB, and the encoded points are read once from HBM; the
                          # activations live in L2).  The kernel's operand stream is L2 -> SM: 0.48 GB per launch.
-                         "traffic": (8.18e6 if (_prev == 2 and H == 512 and S == 64) else None),
-                         "traffic_unit": "bytes of DRAM traffic per launch (ncu, profiles/r1l_mlp_h16_ncu.md)",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE mlp_h16 launch of this workload, NOT measured
+                         # by this run: the constant is read from the committed ncu --set full capture named beside it
+                         "traffic": (MLP_H16_TRAFFIC.get((H, S)) if _prev == 2 else None),
+                         "traffic_source": MLP_H16_TRAFFIC_SOURCE,
                          "mode": roof_mode + "; achieved = ALGORITHMIC fp32 FLOPs of the evaluations executed / tracer time "
                                  "(whole tracer call incl. its state-machine kernels); peak = bf16 dense tensor, sustained, of "
                                  + pk["source"],
                          "frac_of_split_ceiling": achieved / (peak / split_cost) if peak else None,
                          "flop_per_eval": flop_per_eval, "evals_per_step": evals / args.steps,
-                         "kernel_ms_per_step": tr_total_ms / args.steps,
-                         "kernel_share_of_step": tr_total_ms / my_ms if my_ms else None},
+                         "kernel_ms_per_step": tr_total_ms / max(len(tr_ms), 1),
+                         "kernel_share_of_step": (tr_total_ms / len(tr_ms)) / (my_ms / args.steps) if (my_ms and tr_ms) else None},
             "tracer": {"evals_sphere": stats[0] / args.steps, "evals_sampler": stats[1] / args.steps,
                        "evals_bisect": stats[2] / args.steps, "sampler_rays": stats[3] / args.steps,
                        "root_rays": stats[4] / args.steps, "k_max": stats[5], "hits": hits, "rays": S * S,
@@ -614,6 +624,8 @@ def run_ours(args):
             "rank_ms_per_step": [round(x, 4) for x in rank_ms], "rank_crop_ul": [list(crop_corner(r, S)) for r in range(world)],
             "loss": loss_host,
             "step_ms": [round(x, 3) for x in step_ms], "tracer_ms": [round(x, 3) for x in tr_ms],
+            "tracer_ms_source": ("one sample per replay of the e2e loop (external CUDA-event pair inside the graph)"
+                                 if gs is not None else "CUDA-event pair around every tracer call of the timed steps"),
         }
         if world == 1 and not args.no_cpu:
             line["ggx_roofline"] = ggx_microbench(dev, pk)
@@ -629,15 +641,120 @@ def run_ours(args):
                 "rel_err_vs_oracle_cpu": rel(loss_host, cb["loss"]) if cb["rays"] == S * S else None}
         emit(line)
     faulthandler.cancel_dump_traceback_later()
+    # orderly teardown while the CUDA context is alive: the captured graph (its memory pool, streams and external events)
+    # first, then the process group; the interpreter then exits normally with the process's real status
+    if gs is not None:
+        gs.close()
+    del gs
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    # The measurement is complete and the line is out.  Leave without running the interpreter's teardown: destroying the
-    # captured graph, its private memory pool, the side streams and the external events in arbitrary order at exit crashed
-    # one soak run in three (SIGSEGV after the last replay) -- nothing of value happens after this point.
+    stage("done")
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
+
+
+def run_render(args):
+    """--workload render1024 (BASELINE configs[2]): render_surface.py's full-frame forward render -- the 512x512 fixture view
+    resized to 1024 x 1024 (1,048,576 rays), render_camera(is_training=False): sphere tracing + dense sampling + bisection in
+    <= 50,000-ray tracer calls, get_all + materials + GGX on the compacted hits in <= 320,000-point chunks, no backward.
+    Single GPU.  `value` = rays/s device-timed; `e2e` adds the camera upload and the D2H copy of the rendered image."""
+    import torch
+    import iron_b200 as ib
+    from iron_b200 import _lib
+    from oracle import iron_oracle as O
+    lib = _lib.load()
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    H = args.hidden
+    torch.manual_seed(0)
+    nets = ib.init_rendering_network_dict("ggx")
+    torch.manual_seed(0)
+    sdf = ib.SDFNetwork(d_in=3, d_out=257, d_hidden=H, n_layers=8, skip_in=[4], multires=6, bias=0.5, scale=1.0,
+                        geometric_init=True, weight_norm=True).to(dev)
+    nets["point_light_network"].set_light(32.0)
+    nets = {k: v.to(dev) for k, v in nets.items()}
+    render_fn = ib.make_render_fn(ib.GGXColocatedRenderer(use_cuda=True))
+    tracer = ib.RayTracer()
+    tracer.collect_stats = True
+    K_h = torch.tensor(O.FIXTURE_K, dtype=torch.float64).reshape(4, 4).float().pin_memory()
+    W2C_h = torch.tensor(O.FIXTURE_W2C, dtype=torch.float64).reshape(4, 4).float().pin_memory()
+    R = 1024
+
+    def make_cam():
+        return ib.Camera(512, 512, K_h.to(dev, non_blocking=True), W2C_h.to(dev, non_blocking=True)).resize(R / 512.0)[0]
+
+    cam = make_cam()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    pin = torch.empty(R, R, 3, dtype=torch.float32).pin_memory()
+
+    def frame(c):
+        with torch.no_grad():
+            return ib.render_camera(c, sdf, tracer, nets, render_fn, fill_holes=False, handle_edges=False, is_training=False)
+
+    for _ in range(max(args.warmup, 3)):
+        res = frame(cam)
+    torch.cuda.synchronize()
+    l0 = lib.ironb_launch_count()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = frame(cam)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    launches = lib.ironb_launch_count() - l0
+    ms = [a.elapsed_time(b) for a, b in evs]
+    t = sum(ms) / len(ms)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = frame(make_cam())
+        pin.copy_(res["color"], non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_t = (time.perf_counter() - t0) / args.steps
+    hits = int(res["convergent_mask"].sum().item())
+    line = {"metric": "traced+shaded rays/sec forward (1024x1024 full-frame render, 8x512 SDF MLP, GGX)", "value": R * R / (t * 1e-3),
+            "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]: render_surface.py full-frame forward render 1024x1024 (the 512x512 fixture view "
+                                   "resized x2): sphere tracing + dense sampling + bisection + get_all + materials + GGX, no backward",
+                       "sdf_mlp": f"8x{H}, PE L=6, skip@4, softplus(100), weight-norm", "rays": R * R, "hits": hits,
+                       "chunking": "<= 50,000 rays per tracer call, <= 320,000 hit points per shading chunk (the reference's)",
+                       "l2": "256 MiB flush between frames", "execution": "eager (the hit count of every shading chunk is read back)"},
+            "e2e": {"value": R * R / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 2 * 64, "d2h_bytes_per_step": R * R * 3 * 4,
+                    "ms_per_step": e2e_t * 1e3},
+            "gpu_launches": int(launches), "step_ms": [round(x, 2) for x in ms]}
+    if not args.no_cpu:
+        # the reference path as eager PyTorch on this GPU, same frame (one warm-up + one timed frame: ~10 s each)
+        import torch.backends.cuda
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        st = oracle_setup(H, 64, 0, device=dev)
+        Oc, sdf_p, mats, light = st[0], st[1], st[2], st[3]
+        fx = Oc.OCamera.fixture()
+        ocam = Oc.OCamera(512, 512, fx.K.to(dev), fx.W2C.to(dev)).resize(R / 512.0)
+        with torch.device(dev), torch.no_grad():
+            Oc.render_camera(sdf_p, mats, light.detach(), ocam.crop(256, 256, (384, 384)), handle_edges=False)   # warm-up
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ores = Oc.render_camera(sdf_p, mats, light.detach(), ocam, handle_edges=False)
+            e1.record()
+            torch.cuda.synchronize()
+        tm = e0.elapsed_time(e1)
+        m, mr = res["convergent_mask"], ores["convergent_mask"]
+        both = m & mr
+        line["cuda_eager_baseline"] = {
+            "value": R * R / (tm * 1e-3), "unit": UNIT, "ms_per_step": tm, "steps": 1,
+            "what": "the reference path (oracle restatement) as eager PyTorch on cuda:0, fp32, allow_tf32=False, same frame",
+            "speedup_of_this_library": line["value"] / (R * R / (tm * 1e-3)),
+            "mask_agreement": float((m == mr).float().mean()),
+            "rgb_within_1e-3": float(((res["color"] - ores["color"]).abs().amax(-1)[both] <= 1e-3).float().mean())}
+    emit(line)
 
 
 _REAL_STDOUT = None
@@ -669,6 +786,9 @@ def main():
     ap.add_argument("--patch", type=int, default=64)
     ap.add_argument("--loss", default="reference", choices=["reference", "l2"],
                     help="reference: PyramidL2 + SSIM + roughness range (render_surface.py:594-613), in every arm; l2: round 1's plain L2")
+    ap.add_argument("--workload", default="step", choices=["step", "render1024"],
+                    help="step: the stage-2 training step (configs[1]; --patch 256 = configs[3]); render1024: configs[2], the "
+                         "full-frame 1024x1024 forward render")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--driver-defaults", action="store_true",
                     help="also run hole filling + edge sampling (the reference drivers' fill_holes=True, handle_edges=True)")
@@ -686,36 +806,9 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
-    single = int(os.environ.get("WORLD_SIZE", "1")) == 1
-    if args.exec_mode == "graph" and single and not os.environ.get("IRONB_BENCH_CHILD"):
-        # Safety net (single process only): the measurement runs in a child; if the graph-replay path dies (a CUDA fault
-        # kills the context, nothing can be measured in this process afterwards) the same step is measured with eager
-        # execution in a fresh child and the line says so.  The child's JSON line is relayed unchanged otherwise.
-        env = dict(os.environ, IRONB_BENCH_CHILD="1")
-        try:    # the C-ABI library is loaded here too (fails loudly if it is missing), although the child does the GPU work
-            from iron_b200 import _lib as _parent_lib
-            _parent_lib.load()
-        except Exception as e:
-            sys.stderr.write(f"bench.py: cannot load libiron_b200.so: {e}\n")
-            sys.exit(1)
-        for attempt, extra in enumerate(([], ["--exec", "eager"])):
-            try:
-                r = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + extra, env=env,
-                                   stdout=subprocess.PIPE, stderr=None, timeout=float(os.environ.get("IRONB_BENCH_CHILD_TIMEOUT", "240")))
-            except subprocess.TimeoutExpired as te:
-                sys.stderr.write(f"bench.py: child (attempt {attempt}) did not finish in {te.timeout:.0f} s; killed\n")
-                continue
-            lines = [ln for ln in r.stdout.decode("utf-8", "replace").splitlines() if ln.startswith("{")]
-            if lines and r.returncode != 0:
-                sys.stderr.write(f"bench.py: child exited with code {r.returncode} AFTER printing its result line (teardown)\n")
-            if lines:
-                line = json.loads(lines[-1])
-                if attempt == 1:
-                    line["config"]["execution"] += " -- FALLBACK: the CUDA-graph child exited with an error"
-                emit(line)
-                return
-            sys.stderr.write(f"bench.py: child (attempt {attempt}) exited with code {r.returncode}\n")
-        sys.exit(1)
+    if args.workload == "render1024":
+        run_render(args)
+        return
     guarded_run_ours(args)
 
 
