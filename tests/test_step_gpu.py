@@ -530,6 +530,13 @@ def test_step_with_the_reference_loss_golden(golden, trace_mode):
     check(loss, res, "eager, compacted shading")
     if trace_mode != "batched-tcgen05":
         return          # the graph replay is built on the default tracer (the fused FFMA tracer is a diagnostic mode)
+    # fresh modules for the graph: it has to be captured before any eager backward through the same parameters
+    ib, sdf, nets, cam512 = build()
+    with torch.no_grad():
+        nets["specular_roughness_network"].lin4.bias.add_(float(g["rough_bias_shift"]))
+    named[:] = [("sdf." + k, p) for k, p in sdf.named_parameters()]
+    for nm in ("diffuse_albedo_network", "specular_albedo_network", "specular_roughness_network", "point_light_network"):
+        named += [(nm + "." + k, p) for k, p in nets[nm].named_parameters()]
     Kh = torch.tensor(O.FIXTURE_K, dtype=torch.float64).reshape(4, 4).float()
     Wh = torch.tensor(O.FIXTURE_W2C, dtype=torch.float64).reshape(4, 4).float()
     gs = ib.GraphedStage2Step(sdf, nets, ib.RayTracer(), rf, Kh, Wh, (32, 32), eik.shape[0], crop_ul=ul, eik_weight=0.1,
