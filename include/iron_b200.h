@@ -218,6 +218,23 @@ typedef struct {
 int ironb_adam_step(const ironb_adam_tensor* tensors_dev, int n_tensors, int64_t max_numel, double beta1, double beta2,
                     double eps, int* step_dev, void* stream);
 
+/* ---------------------------------------------------------------- CompositeRenderer ("comp2")
+ * models/renderer_ggx.py:781-858: rough-plastic diffuse lobe (the GGX tables) + exact-Fresnel conductor lobe + dielectric
+ * microfacet lobe, colocated flash.  M points; kd/ks [M,3]; alpha, metallic_eta, metallic_k, dielectric_eta, dist [M];
+ * normal, viewdir [M,3]; light: device scalar.  Outputs [M,3] each.  The reference accumulates rgb in place into its
+ * diffuse tensor, so its "diffuse_rgb" output IS rgb: pass the sum of both upstream gradients as g_rgb.
+ * Backward: any upstream may be NULL; d_light is ACCUMULATED (caller zeroes it), the others are written. */
+int ironb_composite_fwd(const float* light, const float* dist, const float* normal, const float* viewdir, const float* kd,
+                        const float* ks, const float* alpha, const float* metallic_eta, const float* metallic_k,
+                        const float* dielectric_eta, const float* trans, const float* diff_trans, int64_t M, float* rgb,
+                        float* specular_rgb, float* metallic_rgb, float* dielectric_rgb, void* stream);
+int ironb_composite_bwd(const float* light, const float* dist, const float* normal, const float* viewdir, const float* kd,
+                        const float* ks, const float* alpha, const float* metallic_eta, const float* metallic_k,
+                        const float* dielectric_eta, const float* trans, const float* diff_trans, int64_t M,
+                        const float* g_rgb, const float* g_specular, const float* g_metallic, const float* g_dielectric,
+                        float* d_light, float* d_dist, float* d_normal, float* d_kd, float* d_ks, float* d_alpha,
+                        float* d_metallic_eta, float* d_metallic_k, float* d_dielectric_eta, void* stream);
+
 /* ---------------------------------------------------------------- patch losses
  * One [C][H][W] image pair (C <= 4), addressed through ELEMENT strides {channel, row, column}, so the [1,3,H,W] view of
  * the renderer's [H,W,3] buffer is read in place.  Value and gradient w.r.t. the first image in one call; `ws` from

@@ -6,9 +6,9 @@ from .fields import RenderingNetwork, SDFNetwork
 from .network_conf import (PointLightNetwork, choose_renderer, init_rendering_network_dict, init_sdf_network_dict)
 from .raytracer import (Camera, RayTracer, intersect_sphere, locate_edge_points, raytrace_camera, raytrace_pixels,
                         render_camera, render_edge_pixels, render_normal_and_color, reparam_points)
-from .render_fn import make_render_fn
-from .renderer_ggx import GGXColocatedRenderer
-from .rendering_func import get_materials
+from .render_fn import make_render_fn, make_render_fn_comp2
+from .renderer_ggx import CompositeRenderer, GGXColocatedRenderer
+from .rendering_func import get_materials, get_materials_comp
 from .embedder import get_embedder
 from .optim import FusedAdam
 from .image_losses import PyramidL2Loss, ssim_loss_fn
@@ -18,6 +18,6 @@ __all__ = [
     "SDFNetwork", "RenderingNetwork", "PointLightNetwork", "GGXColocatedRenderer", "RayTracer", "Camera",
     "intersect_sphere", "raytrace_pixels", "raytrace_camera", "render_camera", "render_normal_and_color",
     "reparam_points", "locate_edge_points", "render_edge_pixels", "get_materials", "get_embedder", "make_render_fn", "stage2_step", "GraphedStage2Step", "FusedAdam",
-    "PyramidL2Loss", "ssim_loss_fn",
+    "PyramidL2Loss", "ssim_loss_fn", "CompositeRenderer", "get_materials_comp", "make_render_fn_comp2",
     "init_sdf_network_dict", "init_rendering_network_dict", "choose_renderer",
 ]

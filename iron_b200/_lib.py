@@ -64,6 +64,8 @@ _PROTOS = {
     "ironb_matnet_bwd": (_INT, [_LAY, _CFG, _P, _I64, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "ironb_ggx_fwd": (_INT, [_P] * 9 + [_I64] + [_P] * 4),
     "ironb_ggx_bwd": (_INT, [_P] * 9 + [_I64] + [_P] * 11),
+    "ironb_composite_fwd": (_INT, [_P] * 12 + [_I64] + [_P] * 5),
+    "ironb_composite_bwd": (_INT, [_P] * 12 + [_I64] + [_P] * 14),
     "ironb_camera_rays": (_INT, [_P, _I64, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P]),
     "ironb_intersect_sphere": (_INT, [_P, _P, _I64, _F, _P, _P, _P, _P]),
     "ironb_trace_workspace_bytes": (_I64, [_LAY, _I64]),

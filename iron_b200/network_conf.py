@@ -4,7 +4,7 @@ import torch
 import torch.nn as nn
 
 from .fields import RenderingNetwork, SDFNetwork
-from .renderer_ggx import GGXColocatedRenderer
+from .renderer_ggx import CompositeRenderer, GGXColocatedRenderer
 
 
 class PointLightNetwork(nn.Module):
@@ -29,27 +29,48 @@ def init_sdf_network_dict(d_hidden=256):
 
 
 def init_rendering_network_dict(renderer_name="ggx"):
-    if renderer_name != "ggx":
-        raise NotImplementedError(f"renderer {renderer_name!r} is outside the hot path rebuilt here (only 'ggx')")
+    """'ggx' (models/network_conf.py:48-120) and 'comp2' (:318-478, the CompositeRenderer's heads), built in the reference's
+    dict-literal order so that a seeded construction consumes the RNG identically."""
     mk = RenderingNetwork
     d = {}
-    # dict-literal order of the reference (RNG consumption): color, diffuse, specular (twice: duplicate key), roughness
-    d["color_network"] = mk(d_in=9, d_out=3, d_feature=256, d_hidden=256, n_layers=4, multires_view=4, mode="idr",
-                            squeeze_out=True).cuda()
-    d["diffuse_albedo_network"] = mk(d_in=9, d_out=3, d_feature=256, d_hidden=256, n_layers=4, multires_view=4,
-                                     mode="idr", squeeze_out=True).cuda()
-    for _ in range(2):
-        d["specular_albedo_network"] = mk(d_in=6, d_out=3, d_feature=256, d_hidden=256, n_layers=4, multires=6,
-                                          multires_view=-1, mode="no_view_dir", squeeze_out=False, output_bias=0.4,
-                                          output_scale=0.1).cuda()
-    d["specular_roughness_network"] = mk(d_in=6, d_out=1, d_feature=256, d_hidden=256, n_layers=4, multires=6,
-                                         multires_view=-1, mode="no_view_dir", squeeze_out=False, output_bias=0.1,
-                                         output_scale=0.1).cuda()
-    d["point_light_network"] = PointLightNetwork().cuda()
-    return d
+    if renderer_name == "ggx":
+        # color, diffuse, specular (twice: duplicate key in the reference's literal), roughness
+        d["color_network"] = mk(d_in=9, d_out=3, d_feature=256, d_hidden=256, n_layers=4, multires_view=4, mode="idr",
+                                squeeze_out=True).cuda()
+        d["diffuse_albedo_network"] = mk(d_in=9, d_out=3, d_feature=256, d_hidden=256, n_layers=4, multires_view=4,
+                                         mode="idr", squeeze_out=True).cuda()
+        for _ in range(2):
+            d["specular_albedo_network"] = mk(d_in=6, d_out=3, d_feature=256, d_hidden=256, n_layers=4, multires=6,
+                                              multires_view=-1, mode="no_view_dir", squeeze_out=False, output_bias=0.4,
+                                              output_scale=0.1).cuda()
+        d["specular_roughness_network"] = mk(d_in=6, d_out=1, d_feature=256, d_hidden=256, n_layers=4, multires=6,
+                                             multires_view=-1, mode="no_view_dir", squeeze_out=False, output_bias=0.1,
+                                             output_scale=0.1).cuda()
+        d["point_light_network"] = PointLightNetwork().cuda()
+        return d
+    if renderer_name in ("comp2", "comp"):
+        head = lambda d_out, bias: mk(d_in=6, d_out=d_out, d_feature=256, d_hidden=256, n_layers=4, multires=6, multires_view=-1,
+                                      mode="no_view_dir", squeeze_out=False, output_bias=bias, output_scale=1.0).cuda()
+        d["color_network"] = mk(d_in=9, d_out=3, d_feature=256, d_hidden=256, n_layers=4, multires_view=4, mode="idr",
+                                squeeze_out=True).cuda()
+        d["diffuse_albedo_network"] = mk(d_in=9, d_out=3, d_feature=256, d_hidden=256, n_layers=4, multires_view=4,
+                                         mode="idr", squeeze_out=True).cuda()
+        d["specular_albedo_network"] = head(3, 0.0)
+        d["specular_roughness_network"] = head(1, 0.1)
+        d["point_light_network"] = PointLightNetwork().cuda()
+        d["env_light_network"] = mk(d_in=3, d_out=1, d_feature=256, d_hidden=256, n_layers=4, multires=6, multires_view=-1,
+                                    mode="points_only", squeeze_out=False, output_bias=0.0, output_scale=1.0).cuda()
+        for name in ("metallic_network", "dielectric_network", "metallic_eta_network", "metallic_k_network",
+                     "dielectric_eta_network"):
+            d[name] = head(1, 0.1)
+        return d
+    raise NotImplementedError(f"renderer {renderer_name!r} is outside the hot path rebuilt here ('ggx', 'comp2')")
 
 
 def choose_renderer(renderer_name="ggx"):
-    if renderer_name != "ggx":
-        raise NotImplementedError(f"renderer {renderer_name!r} is outside the hot path rebuilt here (only 'ggx')")
-    return GGXColocatedRenderer(use_cuda=True)
+    """models/network_conf.py:748-765."""
+    if renderer_name == "ggx":
+        return GGXColocatedRenderer(use_cuda=True)
+    if renderer_name in ("comp", "comp2"):
+        return CompositeRenderer(use_cuda=True)
+    raise NotImplementedError(f"renderer {renderer_name!r} is outside the hot path rebuilt here ('ggx', 'comp2')")

@@ -44,3 +44,19 @@ def get_materials(network_dict, points, normals, features, is_metal=False):
         "specular_albedo": specular_albedo,
         "specular_roughness": specular_roughness,
     }
+
+
+def get_materials_comp(network_dict, points, normals, features):
+    """models/rendering_func.py:19-48: the nine material heads of the "comp2" renderer (all RenderingNetworks, fused CUDA
+    forward / backward), each followed by the reference's abs()."""
+    net = lambda name, v: network_dict[name](points, normals, v, features).abs()
+    return {
+        "diffuse_albedo": net("diffuse_albedo_network", -normals),
+        "specular_albedo": net("specular_albedo_network", None),
+        "metallic": net("metallic_network", None),
+        "dielectric": net("dielectric_network", None),
+        "specular_roughness": net("specular_roughness_network", None),
+        "metallic_eta": net("metallic_eta_network", None),
+        "metallic_k": net("metallic_k_network", None),
+        "dielectric_eta": net("dielectric_eta_network", None),
+    }

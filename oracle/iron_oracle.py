@@ -372,6 +372,17 @@ def material_forward(p: Params, cfg: dict, points: Tensor, normals: Tensor,
     return h
 
 
+def comp2_material_cfgs() -> Dict[str, Tuple[str, dict]]:
+    """Output head -> (network name, RenderingNetwork kwargs) of the 'comp2' dictionary, models/network_conf.py:318-478, as
+    get_material_comp queries them (model_bed.py:115-154 / models/rendering_func.py:19-48)."""
+    idr = dict(mode="idr", multires=0, multires_view=4, squeeze_out=True, output_bias=0.0, output_scale=1.0)
+    nv = lambda bias: dict(mode="no_view_dir", multires=6, multires_view=0, squeeze_out=False, output_bias=bias, output_scale=1.0)
+    return {"diffuse_albedo": ("diffuse_albedo_network", idr), "specular_albedo": ("specular_albedo_network", nv(0.0)),
+            "specular_roughness": ("specular_roughness_network", nv(0.1)), "metallic": ("metallic_network", nv(0.1)),
+            "dielectric": ("dielectric_network", nv(0.1)), "metallic_eta": ("metallic_eta_network", nv(0.1)),
+            "metallic_k": ("metallic_k_network", nv(0.1)), "dielectric_eta": ("dielectric_eta_network", nv(0.1))}
+
+
 def get_materials(nets: Dict[str, Params], points: Tensor, normals: Tensor, feats: Tensor,
                   is_metal: bool = False) -> Dict[str, Tensor]:
     """models/rendering_func.py:5-16."""
@@ -443,6 +454,60 @@ def ggx_shade(light: Tensor, distance: Tensor, normal: Tensor, viewdir: Tensor,
     Fdr = torch.clamp(1.0 - diff_trans[idy], min=0.0, max=1.0)
     diff = L * (kd / (1.0 - Fdr + 1e-10) / np.pi) * c * T12 * T12 * inv_eta2
     return {"diffuse_rgb": diff, "specular_rgb": spec, "rgb": diff + spec}
+
+
+def composite_shade(light: Tensor, distance: Tensor, normal: Tensor, viewdir: Tensor, params: Dict[str, Tensor]) -> Dict[str, Tensor]:
+    """CompositeRenderer.forward (use_env_light=False), models/renderer_ggx.py:781-858, with its helpers: calc_D_specular
+    :767-771 (called with eta in the roughness slot, :803), calc_G_specular / smithG1 :12-16, 773-776,
+    fresnel_conductor_exact :592-606, the MODULE-level fresnel_dielectric :398-416 (called by dielectric_reflection :613),
+    diffuse_reflection_ggx :669-697.  rgb is accumulated in place into the diffuse tensor (:846-851): "diffuse_rgb" is rgb."""
+    trans, diff_trans = ggx_tables(normal.device)
+    alpha = torch.clamp(params["specular_roughness"], min=0.00001)
+    deta = torch.clamp(params["dielectric_eta"], min=1.000001, max=1.999999)
+    meta = torch.clamp(params["metallic_eta"], min=0.099999, max=4.999999)
+    mk = torch.clamp(params["metallic_k"], min=0.099999, max=9.999999)
+    ks = torch.clamp(params["specular_albedo"], min=0.00001)
+    kd = torch.clamp(params["diffuse_albedo"], min=0.00001)
+    eta = 1.48958738
+    c = torch.clamp(torch.sum(viewdir * normal, dim=-1, keepdim=True), min=0.00001, max=0.99999)
+    c2 = c * c
+    root = c2 + (1.0 - c2) / (eta * eta + 1e-10)
+    D = 1.0 / (np.pi * eta * eta * root * root + 1e-10)
+    tan_t = torch.sqrt(1.0 - c * c) / (c + 1e-10)
+    rt = alpha * tan_t
+    G1 = 2.0 / (1.0 + torch.hypot(rt, torch.ones_like(rt)))
+    G = G1 * G1
+    # conductor
+    s2 = 1 - c2
+    t1 = meta * meta - mk * mk - s2
+    a2pb2 = torch.sqrt(t1 * t1 + 4 * mk * mk * meta * meta)
+    a = torch.sqrt(0.5 * (a2pb2 + t1))
+    term1 = a2pb2 + c2
+    term2 = 2 * a * c
+    Rs2 = (term1 - term2) / (term1 + term2)
+    term3 = a2pb2 * c2 + s2 * s2
+    term4 = term2 * s2
+    Fm = 0.5 * (Rs2 * (term3 - term4) / (term3 + term4) + Rs2)
+    # dielectric (c > 0: scale = 1 / eta)
+    scale = 1.0 / deta
+    ct = torch.sqrt(1 - (1 - c ** 2) * (scale ** 2))
+    Rs = (c - deta * ct) / (c + deta * ct)
+    Rp = (deta * c - ct) / (deta * c + ct)
+    Fd = 0.5 * (Rs * Rs + Rp * Rp)
+    L = light / (distance * distance + 1e-10)
+    metallic_rgb = ks * Fm * L
+    dielectric_rgb = ks * Fd * D * G / (4.0 * torch.abs(c)) * L
+    spec = dielectric_rgb + metallic_rgb
+    a4 = torch.clamp(alpha, min=0.0001)
+    wc = c ** 0.25
+    wa = ((a4 - 0) / (4 - 0)) ** 0.25
+    tx = torch.floor(wc * 100).long()
+    ty = torch.floor(wa * 50).long()
+    T12 = torch.clamp(trans[torch.clamp(ty * 100 + tx, min=0, max=4999)], min=0.0, max=1.0)
+    Fdr = torch.clamp(1.0 - diff_trans[torch.clamp(ty, min=0, max=49)], min=0.0, max=1.0)
+    diffuse = L * (kd / (1.0 - Fdr + 1e-10) / np.pi) * c * T12 * T12 * (1.0 / (eta * eta))
+    rgb = diffuse + spec
+    return {"diffuse_rgb": rgb, "specular_rgb": spec, "metallic_rgb": metallic_rgb, "dielectric_rgb": dielectric_rgb, "rgb": rgb}
 
 
 # --------------------------------------------------------------------------

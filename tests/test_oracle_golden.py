@@ -323,3 +323,27 @@ def test_full_step_with_the_reference_loss(golden):
         if "g." + k in g:
             ref = g["g." + k]
             close(v.grad.numpy(), ref, 1e-4 * np.abs(ref).max(), 1e-3)
+
+
+def _composite_inputs(g, requires_grad=True):
+    names = ["diffuse_albedo", "specular_albedo", "specular_roughness", "metallic", "dielectric", "metallic_eta", "metallic_k",
+             "dielectric_eta"]
+    P = {k: T(g["p." + k]).requires_grad_(requires_grad) for k in names}
+    return T(g["light"]).requires_grad_(requires_grad), T(g["dist"]).requires_grad_(requires_grad), \
+        T(g["normal"]).requires_grad_(requires_grad), T(g["viewdir"]), P
+
+
+def test_composite_renderer_forward_backward(golden):
+    """oracle.composite_shade against the real CompositeRenderer.forward (models/renderer_ggx.py:781-858), values of all five
+    outputs and gradients w.r.t. every differentiable input, including rows that sit on the clamps."""
+    g = golden("composite")
+    light, dist, n, v, P = _composite_inputs(g)
+    out = O.composite_shade(light, dist, n, v, P)
+    for k in ("rgb", "diffuse_rgb", "specular_rgb", "metallic_rgb", "dielectric_rgb"):
+        close(out[k].detach().numpy(), g["out." + k], 1e-7, 2e-6)
+    loss = sum((out[k] * T(g["up." + k])).sum() for k in ("rgb", "specular_rgb", "metallic_rgb", "dielectric_rgb", "diffuse_rgb"))
+    names = ["diffuse_albedo", "specular_albedo", "specular_roughness", "metallic_eta", "metallic_k", "dielectric_eta"]
+    grads = torch.autograd.grad(loss, [light, dist, n] + [P[k] for k in names])
+    for k, gr in zip(["light", "dist", "normal"] + names, grads):
+        ref = g["g." + k]
+        close(gr.numpy(), ref, 1e-6 * max(np.abs(ref).max(), 1e-12), 2e-5)
