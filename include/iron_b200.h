@@ -82,6 +82,10 @@ int ironb_set_trace_mode(int mode);
 /* Truncation de-bias factor of the default tracer's tcgen05 accumulators (csrc/mlp_h16.cu: mlp16_debias); g < 0 only
  * queries.  Returns the previous factor.  IRONB_MLP_DEBIAS sets it at start-up; 0 switches the correction off. */
 float ironb_set_mlp_debias(float g);
+/* Shape of the default tracer's fused MLP kernel: 0 = automatic (64 output features per CTA in clusters of H/64 CTAs for
+ * tracer calls of at most ~8,192 rays -- the latency shape -- else 128 per CTA in clusters of H/128), 64 / 128 force one.
+ * Returns the previous setting.  IRONB_MLP_RN sets it at start-up. */
+int ironb_set_mlp_rn(int rn);
 /* C[M][ldc] = A[M][lda] * B[N][ldb]^T (fp32, K-major operands, N/K/ld multiples of 4): unit-test entry of both GEMMs. */
 int ironb_gemm_nt(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float* C, int ldc,
                   int mode, void* stream);

@@ -42,8 +42,8 @@ int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld) {
   return IRONB_OK;
 }
 
-// rows x K fp16 matrix with row pitch ld halfs -> 2-D map with a (64 x 128) SWIZZLE_128B box (mlp_h16.cu operands)
-int make_map_h(CUtensorMap* map, const void* ptr, int rows, int K, int ld) {
+// rows x K fp16 matrix with row pitch ld halfs -> 2-D map with a (64 x box_rows) SWIZZLE_128B box (mlp_h16.cu operands)
+int make_map_h(CUtensorMap* map, const void* ptr, int rows, int K, int ld, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("tcgen05 mlp: cuTensorMapEncodeTiled is unavailable"); return IRONB_ENOSUP; }
   if ((reinterpret_cast<uintptr_t>(ptr) & 15u) || (ld & 7) || K <= 0 || rows <= 0) {
@@ -52,7 +52,7 @@ int make_map_h(CUtensorMap* map, const void* ptr, int rows, int K, int ld) {
   }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2u};
-  cuuint32_t box[2] = {64u, 128u};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

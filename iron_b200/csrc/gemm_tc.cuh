@@ -342,7 +342,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn encode_fn();
 // rows x K fp32 matrix with row pitch ld floats -> 2-D map with a (BK x 128) SWIZZLE_128B box, zero fill out of bounds
 int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld);
-int make_map_h(CUtensorMap* map, const void* ptr, int rows, int K, int ld);   // fp16, 64 x 128 box
+int make_map_h(CUtensorMap* map, const void* ptr, int rows, int K, int ld, int box_rows = 128);   // fp16, 64 x box_rows box
 bool tc_enabled();
 bool pdl_enabled();       // programmatic dependent launch of the GEMM kernels (IRONB_PDL=1 switches it on; see gemm_tc.cu)
 bool split_writes_hi();   // 0 (default): raw fp32 stays as the hi operand; 1 (IRONB_SPLIT_WRITE_HI=1): store the truncated hi back

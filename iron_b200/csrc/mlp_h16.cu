@@ -39,24 +39,37 @@ namespace mlp16 {
 using namespace tc;
 
 constexpr int MAXH = 8;
-constexpr int RM = 128, RN = 128;             // rows per tile, features per CTA
+constexpr int RM = 128;                       // rows per tile
 constexpr int BKH = 64;                       // K elements per stage: one 128-byte SWIZZLE_128B row of halfs
-constexpr int TILE = 128 * 128;               // bytes of one operand box (128 rows x 128 B)
-constexpr int STAGE = 4 * TILE;
-constexpr int NSTAGE = 3;
+constexpr int TILE = 128 * 128;               // bytes of one 128-row operand box (128 rows x 128 B)
 constexpr int STG = 2 * TILE;
 constexpr int NWARP_EPI = 16;
 constexpr int NCTRL = 4;                      // warp 0 TMA loads, warp 1 MMA + TMEM alloc, warps 2 / 3 TMA stores of half 0 / 1
 constexpr int NT = (NCTRL + NWARP_EPI) * 32;  // warps 4.. epilogue
-constexpr int SMEM = NSTAGE * STAGE + STG + 1024 + 256;
 constexpr float LO_SCALE = 2048.f, LO_INV = 1.f / 2048.f, RSQRT2 = 0.70710678118654752f;
-// kind::f16: fp16 A and B (format 0), fp32 accumulate, both K-major, M = 128, N = 128
-constexpr uint32_t IDESC_F16 = (1u << 4) | ((uint32_t)(RN >> 3) << 17) | ((uint32_t)(RM >> 4) << 24);
+
+// Per-variant geometry.  RN = output features per CTA: 128 (clusters of H/128 CTAs: the throughput shape, least L2 -> SM
+// traffic per row) or 64 (clusters of H/64 CTAs: the LATENCY shape).  One 128-row tile's layer costs a CTA
+// 96 x (RN/128) x 64 cycles of MMA issue plus an epilogue over RN columns; with RN = 64 both halve, so the layer-to-layer
+// chain of a tile -- which is all that matters when a launch holds no more tiles than the GPU has clusters, i.e. for the
+// 4,096-ray training patch and for every late tracer round -- drops from ~15k to ~10k cycles, while two tiles in flight per
+// cluster (2 x 2 x 64 TMEM columns) keep the tensor pipe of each SM busy during the other tile's hand-off.
+template <int RN>
+struct Geo {
+  static constexpr int TILE_B = RN * 128;                     // bytes of one weight box (RN rows x 128 B)
+  static constexpr int STAGE = 2 * TILE + 2 * TILE_B;         // [A_hi][B_hi][A_lo][B_lo]
+  static constexpr int NSTAGE = (RN == 128) ? 3 : 4;          // 192 KiB of operand ring either way
+  static constexpr int HP = RN / 64;                          // 64-column halves (= k-blocks of the next layer) per CTA
+  static constexpr int OFF_BH = TILE, OFF_AL = TILE + TILE_B, OFF_BL = 2 * TILE + TILE_B;
+  static constexpr int SMEM = NSTAGE * STAGE + STG + 1024 + 256;
+  // kind::f16: fp16 A and B (format 0), fp32 accumulate, both K-major, M = 128, N = RN
+  static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(RN >> 3) << 17) | ((uint32_t)(RM >> 4) << 24);
+};
 
 struct Maps {
   CUtensorMap e[2];          // encoded points  [cap][Epad]   (hi, lo) fp16
   CUtensorMap u[2][2];       // activation ping-pong [cap][H]  [buffer][hi, lo] fp16
-  CUtensorMap w[MAXH][2];    // hidden-layer weights W_l [H][K_l] [layer][hi, lo] fp16
+  CUtensorMap w[MAXH][2];    // hidden-layer weights W_l [H][K_l] [layer][hi, lo] fp16, (64 x RN) boxes
 };
 
 struct Args {
@@ -140,31 +153,32 @@ struct EpiCtx {
 // One (tile, layer) unit of the epilogue for one thread: row = TMEM lane, 16 columns in each of the two 64-column halves.
 // PRE_SKIP: the layer before the skip connection (cat(h, PE) / sqrt 2 fills the columns past n_true); LAST: the last hidden
 // layer is not stored, it is dotted with the sdf row of the output layer.
-template <bool PRE_SKIP, bool LAST>
+template <int RN, bool PRE_SKIP, bool LAST>
 __device__ __forceinline__ void epi_unit(const Args& a, const EpiCtx& c, int l, int s, int m0, float mybias, float mywl,
                                          uint32_t tfree, uint32_t& se_n) {
+  constexpr int HP = Geo<RN>::HP;
   const int m = m0 + c.row;
   const int n_true = a.n_true[l];
   const float gam = a.gam[l];
   float dot = 0.f;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int c0 = h * 64 + c.blk * 16;                   // column inside the CTA's 128
+  for (int h = 0; h < HP; ++h) {
+    const int c0 = h * 64 + c.blk * 16;                   // column inside the CTA's RN
     uint32_t r0[16], rl[16];
-    const uint32_t taddr = c.tmem + ((uint32_t)(c.q * 32) << 16) + (uint32_t)s * 256u + (uint32_t)c0;
+    const uint32_t taddr = c.tmem + ((uint32_t)(c.q * 32) << 16) + (uint32_t)s * (uint32_t)(RN * (a.nhh + 1)) + (uint32_t)c0;
     tmem_ld16(taddr, r0);
     if (a.nhh == 2) {
       uint32_t r1[16];
-      tmem_ld16(taddr + 128u, r1);
-      tmem_ld16(taddr + 256u, rl);
+      tmem_ld16(taddr + (uint32_t)RN, r1);
+      tmem_ld16(taddr + 2u * (uint32_t)RN, rl);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
       for (int i = 0; i < 16; ++i) r0[i] = __float_as_uint(__fadd_rn(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
     } else {
-      tmem_ld16(taddr + 128u, rl);
+      tmem_ld16(taddr + (uint32_t)RN, rl);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     }
-    if (h == 1) {                                         // this warp has drained its part of the slot's accumulators
+    if (h == HP - 1) {                                    // this warp has drained its part of the slot's accumulators
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (c.lane == 0) mbar_arrive(tfree);
@@ -240,7 +254,10 @@ __device__ __forceinline__ void epi_unit(const Args& a, const EpiCtx& c, int l, 
   const int sp = two ? j : ((nslots == 2) ? ((l + 1) & 1) : 0);             \
   (void)sp;
 
+template <int RN>
 __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ Maps maps, const Args a) {
+  typedef Geo<RN> GEO;
+  constexpr int STAGE = GEO::STAGE, NSTAGE = GEO::NSTAGE, HP = GEO::HP;
   int M = a.rows_cap;
   if (a.m_dev != nullptr) {
     const int md = *a.m_dev * a.m_mul;
@@ -251,7 +268,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
   const int ntiles = (M + RM - 1) / RM;
   const int rank = blockIdx.x, n0 = rank * RN;
   const int nslots = (a.nhh == 1) ? 2 : 1;
-  const uint32_t ncol_slot = 256u;
+  const uint32_t ncol_slot = (uint32_t)(RN * (a.nhh + 1));
 
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -314,30 +331,30 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
       const int C = a.C;
       int ib = 0;                                         // stages whose barrier is armed and whose weight boxes are issued
       for (int ia = 0; ia < nk; ++ia) {
-        const bool wait_pt = (l > 0) && (ia == 0 || ia == C);
+        const bool wait_pt = (l > 0) && (ia % C == 0) && (ia / C < HP);
         const int ahead = wait_pt ? (ia + a.preb < nk ? ia + a.preb : nk) : ia + 1;
         for (; ib < ahead; ++ib) {                        // weights do not depend on the previous layer: run ahead
           const uint32_t sidx = (it + ib) % NSTAGE, ph = ((it + ib) / NSTAGE) & 1u;
-          const int kb = (l == 0) ? ib : 2 * (ib % C) + (ib / C);
+          const int kb = (l == 0) ? ib : HP * (ib % C) + (ib / C);
           mbar_wait(empty(sidx), ph ^ 1u);
           const uint32_t st = base + sidx * STAGE;
           if (leader) {
             mbar_arrive_expect_tx(full(sidx), STAGE);
-            tma_load_2d(st + TILE, mBh, kb * BKH, n0, full(sidx));
-            tma_load_2d(st + 3 * TILE, mBl, kb * BKH, n0, full(sidx));
+            tma_load_2d(st + GEO::OFF_BH, mBh, kb * BKH, n0, full(sidx));
+            tma_load_2d(st + GEO::OFF_BL, mBl, kb * BKH, n0, full(sidx));
           }
         }
         if (wait_pt) {
-          const int h = (ia == 0) ? 0 : 1;
+          const int h = ia / C;
           mbar_wait_cluster(ready(sp, h), (rdy_bits >> (sp * 2 + h)) & 1u);
           rdy_bits ^= 1u << (sp * 2 + h);
         }
         const uint32_t sidx = (it + ia) % NSTAGE;
-        const int kb = (l == 0) ? ia : 2 * (ia % C) + (ia / C);
+        const int kb = (l == 0) ? ia : HP * (ia % C) + (ia / C);
         const uint32_t st = base + sidx * STAGE;
         if (leader) {
           tma_load_2d(st, mAh, kb * BKH, m0, full(sidx));
-          tma_load_2d(st + 2 * TILE, mAl, kb * BKH, m0, full(sidx));
+          tma_load_2d(st + GEO::OFF_AL, mAl, kb * BKH, m0, full(sidx));
         }
       }
       it += nk;
@@ -356,7 +373,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
       ++free_n[s];
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = tmem + (uint32_t)s * ncol_slot;
-      const uint32_t acc_lo = acc + 128u * nhh;
+      const uint32_t acc_lo = acc + (uint32_t)RN * nhh;
       for (int i = 0; i < nk; ++i) {
         const uint32_t sidx = (it + i) % NSTAGE, ph = ((it + i) / NSTAGE) & 1u;
         if (stamp && leader && i == 0 && t0 == 0 && j == 0) a.dbg[l * 8 + 0] = clock64();
@@ -364,18 +381,18 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
         if (stamp && leader && i == 0 && t0 == 0 && j == 0) a.dbg[l * 8 + 1] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = base + sidx * STAGE;
-        const uint64_t a_hi = make_desc(st), b_hi = make_desc(st + TILE);
-        const uint64_t a_lo = make_desc(st + 2 * TILE), b_lo = make_desc(st + 3 * TILE);
+        const uint64_t a_hi = make_desc(st), b_hi = make_desc(st + GEO::OFF_BH);
+        const uint64_t a_lo = make_desc(st + GEO::OFF_AL), b_lo = make_desc(st + GEO::OFF_BL);
         const int kmax = ksteps - i * (BKH / 16);         // k-steps of this stage that hold data (layer 0: K = 40)
 #pragma unroll
         for (int kk = 0; kk < BKH / 16; ++kk) {
           const uint32_t g = (uint32_t)(i * (BKH / 16) + kk);
           const uint64_t adv = (uint64_t)(kk * 2);        // 16 halfs = 32 B = 2 x 16 B along the swizzled row
-          const uint32_t acc_hh = acc + ((nhh == 2u && (g & 1u)) ? 128u : 0u);
+          const uint32_t acc_hh = acc + ((nhh == 2u && (g & 1u)) ? (uint32_t)RN : 0u);
           if (leader && kk < kmax) {
-            tc_mma_f16(acc_hh, a_hi + adv, b_hi + adv, IDESC_F16, g >= nhh ? 1u : 0u);
-            tc_mma_f16(acc_lo, a_lo + adv, b_hi + adv, IDESC_F16, g >= 1u ? 1u : 0u);
-            tc_mma_f16(acc_lo, a_hi + adv, b_lo + adv, IDESC_F16, 1u);
+            tc_mma_f16(acc_hh, a_hi + adv, b_hi + adv, GEO::IDESC, g >= nhh ? 1u : 0u);
+            tc_mma_f16(acc_lo, a_lo + adv, b_hi + adv, GEO::IDESC, g >= 1u ? 1u : 0u);
+            tc_mma_f16(acc_lo, a_hi + adv, b_lo + adv, GEO::IDESC, 1u);
           }
         }
         if (leader) tc_commit(empty(sidx));
@@ -391,6 +408,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
     const int h = warp - 2;
     const bool leader = elect_one();
     uint32_t sf_n = 0;
+    if (h < HP)
     MLP16_FOR_UNITS {
       if (l == a.n_hidden - 1) continue;
       MLP16_UNIT_SLOTS
@@ -431,17 +449,18 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
       // bias (and, for the last layer, the sdf-row weights) of this warp's 2 x 16 columns: one value per lane, fetched
       // BEFORE the accumulator wait so the global-load latency hides behind the mainloop; broadcast by shuffle below
       const int mycol = n0 + (lane >> 4) * 64 + c.blk * 16 + (lane & 15);
-      const float mybias = __ldg(a.bias[l] + mycol);
-      const float mywl = last ? __ldg(a.w_last + mycol) : 0.f;
+      const bool mine = (lane >> 4) < HP;                   // RN = 64: lanes 16..31 hold no column
+      const float mybias = mine ? __ldg(a.bias[l] + mycol) : 0.f;
+      const float mywl = (last && mine) ? __ldg(a.w_last + mycol) : 0.f;
       mbar_wait(acc_full(s), acc_n[s] & 1u);
       ++acc_n[s];
       const bool st = stamp && threadIdx.x == NCTRL * 32 && t0 == 0 && j == 0;
       if (st) a.dbg[l * 8 + 3] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tfree = tmem_free(s);
-      if (last) epi_unit<false, true>(a, c, l, s, m0, mybias, mywl, tfree, se_n);
-      else if (pre_skip) epi_unit<true, false>(a, c, l, s, m0, mybias, mywl, tfree, se_n);
-      else epi_unit<false, false>(a, c, l, s, m0, mybias, mywl, tfree, se_n);
+      if (last) epi_unit<RN, false, true>(a, c, l, s, m0, mybias, mywl, tfree, se_n);
+      else if (pre_skip) epi_unit<RN, true, false>(a, c, l, s, m0, mybias, mywl, tfree, se_n);
+      else epi_unit<RN, false, false>(a, c, l, s, m0, mybias, mywl, tfree, se_n);
       if (st) a.dbg[l * 8 + 4] = clock64();
     }
   }
@@ -497,13 +516,101 @@ int mlp16_nhh() {
   return g_nhh;
 }
 
-// maps: e[2], u[2][2], w[n_hidden][2] (hi, lo), all fp16 with 64 x 128 boxes.
+// Co-resident clusters of C CTAs of variant RN on this device (GPC packing decides, not SMs / C); < 0: the shape cannot be
+// scheduled.  First use also raises the kernel's dynamic shared-memory limit.
+template <int RN>
+static int resident_clusters(int C) {
+  using namespace mlp16;
+  static int resident[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (C < 1 || C > 8) return -1;
+  if (resident[C] == 0) {
+    int nc = -1;
+    if (cudaFuncSetAttribute(mlp_h16_kernel<RN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<RN>::SMEM) == cudaSuccess) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cfg.blockDim = dim3(NT, 1, 1);
+      cfg.dynamicSmemBytes = Geo<RN>::SMEM;
+      cfg.gridDim = dim3((unsigned)C, (unsigned)(num_sms() / C), 1);
+      if (cudaOccupancyMaxActiveClusters(&nc, mlp_h16_kernel<RN>, &cfg) != cudaSuccess || nc < 1) nc = -1;
+    }
+    (void)cudaGetLastError();
+    const char* ov = getenv("IRONB_MLP_CLUSTERS");
+    if (nc > 0 && ov && atoi(ov) > 0) nc = atoi(ov);
+    resident[C] = nc;
+  }
+  return resident[C];
+}
+
+// Narrow (RN = 64, clusters of H/64 CTAs) or wide (RN = 128, clusters of H/128 CTAs) variant for a tracer call over `rays`
+// rays: the narrow one wins while a launch cannot fill the GPU's clusters with two tiles each, i.e. for small patches.
+// IRONB_MLP_RN=64 / 128 forces one (if schedulable).
+static int g_rn_force = -1;
+int mlp16_pick_rn(const ironb_mlp_layout* lay, int64_t rays) {
+  if (g_rn_force < 0) {
+    const char* e = getenv("IRONB_MLP_RN");
+    g_rn_force = (e && atoi(e) == 64) ? 64 : (e && atoi(e) == 128) ? 128 : 0;
+  }
+  const int H = lay->d_hidden;
+  const bool narrow_ok = H % 64 == 0 && H / 64 <= 8 && resident_clusters<64>(H / 64) > 0;
+  const bool wide_ok = H % 128 == 0 && resident_clusters<128>(H / 128) > 0;
+  if (g_rn_force == 64 && narrow_ok) return 64;
+  if (g_rn_force == 128 && wide_ok) return 128;
+  // Measured (tests/probe_mlp_rn.py, profiles/r2_mlp_h16_rn.md): a tile's layer is bound by the SM's L2 ingest (~64 B/clk:
+  // 512 KiB of operands per CTA and layer at RN = 128, 384 KiB at RN = 64), not by the tensor pipe, so the narrow shape
+  // only pays while every tile has a cluster of its own (H = 512: 15 resident 8-CTA clusters -> at most 1,920 rays;
+  // H = 256: 33 4-CTA clusters); beyond that its 1.5x operand traffic per row loses (3.6 vs 2.4 ms at 4,096 rays, H = 512).
+  if (narrow_ok && (!wide_ok || rays <= (int64_t)mlp16::RM * resident_clusters<64>(H / 64))) return 64;
+  return 128;
+}
+
+int mlp16_set_rn(int rn) {
+  const int prev = g_rn_force < 0 ? 0 : g_rn_force;
+  g_rn_force = (rn == 64 || rn == 128) ? rn : 0;
+  return prev;
+}
+
+template <int RN>
+static int launch_variant(const mlp16::Maps& maps, mlp16::Args& a, int C, int rows_cap, cudaStream_t st) {
+  using namespace mlp16;
+  typedef Geo<RN> GEO;
+  { static int preb = -1;
+    if (preb < 0) { const char* e = getenv("IRONB_MLP_PREB"); preb = (e && atoi(e) >= 1 && atoi(e) <= GEO::NSTAGE) ? atoi(e) : GEO::NSTAGE; }
+    a.preb = preb; }
+  const int res = resident_clusters<RN>(C);
+  if (res < 0) return IRONB_ENOSUP;                         // this cluster shape cannot be scheduled here
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cfg.blockDim = dim3(NT, 1, 1);
+  cfg.dynamicSmemBytes = GEO::SMEM;
+  cfg.stream = st;
+  const int64_t tiles = ceil_div64(rows_cap, RM);
+  cfg.gridDim = dim3((unsigned)C, (unsigned)(tiles < res ? tiles : res), 1);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_h16_kernel<RN>, maps, a);
+  note_launch();
+  if (e != cudaSuccess) { set_error("mlp_h16<%d> launch: %s", RN, cudaGetErrorString(e)); return (int)e; }
+  return IRONB_OK;
+}
+
+// maps: e[2], u[2][2] with (64 x 128) boxes; w[n_hidden][2] (hi, lo) with (64 x rn) boxes: the caller builds them for the
+// variant `rn` it got from mlp16_pick_rn.  Returns IRONB_ENOSUP if that variant's cluster shape cannot be scheduled.
 int launch_trace_mlp_h16(const ironb_mlp_layout* lay, const float* packed, const CUtensorMap* mE, const CUtensorMap* mU,
                          const CUtensorMap* mW, const void* Ehi, const void* Elo, void* const* Uhi, void* const* Ulo,
-                         float* Fpart, int rows_cap, int cap, const int* m_dev, int m_mul, cudaStream_t st) {
+                         float* Fpart, int rows_cap, int cap, const int* m_dev, int m_mul, int rn, cudaStream_t st) {
   using namespace mlp16;
   if (!trace_mlp_fused_supported(lay)) return IRONB_ENOSUP;
-  const int H = lay->d_hidden, last = lay->n_lin - 1, C = H / 128;
+  if (rn != 64 && rn != 128) return IRONB_EINVAL;
+  const int H = lay->d_hidden, last = lay->n_lin - 1, C = H / rn;
+  if (C < 1 || C > 8) return IRONB_ENOSUP;
   static Maps maps;
   maps.e[0] = mE[0]; maps.e[1] = mE[1];
   for (int b = 0; b < 2; ++b) { maps.u[b][0] = mU[b * 2]; maps.u[b][1] = mU[b * 2 + 1]; }
@@ -526,42 +633,20 @@ int launch_trace_mlp_h16(const ironb_mlp_layout* lay, const float* packed, const
   a.nhh = mlp16_nhh();
   for (int l = 0; l < last; ++l)
     a.gam[l] = mlp16_debias() * (float)((lay->in_pad[l] + 15) / 16) / (float)a.nhh * 5.9604645e-8f;   // g * n_steps * 2^-24
-  { static int preb = -1; if (preb < 0) { const char* e = getenv("IRONB_MLP_PREB"); preb = (e && atoi(e) >= 1 && atoi(e) <= NSTAGE) ? atoi(e) : NSTAGE; } a.preb = preb; }
   a.dbg = g_mlp_dbg;
-
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cfg.blockDim = dim3(NT, 1, 1);
-  cfg.dynamicSmemBytes = SMEM;
-  cfg.stream = st;
-  static int resident[5] = {0, 0, 0, 0, 0};   // co-resident clusters per cluster size (GPC packing decides, not SMs / C)
-  if (resident[C] == 0) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_h16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) { set_error("mlp_h16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    cfg.gridDim = dim3((unsigned)C, (unsigned)(num_sms() / C), 1);
-    int nc = 0;
-    e = cudaOccupancyMaxActiveClusters(&nc, mlp_h16_kernel, &cfg);
-    if (e != cudaSuccess || nc < 1) { (void)cudaGetLastError(); nc = num_sms() / C; }
-    const char* ov = getenv("IRONB_MLP_CLUSTERS");
-    if (ov && atoi(ov) > 0) nc = atoi(ov);
-    resident[C] = nc;
-  }
-  const int64_t tiles = ceil_div64(rows_cap, RM);
-  cfg.gridDim = dim3((unsigned)C, (unsigned)(tiles < resident[C] ? tiles : resident[C]), 1);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_h16_kernel, maps, a);
-  note_launch();
-  if (e != cudaSuccess) { set_error("mlp_h16 launch: %s", cudaGetErrorString(e)); return (int)e; }
-  return IRONB_OK;
+  return rn == 64 ? launch_variant<64>(maps, a, C, rows_cap, st) : launch_variant<128>(maps, a, C, rows_cap, st);
 }
 
 }  // namespace ironb
 
 extern "C" float ironb_set_mlp_debias(float g) { return ironb::mlp16_set_debias(g); }
+extern "C" int ironb_set_mlp_rn(int rn) { return ironb::mlp16_set_rn(rn); }
+// diagnostic: co-resident clusters of the MLP kernel variant `rn` for hidden width H on the current device (< 0: unschedulable)
+extern "C" int ironb_debug_mlp_resident_clusters(int rn, int H) {
+  if (rn == 64) return ironb::resident_clusters<64>(H / 64);
+  if (rn == 128) return ironb::resident_clusters<128>(H / 128);
+  return -1;
+}
 
 // debugging aid: IRONB_MLP_DBG timeline of the fused MLP kernel (cluster 0, rank 0, first tile), 8 stamps per layer
 extern "C" int ironb_debug_mlp_timeline(long long* host_out, int n) {

@@ -26,9 +26,10 @@ namespace ironb {
 
 bool trace_mlp_fused_supported(const ironb_mlp_layout* lay);
 // the fused MLP evaluation (mlp_h16.cu): operands are fp16 hi and fp16 (x - hi) * 2^11
+int mlp16_pick_rn(const ironb_mlp_layout* lay, int64_t rays);
 int launch_trace_mlp_h16(const ironb_mlp_layout* lay, const float* packed, const CUtensorMap* mE, const CUtensorMap* mU,
                          const CUtensorMap* mW, const void* Ehi, const void* Elo, void* const* Uhi, void* const* Ulo,
-                         float* Fpart, int rows_cap, int cap, const int* m_dev, int m_mul, cudaStream_t st);
+                         float* Fpart, int rows_cap, int cap, const int* m_dev, int m_mul, int rn, cudaStream_t st);
 
 namespace {
 
@@ -339,7 +340,7 @@ BWs carve_b(const ironb_mlp_layout* lay, int64_t N, unsigned char* base) {
   w.root_ray = (int*)take(N * 4); w.root_lo = (float*)take(N * 4); w.root_hi = (float*)take(N * 4);
   w.root_mid = (float*)take(N * 4); w.root_work = (int*)take(N * 4);
   w.Ehi = (float*)take(cap * Epad * 4); w.Elo = (float*)take(cap * Epad * 4);
-  w.Fpart = (float*)take(cap * 4 * 16);
+  w.Fpart = (float*)take(cap * 4 * 32);          // up to 4 x 8 partial sums of the sdf row per work item
   for (int b = 0; b < 2; ++b) { w.Uhi[b] = (float*)take(cap * (int64_t)H * 4); w.Ulo[b] = (float*)take(cap * (int64_t)H * 4); }
   w.bytes = off;
   return w;
@@ -400,7 +401,8 @@ int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float*
   A.root_ray = w.root_ray; A.root_lo = w.root_lo; A.root_hi = w.root_hi; A.root_mid = w.root_mid; A.root_work = w.root_work;
   A.Ehi = w.Ehi; A.Elo = w.Elo;
   A.cap_groups = (int)(w.cap / 32);
-  const int C = H / 128;
+  int rn = mlp16_pick_rn(lay, N);                 // features per CTA of the MLP kernel: 64 (latency shape) or 128
+  int C = H / rn;
   A.Fpart = w.Fpart; A.b_last = packed + lay->off_b[last]; A.nparts = 4 * C; A.cap = (int)w.cap;
 
   // The fp16x2-split weight copies come with the packed buffer (ironb_mlp_fold writes them once per parameter update;
@@ -409,7 +411,9 @@ int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float*
   for (int l = 0; l < last; ++l)
     if (lay->off_h16[l] <= 0) { set_error("trace: the layout carries no fp16 weight copies (layer %d)", l); return IRONB_EINVAL; }
   CUtensorMap mE[2], mU[4], mW[2 * IRONB_MAX_LIN];
-  auto mk = [&](CUtensorMap* m, const void* p, int rows, int K, int ld) -> int { return tc::make_map_h(m, p, rows, K, ld); };
+  auto mk = [&](CUtensorMap* m, const void* p, int rows, int K, int ld, int box_rows = 128) -> int {
+    return tc::make_map_h(m, p, rows, K, ld, box_rows);
+  };
   if ((rc = mk(&mE[0], w.Ehi, (int)w.cap, Epad, Epad))) return rc;
   if ((rc = mk(&mE[1], w.Elo, (int)w.cap, Epad, Epad))) return rc;
   for (int b = 0; b < 2; ++b) {
@@ -419,15 +423,15 @@ int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float*
   for (int l = 0; l < last; ++l) {
     const __half* whi = reinterpret_cast<const __half*>(packed + lay->off_h16[l]);
     const __half* wlo = whi + (int64_t)lay->out_pad[l] * lay->in_pad[l];
-    if ((rc = mk(&mW[l * 2], whi, lay->out_pad[l], lay->in_pad[l], lay->in_pad[l]))) return rc;
-    if ((rc = mk(&mW[l * 2 + 1], wlo, lay->out_pad[l], lay->in_pad[l], lay->in_pad[l]))) return rc;
+    if ((rc = mk(&mW[l * 2], whi, lay->out_pad[l], lay->in_pad[l], lay->in_pad[l], rn))) return rc;
+    if ((rc = mk(&mW[l * 2 + 1], wlo, lay->out_pad[l], lay->in_pad[l], lay->in_pad[l], rn))) return rc;
   }
   // one MLP evaluation of the first (*m_dev x m_mul) rows: all hidden layers + the sdf row in one cluster launch
   // (mlp_h16.cu: fp16x2 split, two tiles in flight)
   auto mlp = [&](int rows_cap, const int* m_dev, int m_mul) -> int {
     void* uh[2] = {w.Uhi[0], w.Uhi[1]};
     void* ul[2] = {w.Ulo[0], w.Ulo[1]};
-    return launch_trace_mlp_h16(lay, packed, mE, mU, mW, w.Ehi, w.Elo, uh, ul, w.Fpart, rows_cap, (int)w.cap, m_dev, m_mul, st);
+    return launch_trace_mlp_h16(lay, packed, mE, mU, mW, w.Ehi, w.Elo, uh, ul, w.Fpart, rows_cap, (int)w.cap, m_dev, m_mul, rn, st);
   };
   const int nb = (int)ceil_div64(N * PE_T, 256);    // st_* / bis_* kernels: PE_T threads per work item
   const int nb1 = (int)ceil_div64(N, 256);

@@ -51,16 +51,20 @@ def gemm_mode(request):
     lib.ironb_set_gemm_mode(prev)
 
 
-TRACE_MODES = {"fused-ffma": 0, "batched-tcgen05": 2}
+TRACE_MODES = {"fused-ffma": 0, "batched-tcgen05": 2, "batched-tcgen05-wide": 2}
 
 
 @pytest.fixture(params=list(TRACE_MODES))
 def trace_mode(request):
     """Both tracer implementations: the fused persistent fp32-FFMA kernels (exact fp32 association) and the batched
-    tcgen05 rounds with fp16x2-split operands and two tiles in flight (default).  (The 3xTF32 predecessor of the
-    latter was retired in round 2.)"""
+    tcgen05 rounds with fp16x2-split operands and two tiles in flight (default; both cluster shapes of its MLP kernel).
+    (The 3xTF32 predecessor of the latter was retired in round 2.)"""
     from iron_b200 import _lib
     lib = _lib.load()
     prev = lib.ironb_set_trace_mode(TRACE_MODES[request.param])
+    # the fused MLP kernel has two shapes (csrc/mlp_h16.cu): automatic selection takes the 64-column one for the small ray
+    # counts of these tests; "-wide" forces the 128-column one, which large patches use
+    prev_rn = lib.ironb_set_mlp_rn(128 if request.param.endswith("-wide") else 0)
     yield request.param
+    lib.ironb_set_mlp_rn(prev_rn)
     lib.ironb_set_trace_mode(prev)
