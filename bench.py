@@ -368,7 +368,7 @@ def run_ours(args):
     if args.tracer != "default":
         lib.ironb_set_trace_mode({"batched": 2, "fused": 0}[args.tracer])
     if args.gemm != "default":
-        lib.ironb_set_gemm_mode(1 if args.gemm == "tcgen05" else 0)
+        lib.ironb_set_gemm_mode({"tcgen05": 2, "tf32": 1, "ffma": 0}[args.gemm])
     _prev = lib.ironb_set_trace_mode(2)
     lib.ironb_set_trace_mode(_prev)
     tracer_impl = {2: "batched tcgen05 (fp16x2 split)", 0: "fused persistent fp32 FFMA"}[_prev]
@@ -800,7 +800,7 @@ def main():
                     help="dense: shade every ray and mask (no hit-count read-back, host runs ahead of the tracer); compact: the "
                          "reference's order (compact the hits first: one host sync per step)")
     ap.add_argument("--tracer", default="default", choices=["default", "batched", "fused"])
-    ap.add_argument("--gemm", default="default", choices=["default", "tcgen05", "ffma"])
+    ap.add_argument("--gemm", default="default", choices=["default", "tcgen05", "tf32", "ffma"])
     args = ap.parse_args()
     IMAGE_LOSS[0] = args.loss
     if args.impl == "reference":

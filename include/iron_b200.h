@@ -60,9 +60,11 @@ typedef struct ironb_mlp_layout {
   int64_t off_wt[IRONB_MAX_LIN];   /* W_l^T [in_pad][out_pad] */
   int64_t off_b[IRONB_MAX_LIN];    /* b_l  [out_pad] */
   int64_t packed_floats;           /* size of the fp32 part (W, W^T, b of every layer): the size of a dpacked buffer */
-  int64_t off_h16[IRONB_MAX_LIN];  /* SDF nets, hidden layers: fp16x2-split copy of W_l written by ironb_mlp_fold -- hi
-                                      [out_pad][in_pad] halfs, then lo = fp16((w - hi) * 2^11), same shape; float offset.
-                                      The default tracer's tcgen05 operands (csrc/mlp_h16.cu); 0 = absent */
+  int64_t off_h16[IRONB_MAX_LIN];  /* fp16x2-split copy of W_l written by ironb_mlp_fold -- hi [out_pad][in_pad] halfs, then
+                                      lo = fp16((w - hi) * 2^11), same shape; float offset into the packed buffer.  The
+                                      tensor-core operands of the default tracer (csrc/mlp_h16.cu) and of the forward-type
+                                      GEMMs (csrc/gemm_h16.cuh) */
+  int64_t off_h16t[IRONB_MAX_LIN]; /* the same for W_l^T [in_pad][out_pad] (SDF nets: the input-gradient chain); 0 = absent */
   int64_t packed_total_floats;     /* size of the packed buffer ironb_mlp_fold writes (fp32 part + fp16 copies), in floats */
 } ironb_mlp_layout;
 
@@ -72,8 +74,10 @@ int ironb_version(void);
 int64_t ironb_launch_count(void);
 
 /* GEMM arithmetic of the differentiable part (get_all forward / double backward, material MLPs):
- * 1 = tcgen05 3xTF32 split (tensor cores, fp32-grade accuracy; the default), 0 = fp32 FFMA tiles.
- * Returns the previous mode.  The environment variable IRONB_GEMM=simt selects 0 at start-up. */
+ * 2 = tcgen05 with fp16x2 pre-split operands for the forward-type products (get_all forward, input-gradient chain,
+ *     material forward: O(1) operands) and the 3xTF32 split for products with gradient operands (the default),
+ * 1 = tcgen05 3xTF32 split everywhere, 0 = fp32 FFMA tiles.  All fp32-grade.  Returns the previous mode.
+ * IRONB_GEMM=simt / tf32 selects 0 / 1 at start-up. */
 int ironb_set_gemm_mode(int mode);
 /* Tracer implementation: 2 = batched tcgen05 rounds, fp16x2-split operands (default); 0 = fused persistent fp32-FFMA
  * kernels (exact fp32 association).  Returns the previous mode.  IRONB_TRACE=fused selects 0 at start-up.
@@ -89,6 +93,11 @@ int ironb_set_mlp_rn(int rn);
 /* C[M][ldc] = A[M][lda] * B[N][ldb]^T (fp32, K-major operands, N/K/ld multiples of 4): unit-test entry of both GEMMs. */
 int ironb_gemm_nt(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float* C, int ldc,
                   int mode, void* stream);
+
+/* The same product on fp16x2 PRE-SPLIT operands (csrc/gemm_h16.cuh): hi = fp16(x), lo = fp16((x - hi) * 2^11) as separate
+ * K-major half arrays, pitches in halfs (multiples of 8).  Unit-test entry of the forward-type tensor-core GEMM. */
+int ironb_gemm_nt_h16(const void* Ah, const void* Al, int lda, const void* Bh, const void* Bl, int ldb, int M, int N, int K,
+                      float* C, int ldc, void* stream);
 
 /* C[Nd][ldc] += A[M][lda]^T * B[M][ldb] (the weight-gradient product; C is accumulated): unit-test entry. */
 int64_t ironb_gemm_tn_scratch_bytes(int M, int Nd, int Kd);

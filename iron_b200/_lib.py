@@ -21,7 +21,7 @@ class MlpLayout(C.Structure):
         ("in_pad", C.c_int32 * MAX_LIN), ("out_pad", C.c_int32 * MAX_LIN),
         ("off_w", C.c_int64 * MAX_LIN), ("off_wt", C.c_int64 * MAX_LIN), ("off_b", C.c_int64 * MAX_LIN),
         ("packed_floats", C.c_int64),
-        ("off_h16", C.c_int64 * MAX_LIN), ("packed_total_floats", C.c_int64),
+        ("off_h16", C.c_int64 * MAX_LIN), ("off_h16t", C.c_int64 * MAX_LIN), ("packed_total_floats", C.c_int64),
     ]
 
 
@@ -50,6 +50,7 @@ _PROTOS = {
     "ironb_set_mlp_debias": (_F, [_F]),
     "ironb_set_mlp_rn": (_INT, [_INT]),
     "ironb_gemm_nt": (_INT, [_P, _INT, _P, _INT, _INT, _INT, _INT, _P, _INT, _INT, _P]),
+    "ironb_gemm_nt_h16": (_INT, [_P, _P, _INT, _P, _P, _INT, _INT, _INT, _INT, _P, _INT, _P]),
     "ironb_gemm_tn_scratch_bytes": (_I64, [_INT, _INT, _INT]),
     "ironb_gemm_tn": (_INT, [_P, _INT, _P, _INT, _INT, _INT, _INT, _P, _INT, _INT, _P, _P]),
     "ironb_sdf_layout": (_INT, [_INT, _INT, _INT, _INT, _INT, _INT, _F, _F, _LAY]),

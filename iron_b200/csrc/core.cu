@@ -46,12 +46,16 @@ static void finish_layout(ironb_mlp_layout* L) {
     off = (off + 63) / 64 * 64;   // keep every block 256-byte aligned
   }
   L->packed_floats = off;
-  // fp16x2-split copies of the hidden-layer weights of an SDF net (the tracer's tensor-core operands), written by the fold
-  for (int l = 0; l < L->n_lin; ++l) L->off_h16[l] = 0;
-  if (L->kind == 0) {
-    for (int l = 0; l + 1 < L->n_lin; ++l) {
-      L->off_h16[l] = off;
-      off += (int64_t)L->out_pad[l] * L->in_pad[l];     // hi + lo halfs = out_pad * in_pad floats
+  // fp16x2-split copies of the weights (tensor-core operands of the tracer's MLP kernel and of the forward-type GEMMs),
+  // written by the fold: W_l for every layer; W_l^T too for SDF nets (the input-gradient chain multiplies by it)
+  for (int l = 0; l < L->n_lin; ++l) {
+    L->off_h16[l] = off;
+    off += (int64_t)L->out_pad[l] * L->in_pad[l];       // hi + lo halfs = out_pad * in_pad floats
+    off = (off + 63) / 64 * 64;
+    L->off_h16t[l] = 0;
+    if (L->kind == 0) {
+      L->off_h16t[l] = off;
+      off += (int64_t)L->out_pad[l] * L->in_pad[l];
       off = (off + 63) / 64 * 64;
     }
   }

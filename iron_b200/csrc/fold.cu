@@ -45,18 +45,19 @@ __global__ void __launch_bounds__(256) fold_kernel(ironb_mlp_layout L, FoldArgs 
   }
   float* W = packed + L.off_w[l] + (int64_t)n * Kp;
   float* WT = packed + L.off_wt[l] + n;
-  // fp16x2-split copy for the tracer's tensor cores (SDF hidden layers): hi = fp16(w), lo = fp16((w - hi) * 2^11)
+  // fp16x2-split copies for the tensor cores: hi = fp16(w), lo = fp16((w - hi) * 2^11); the lo block follows the hi block
   __half* Whi = L.off_h16[l] > 0 ? reinterpret_cast<__half*>(packed + L.off_h16[l]) + (int64_t)n * Kp : nullptr;
-  __half* Wlo = Whi ? Whi + (int64_t)Np * Kp : nullptr;   // the lo block follows the hi block
+  __half* Wlo = Whi ? Whi + (int64_t)Np * Kp : nullptr;
+  __half* WThi = L.off_h16t[l] > 0 ? reinterpret_cast<__half*>(packed + L.off_h16t[l]) + n : nullptr;
+  __half* WTlo = WThi ? WThi + (int64_t)Np * Kp : nullptr;
   for (int k = lane; k < K; k += 32) {
     float w = v[k] * sc;
     W[k] = w;
     WT[(int64_t)k * Np] = w;
-    if (Whi) {
-      const __half h = __float2half_rn(w);
-      Whi[k] = h;
-      Wlo[k] = __float2half_rn((w - __half2float(h)) * 2048.f);
-    }
+    const __half h = __float2half_rn(w);
+    const __half lo = __float2half_rn((w - __half2float(h)) * 2048.f);
+    if (Whi) { Whi[k] = h; Wlo[k] = lo; }
+    if (WThi) { WThi[(int64_t)k * Np] = h; WTlo[(int64_t)k * Np] = lo; }
   }
   if (lane == 0) packed[L.off_b[l] + n] = A.b[l] ? A.b[l][n] : 0.f;
 }

@@ -5,7 +5,7 @@
 #include <atomic>
 
 #include "gemm.cuh"
-#include "gemm_tc.cuh"
+#include "gemm_h16.cuh"
 
 namespace ironb {
 namespace tc {
@@ -62,15 +62,17 @@ int make_map_h(CUtensorMap* map, const void* ptr, int rows, int K, int ld, int b
 }
 
 static std::atomic<int> g_mode{-1};
-bool tc_enabled() {
+static int mode_now() {
   int m = g_mode.load(std::memory_order_relaxed);
   if (m < 0) {
     const char* e = getenv("IRONB_GEMM");
-    m = (e && (e[0] == 's' || e[0] == 'S' || e[0] == '0')) ? 0 : 1;   // IRONB_GEMM=simt selects the FFMA GEMM
+    // IRONB_GEMM=simt: FFMA GEMMs; =tf32: 3xTF32 everywhere; default: fp16x2 forward-type products + 3xTF32 gradients
+    m = (e && (e[0] == 's' || e[0] == 'S' || e[0] == '0')) ? 0 : (e && (e[0] == 't' || e[0] == 'T' || e[0] == '1')) ? 1 : 2;
     g_mode.store(m, std::memory_order_relaxed);
   }
-  return m == 1;
+  return m;
 }
+bool tc_enabled() { return mode_now() >= 1; }
 bool pdl_enabled() {
 #ifdef IRONB_ENABLE_PDL
   // measured (bench.py, graph replay with three parallel streams): 5.12 ms/step with PDL, 4.99 without -- the early CTAs of
@@ -99,12 +101,15 @@ bool split_writes_hi() {
   return m == 1;
 }
 int set_mode(int mode) {
-  int prev = tc_enabled() ? 1 : 0;
-  g_mode.store(mode ? 1 : 0, std::memory_order_relaxed);
+  int prev = mode_now();
+  g_mode.store(mode <= 0 ? 0 : (mode == 1 ? 1 : 2), std::memory_order_relaxed);
   return prev;
 }
+int mode() { return mode_now(); }
 
 }  // namespace tc
+
+int gemm_mode() { return tc::mode(); }
 
 namespace {
 struct EpiStore {
@@ -129,6 +134,18 @@ extern "C" int ironb_gemm_nt(const float* A, int lda, const float* B, int ldb, i
   if (mode == 1) return tc::launch_gemm_nt_tc(A, lda, B, ldb, M, N, K, ep, as_stream(stream), "gemm_nt (tcgen05)", 1);
   if (mode == 2) return tc::launch_gemm_nt_tc(A, lda, B, ldb, M, N, K, ep, as_stream(stream), "gemm_nt (tcgen05, raw hi)", 0);
   return launch_gemm_nt(A, lda, B, ldb, M, N, K, ep, as_stream(stream), "gemm_nt (simt)");
+}
+
+// The fp16x2 pre-split GEMM (gemm_h16.cuh): operands as hi / lo half arrays (hi = fp16(x), lo = fp16((x - hi) * 2^11)), K-major,
+// pitches in halfs (multiples of 8).  Unit-test entry.
+extern "C" int ironb_gemm_nt_h16(const void* Ah, const void* Al, int lda, const void* Bh, const void* Bl, int ldb, int M, int N,
+                                 int K, float* C, int ldc, void* stream) {
+  IRONB_REQUIRE(Ah && Al && Bh && Bl && C, "gemm_nt_h16: null pointer");
+  IRONB_REQUIRE((N & 3) == 0 && (lda & 7) == 0 && (ldb & 7) == 0 && (ldc & 3) == 0, "gemm_nt_h16: N % 4, lda % 8, ldb % 8, ldc % 4 must be 0");
+  EpiStore ep{C, ldc};
+  return h16::launch_gemm_h16(reinterpret_cast<const __half*>(Ah), reinterpret_cast<const __half*>(Al), lda,
+                              reinterpret_cast<const __half*>(Bh), reinterpret_cast<const __half*>(Bl), ldb, M, N, K, ep,
+                              as_stream(stream), "gemm_nt_h16");
 }
 
 // C[Nd][ldc] += A[M][lda]^T * B[M][ldb]  (weight-gradient shape): unit-test entry; mode 1 = tcgen05 (transpose + split-K

@@ -3,7 +3,7 @@
 // -> Linear -> output_scale * (x + output_bias) -> [squeeze_out_scale * sigmoid].  skip_in = () only.
 // One fp32 tile GEMM per layer (gemm.cuh); ReLU / output transform fused into the epilogues, the input
 // concatenation + positional encodings and their backward are two small elementwise kernels.
-#include "gemm_tc.cuh"
+#include "gemm_h16.cuh"
 
 namespace ironb {
 namespace {
@@ -39,7 +39,8 @@ __device__ __forceinline__ float pe_col(const float* __restrict__ x3, int j) {
 __global__ void __launch_bounds__(256) assemble_kernel(ironb_matnet_cfg cfg, CatPlan pl, const float* __restrict__ pts,
                                                        const float* __restrict__ nrm, const float* __restrict__ view,
                                                        const float* __restrict__ feats, int64_t M, int ld,
-                                                       float* __restrict__ U0) {
+                                                       float* __restrict__ U0, __half* __restrict__ U0h,
+                                                       __half* __restrict__ U0l) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= M * ld) return;
   int64_t m = i / ld;
@@ -50,6 +51,11 @@ __global__ void __launch_bounds__(256) assemble_kernel(ironb_matnet_cfg cfg, Cat
   else if (j < pl.off_f) v = nrm[m * 3 + (j - pl.off_n)];
   else if (j < pl.total) v = __ldg(feats + m * cfg.d_feature + (j - pl.off_f));
   U0[i] = v;
+  if (U0h != nullptr) {        // fp16x2-split copy: the first layer's tensor-core operand (gemm_h16.cuh)
+    const __half h = __float2half_rn(v);
+    U0h[i] = h;
+    U0l[i] = __float2half_rn((v - __half2float(h)) * 2048.f);
+  }
 }
 
 // backward of one encoded 3-vector block: dx = de[0:3] + sum_k 2^k (cos_k de_sin,k - sin_k de_cos,k)
@@ -96,6 +102,7 @@ struct EpiRelu {
   const float* bias;
   float* Unext;
   int ld, n_true;
+  __half *Uh, *Ul;      // fp16x2-split copy of Unext or null
   __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[4]) const {
     float u[4];
 #pragma unroll
@@ -104,6 +111,7 @@ struct EpiRelu {
       u[j] = n < n_true ? fmaxf(acc[j] + __ldg(bias + n), 0.f) : 0.f;
     }
     *reinterpret_cast<float4*>(Unext + (int64_t)m * ld + n0) = make_float4(u[0], u[1], u[2], u[3]);
+    if (Uh) h16::store_split4(Uh, Ul, (int64_t)m * ld + n0, u);
   }
 };
 
@@ -171,6 +179,7 @@ struct MatWs {
   float* U[IRONB_MAX_LIN];
   float* D[2];
   float* wg;
+  __half *Uh[IRONB_MAX_LIN], *Ul[IRONB_MAX_LIN];   // fp16x2-split copies of U_l (gemm mode 2)
   int64_t floats;
 };
 
@@ -186,6 +195,13 @@ MatWs carve_mat(const ironb_mlp_layout* L, int64_t M, float* base) {
   w.D[1] = take(mp);
   w.wg = base ? base + off : nullptr;
   off += (wgrad_scratch_floats(M, mp) + 63) / 64 * 64;
+  if (gemm_mode() == 2) {
+    for (int l = 0; l < L->n_lin; ++l) {
+      float* p = take(L->in_pad[l]);
+      w.Uh[l] = reinterpret_cast<__half*>(p);
+      w.Ul[l] = p ? w.Uh[l] + M * L->in_pad[l] : nullptr;
+    }
+  }
   w.floats = off;
   return w;
 }
@@ -222,19 +238,28 @@ extern "C" int ironb_matnet_fwd(const ironb_mlp_layout* lay, const ironb_matnet_
   cudaStream_t st = as_stream(stream);
   const int last = lay->n_lin - 1;
   int64_t tot = M * lay->in_pad[0];
+  const bool h16m = gemm_mode() == 2;     // forward products on pre-split fp16x2 operands (gemm_h16.cuh)
   assemble_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(*cfg, pl, points, normals, view_dirs, feats, M,
-                                                                 lay->in_pad[0], w.U[0]);
+                                                                 lay->in_pad[0], w.U[0], h16m ? w.Uh[0] : nullptr,
+                                                                 h16m ? w.Ul[0] : nullptr);
   IRONB_CHECK_LAUNCH("assemble_kernel");
+  auto whi = [&](int l) { return reinterpret_cast<const __half*>(packed + lay->off_h16[l]); };
+  auto wlo = [&](int l) { return whi(l) + (int64_t)lay->out_pad[l] * lay->in_pad[l]; };
   for (int l = 0; l < last; ++l) {
-    EpiRelu ep{packed + lay->off_b[l], w.U[l + 1], lay->out_pad[l], lay->out_dim[l]};
-    int rc = launch_gemm_nt_auto(w.U[l], lay->in_pad[l], packed + lay->off_w[l], lay->in_pad[l], (int)M, lay->out_pad[l],
-                            lay->in_pad[l], ep, st, "matnet fwd gemm");
+    EpiRelu ep{packed + lay->off_b[l], w.U[l + 1], lay->out_pad[l], lay->out_dim[l], h16m ? w.Uh[l + 1] : nullptr,
+               h16m ? w.Ul[l + 1] : nullptr};
+    int rc = h16m ? h16::launch_gemm_h16(w.Uh[l], w.Ul[l], lay->in_pad[l], whi(l), wlo(l), lay->in_pad[l], (int)M, lay->out_pad[l],
+                                         lay->in_pad[l], ep, st, "matnet fwd gemm (h16)")
+                  : launch_gemm_nt_auto(w.U[l], lay->in_pad[l], packed + lay->off_w[l], lay->in_pad[l], (int)M, lay->out_pad[l],
+                                        lay->in_pad[l], ep, st, "matnet fwd gemm");
     if (rc) return rc;
   }
   EpiMatOut ep{packed + lay->off_b[last], out, lay->d_out, cfg->squeeze, cfg->out_bias, cfg->out_scale,
                cfg->squeeze_scale};
-  return launch_gemm_nt_auto(w.U[last], lay->in_pad[last], packed + lay->off_w[last], lay->in_pad[last], (int)M,
-                        lay->out_pad[last], lay->in_pad[last], ep, st, "matnet fwd out gemm");
+  return h16m ? h16::launch_gemm_h16(w.Uh[last], w.Ul[last], lay->in_pad[last], whi(last), wlo(last), lay->in_pad[last], (int)M,
+                                     lay->out_pad[last], lay->in_pad[last], ep, st, "matnet fwd out gemm (h16)")
+              : launch_gemm_nt_auto(w.U[last], lay->in_pad[last], packed + lay->off_w[last], lay->in_pad[last], (int)M,
+                                    lay->out_pad[last], lay->in_pad[last], ep, st, "matnet fwd out gemm");
 }
 
 extern "C" int ironb_matnet_bwd(const ironb_mlp_layout* lay, const ironb_matnet_cfg* cfg, const float* packed,

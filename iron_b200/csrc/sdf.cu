@@ -7,15 +7,17 @@
 //   backward of (y, feature, grad) w.r.t. W, b: part B (through grad, ascending l) then part A (ordinary
 //   back-propagation, descending l), with  zbarB_l = sp''(z_l) qa_{l+1} rbar_l = beta (1 - sp'(z_l)) r_l rbar_l.
 // Every product is one fp32 tile GEMM (gemm.cuh) with the elementwise work fused into its epilogue.
-#include "gemm_tc.cuh"
+#include "gemm_h16.cuh"
 
 namespace ironb {
 namespace {
 
 // ------------------------------------------------------------------ positional encoding
 // e = [x', sin(2^0 x'), cos(2^0 x'), ..., sin(2^(L-1) x'), cos(2^(L-1) x')], x' = x*scale; pad columns = 0.
+// ehi / elo (optional): the fp16x2-split copy of the row, the first layer's tensor-core operand (gemm_h16.cuh).
 __global__ void __launch_bounds__(256) pe_kernel(const float* __restrict__ x, int64_t M, int multires, float scale,
-                                                 int Epad, float* __restrict__ e) {
+                                                 int Epad, float* __restrict__ e, __half* __restrict__ ehi,
+                                                 __half* __restrict__ elo) {
   int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (m >= M) return;
   float xs[3] = {x[m * 3] * scale, x[m * 3 + 1] * scale, x[m * 3 + 2] * scale};
@@ -35,6 +37,13 @@ __global__ void __launch_bounds__(256) pe_kernel(const float* __restrict__ x, in
     f *= 2.f;
   }
   for (; w < Epad; ++w) o[w] = 0.f;
+  if (ehi != nullptr) {
+    for (int i = 0; i < Epad; ++i) {
+      const __half h = __float2half_rn(o[i]);
+      ehi[m * Epad + i] = h;
+      elo[m * Epad + i] = __float2half_rn((o[i] - __half2float(h)) * 2048.f);
+    }
+  }
 }
 
 // ------------------------------------------------------------------ epilogues
@@ -47,6 +56,8 @@ struct EpiFwdHidden {
   const float* e;      // PE buffer (pre-skip layer only)
   int ld, n_true, pre_skip, Epad, E;
   float beta, qscale;
+  __half *Uh, *Ul;     // fp16x2-split copy of Unext (next layer's tensor-core operand) or null
+  __half *Rh, *Rl;     // the same for R
   __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[4]) const {
     float zz[4], uu[4], rr[4];
 #pragma unroll
@@ -67,7 +78,11 @@ struct EpiFwdHidden {
     int64_t o = (int64_t)m * ld + n0;
     if (Z) *reinterpret_cast<float4*>(Z + o) = make_float4(zz[0], zz[1], zz[2], zz[3]);
     *reinterpret_cast<float4*>(Unext + o) = make_float4(uu[0], uu[1], uu[2], uu[3]);
-    if (R) *reinterpret_cast<float4*>(R + o) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+    if (Uh) h16::store_split4(Uh, Ul, o, uu);
+    if (R) {
+      *reinterpret_cast<float4*>(R + o) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+      if (Rh) h16::store_split4(Rh, Rl, o, rr);
+    }
   }
 };
 
@@ -97,6 +112,7 @@ struct EpiQ {
   float* P;            // [M][Epad]
   int ld, n_true_prev, is_skip, is_first, Epad, E;
   float beta;
+  __half *Rh, *Rl;     // fp16x2-split copy of Rprev (the next product's tensor-core operand) or null
   __device__ __forceinline__ void operator()(int m, int k0, const float (&acc)[4]) const {
     if (is_first) {
       float4* p = reinterpret_cast<float4*>(P + (int64_t)m * Epad + k0);
@@ -122,6 +138,7 @@ struct EpiQ {
       }
     }
     *reinterpret_cast<float4*>(Rprev + o) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+    if (Rh) h16::store_split4(Rh, Rl, o, rr);
   }
 };
 
@@ -256,6 +273,8 @@ struct SdfWs {
   float* R[IRONB_MAX_LIN];
   float* QB[2]; float* D[2];
   float* wg;                 // transposed-operand scratch of the tensor-core weight gradients
+  __half *Uh[IRONB_MAX_LIN], *Ul[IRONB_MAX_LIN];   // fp16x2-split copies of U_l (gemm mode 2: forward-type tensor-core operands)
+  __half *Rh[IRONB_MAX_LIN], *Rl[IRONB_MAX_LIN];   // ... and of R_l
   int64_t floats;
 };
 
@@ -271,6 +290,13 @@ SdfWs carve(const ironb_mlp_layout* L, int64_t M, bool full, float* base) {
   memset(&w, 0, sizeof(w));
   int64_t off = 0;
   auto take = [&](int64_t cols) { float* p = base ? base + off : nullptr; off += (M * cols + 63) / 64 * 64; return p; };
+  // hi and lo half arrays [M][cols] each = M * cols floats in total
+  auto take_h = [&](int64_t cols, __half*& hi, __half*& lo) {
+    float* p = take(cols);
+    hi = reinterpret_cast<__half*>(p);
+    lo = p ? hi + M * cols : nullptr;
+  };
+  const bool h16 = gemm_mode() == 2;
   const int last = L->n_lin - 1;
   const int mp = max_pad(L);
   w.e = take(L->in_pad[0]);
@@ -278,6 +304,12 @@ SdfWs carve(const ironb_mlp_layout* L, int64_t M, bool full, float* base) {
   if (!full) {
     float* a = take(mp); float* b = take(mp);
     for (int l = 1; l <= last; ++l) w.U[l] = (l & 1) ? a : b;
+    if (h16) {
+      take_h(L->in_pad[0], w.Uh[0], w.Ul[0]);
+      __half *ah, *al, *bh, *bl;
+      take_h(mp, ah, al); take_h(mp, bh, bl);
+      for (int l = 1; l <= last; ++l) { w.Uh[l] = (l & 1) ? ah : bh; w.Ul[l] = (l & 1) ? al : bl; }
+    }
   } else {
     w.P = take(L->in_pad[0]);
     for (int l = 1; l <= last; ++l) w.U[l] = take(L->in_pad[l]);
@@ -287,10 +319,19 @@ SdfWs carve(const ironb_mlp_layout* L, int64_t M, bool full, float* base) {
     w.D[0] = take(mp); w.D[1] = take(mp);
     w.wg = base ? base + off : nullptr;
     off += (wgrad_scratch_floats(M, mp) + 63) / 64 * 64;
+    if (h16) {
+      for (int l = 0; l <= last; ++l) take_h(L->in_pad[l], w.Uh[l], w.Ul[l]);
+      for (int l = 0; l < last; ++l) take_h(L->out_pad[l], w.Rh[l], w.Rl[l]);
+    }
   }
   w.floats = off;
   return w;
 }
+
+// fp16x2-split weights written by the fold: W_l (rows out_pad, K = in_pad) and W_l^T (rows in_pad, K = out_pad)
+inline const __half* w_hi(const ironb_mlp_layout* L, const float* packed, int l) { return reinterpret_cast<const __half*>(packed + L->off_h16[l]); }
+inline const __half* wt_hi(const ironb_mlp_layout* L, const float* packed, int l) { return reinterpret_cast<const __half*>(packed + L->off_h16t[l]); }
+inline int64_t w_elems(const ironb_mlp_layout* L, int l) { return (int64_t)L->out_pad[l] * L->in_pad[l]; }
 
 }  // namespace
 }  // namespace ironb
@@ -318,7 +359,8 @@ extern "C" int ironb_sdf_getall_fwd(const ironb_mlp_layout* lay, const float* pa
   const int Epad = lay->in_pad[0], E = lay->pe_dim;
   const int mblocks = (int)ceil_div64(M, 256);
 
-  pe_kernel<<<mblocks, 256, 0, st>>>(x, M, lay->multires, lay->scale, Epad, w.e);
+  const bool h16m = gemm_mode() == 2;     // forward-type products on pre-split fp16x2 operands (gemm_h16.cuh)
+  pe_kernel<<<mblocks, 256, 0, st>>>(x, M, lay->multires, lay->scale, Epad, w.e, h16m ? w.Uh[0] : nullptr, h16m ? w.Ul[0] : nullptr);
   IRONB_CHECK_LAUNCH("pe_kernel");
 
   for (int l = 0; l < last; ++l) {
@@ -335,14 +377,21 @@ extern "C" int ironb_sdf_getall_fwd(const ironb_mlp_layout* lay, const float* pa
     ep.Epad = Epad; ep.E = E;
     ep.beta = lay->beta;
     ep.qscale = 1.f / lay->scale;
-    int rc = launch_gemm_nt_auto(w.U[l], lay->in_pad[l], packed + lay->off_w[l], lay->in_pad[l], (int)M,
-                            lay->out_pad[l], lay->in_pad[l], ep, st, "sdf fwd hidden gemm");
+    ep.Uh = h16m ? w.Uh[l + 1] : nullptr; ep.Ul = h16m ? w.Ul[l + 1] : nullptr;
+    ep.Rh = (h16m && ep.R) ? w.Rh[l] : nullptr; ep.Rl = (h16m && ep.R) ? w.Rl[l] : nullptr;
+    int rc = h16m ? h16::launch_gemm_h16(w.Uh[l], w.Ul[l], lay->in_pad[l], w_hi(lay, packed, l), w_hi(lay, packed, l) + w_elems(lay, l),
+                                         lay->in_pad[l], (int)M, lay->out_pad[l], lay->in_pad[l], ep, st, "sdf fwd hidden gemm (h16)")
+                  : launch_gemm_nt_auto(w.U[l], lay->in_pad[l], packed + lay->off_w[l], lay->in_pad[l], (int)M,
+                                        lay->out_pad[l], lay->in_pad[l], ep, st, "sdf fwd hidden gemm");
     if (rc) return rc;
   }
   if (y != nullptr || feat != nullptr) {
     EpiFwdLast ep{packed + lay->off_b[last], y, feat, lay->d_out, 1.f / lay->scale};
-    int rc = launch_gemm_nt_auto(w.U[last], lay->in_pad[last], packed + lay->off_w[last], lay->in_pad[last], (int)M,
-                            lay->out_pad[last], lay->in_pad[last], ep, st, "sdf fwd last gemm");
+    int rc = h16m ? h16::launch_gemm_h16(w.Uh[last], w.Ul[last], lay->in_pad[last], w_hi(lay, packed, last),
+                                         w_hi(lay, packed, last) + w_elems(lay, last), lay->in_pad[last], (int)M,
+                                         lay->out_pad[last], lay->in_pad[last], ep, st, "sdf fwd last gemm (h16)")
+                  : launch_gemm_nt_auto(w.U[last], lay->in_pad[last], packed + lay->off_w[last], lay->in_pad[last], (int)M,
+                                        lay->out_pad[last], lay->in_pad[last], ep, st, "sdf fwd last gemm");
     if (rc) return rc;
   }
   if (grad != nullptr) {
@@ -358,8 +407,11 @@ extern "C" int ironb_sdf_getall_fwd(const ironb_mlp_layout* lay, const float* pa
       ep.is_first = (l == 0);
       ep.Epad = Epad; ep.E = E;
       ep.beta = lay->beta;
-      int rc = launch_gemm_nt_auto(w.R[l], lay->out_pad[l], packed + lay->off_wt[l], lay->out_pad[l], (int)M,
-                              lay->in_pad[l], lay->out_pad[l], ep, st, "sdf grad gemm");
+      ep.Rh = (h16m && l >= 1) ? w.Rh[l - 1] : nullptr; ep.Rl = (h16m && l >= 1) ? w.Rl[l - 1] : nullptr;
+      int rc = h16m ? h16::launch_gemm_h16(w.Rh[l], w.Rl[l], lay->out_pad[l], wt_hi(lay, packed, l), wt_hi(lay, packed, l) + w_elems(lay, l),
+                                           lay->out_pad[l], (int)M, lay->in_pad[l], lay->out_pad[l], ep, st, "sdf grad gemm (h16)")
+                    : launch_gemm_nt_auto(w.R[l], lay->out_pad[l], packed + lay->off_wt[l], lay->out_pad[l], (int)M,
+                                          lay->in_pad[l], lay->out_pad[l], ep, st, "sdf grad gemm");
       if (rc) return rc;
     }
     normal_kernel<<<mblocks, 256, 0, st>>>(w.e, w.P, M, lay->multires, Epad, lay->scale, grad);

@@ -39,14 +39,19 @@ def golden():
     return load
 
 
-@pytest.fixture(params=["ffma", "tcgen05"])
+GEMM_MODES = {"ffma": 0, "tcgen05-tf32": 1, "tcgen05": 2}
+
+
+@pytest.fixture(params=list(GEMM_MODES))
 def gemm_mode(request):
-    """Runs a GPU test under both GEMM arithmetics of the differentiable part: fp32 FFMA tiles (tight value
-    tolerances) and the tcgen05 3xTF32 kernel (default; the tensor core accumulates with truncation, so forward
-    values carry ~1e-5 relative error -- still far inside the BASELINE tolerances, which the tests also assert)."""
+    """Runs a GPU test under every GEMM arithmetic of the differentiable part: fp32 FFMA tiles (tight value
+    tolerances), the tcgen05 3xTF32 kernel everywhere ("tcgen05-tf32"; the tensor core accumulates with truncation, so
+    forward values carry ~1e-5 relative error -- still far inside the BASELINE tolerances, which the tests also assert),
+    and the default "tcgen05": fp16x2 pre-split operands for the forward-type products (de-biased accumulators), 3xTF32
+    for products with gradient operands."""
     from iron_b200 import _lib
     lib = _lib.load()
-    prev = lib.ironb_set_gemm_mode(1 if request.param == "tcgen05" else 0)
+    prev = lib.ironb_set_gemm_mode(GEMM_MODES[request.param])
     yield request.param
     lib.ironb_set_gemm_mode(prev)
 

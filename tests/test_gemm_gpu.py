@@ -37,6 +37,35 @@ def test_gemm_nt(M, N, K, mode):
     assert rel < (5e-7 if mode == 0 else 2e-6), rel
 
 
+def split_h(x):
+    hi = x.half()
+    lo = ((x - hi.float()) * 2048.0).half()
+    return hi.contiguous(), lo.contiguous()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (41, 64, 40), (300, 264, 256), (1000, 256, 296), (4096, 512, 512),
+                                   (130, 8, 304), (5000, 512, 40), (5000, 40, 512)])
+def test_gemm_nt_h16(M, N, K):
+    """The pre-split fp16x2 GEMM (forward-type products of get_all / the material nets) against an fp64 product."""
+    from iron_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    B = (torch.randn(N, K, generator=g) / np.sqrt(K)).to(DEV)
+    Ah, Al = split_h(A)
+    Bh, Bl = split_h(B)
+    C = torch.full((M, N), float("nan"), device=DEV)
+    _lib.check(lib.ironb_gemm_nt_h16(Ah.data_ptr(), Al.data_ptr(), K, Bh.data_ptr(), Bl.data_ptr(), K, M, N, K, _lib.ptr(C), N,
+                                     _lib.stream()), "gemm_nt_h16")
+    torch.cuda.synchronize()
+    assert torch.isfinite(C).all()
+    ref = A.double() @ B.double().t()
+    scale = (A.double().abs() @ B.double().abs().t())
+    rel = ((C.double() - ref).abs() / scale).max().item()
+    print(f"h16 M={M} N={N} K={K}: max |err| / sum|a||b| = {rel:.2e}")
+    assert rel < 2e-6, rel
+
+
 def test_gemm_modes_agree_on_structured_input():
     """identity-like B picks single A entries: any swizzle / descriptor mistake shows up as misplaced columns."""
     M, N, K = 256, 128, 64
