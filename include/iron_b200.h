@@ -131,10 +131,12 @@ int ironb_sdf_getall_fwd(const ironb_mlp_layout* lay, const float* packed, const
 /* Gradients of <ybar,y> + <fbar,feat> + <nbar,grad> (each upstream may be NULL) w.r.t. the folded
  * weights/biases, ACCUMULATED into dpacked (caller zeroes it).  This is the double backward of
  * fields.py:106-137 in closed form. `ws` is the saved forward workspace and
- * is clobbered. */
+ * is clobbered.  wgrad_stream (may be NULL = `stream`): a second stream for the 17 weight-gradient products, which only
+ * consume what the two back-propagation chains produce; the call forks to it with events and joins before returning its
+ * last work to `stream` (capturable; both streams are ordered after the call like one). */
 int ironb_sdf_getall_bwd(const ironb_mlp_layout* lay, const float* packed, const float* x, int64_t M,
                          const float* ybar, const float* fbar, const float* nbar, void* ws,
-                         int64_t ws_bytes, float* dpacked, void* stream);
+                         int64_t ws_bytes, float* dpacked, void* stream, void* wgrad_stream);
 
 /* ---------------------------------------------------------------- material networks (RenderingNetwork)
  * mode 0 = 'idr'         input = cat(PE_p(points), PE_v(view_dirs), normals, feats)
@@ -156,11 +158,12 @@ int64_t ironb_matnet_workspace_bytes(const ironb_mlp_layout* lay, int64_t M);
 int ironb_matnet_fwd(const ironb_mlp_layout* lay, const ironb_matnet_cfg* cfg, const float* packed,
                      const float* points, const float* normals, const float* view_dirs,
                      const float* feats, int64_t M, float* out, void* ws, int64_t ws_bytes, void* stream);
-/* d_points/d_normals/d_view/d_feats may be NULL; written (not accumulated). dpacked accumulated. */
+/* d_points/d_normals/d_view/d_feats may be NULL; written (not accumulated). dpacked accumulated.
+ * wgrad_stream: as for ironb_sdf_getall_bwd (may be NULL). */
 int ironb_matnet_bwd(const ironb_mlp_layout* lay, const ironb_matnet_cfg* cfg, const float* packed,
                      int64_t M, const float* out, const float* gout, void* ws, int64_t ws_bytes,
                      float* dpacked, float* d_points, float* d_normals, float* d_view, float* d_feats,
-                     void* stream);
+                     void* stream, void* wgrad_stream);
 
 /* ---------------------------------------------------------------- GGX colocated shading
  * light: device scalar.  dist[M], normal[M,3], viewdir[M,3], kd[M,3], ks[M,3], alpha[M].

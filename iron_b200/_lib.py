@@ -59,11 +59,11 @@ _PROTOS = {
     "ironb_mlp_fold_bwd": (_INT, [_LAY, _PP, _PP, _P, _PP, _PP, _PP, _P]),
     "ironb_sdf_getall_workspace_bytes": (_I64, [_LAY, _I64, _INT, _INT]),
     "ironb_sdf_getall_fwd": (_INT, [_LAY, _P, _P, _I64, _P, _P, _P, _INT, _P, _I64, _P]),
-    "ironb_sdf_getall_bwd": (_INT, [_LAY, _P, _P, _I64, _P, _P, _P, _P, _I64, _P, _P]),
+    "ironb_sdf_getall_bwd": (_INT, [_LAY, _P, _P, _I64, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "ironb_matnet_in_dim": (_INT, [_CFG]),
     "ironb_matnet_workspace_bytes": (_I64, [_LAY, _I64]),
     "ironb_matnet_fwd": (_INT, [_LAY, _CFG, _P, _P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
-    "ironb_matnet_bwd": (_INT, [_LAY, _CFG, _P, _I64, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
+    "ironb_matnet_bwd": (_INT, [_LAY, _CFG, _P, _I64, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P]),
     "ironb_ggx_fwd": (_INT, [_P] * 9 + [_I64] + [_P] * 4),
     "ironb_ggx_bwd": (_INT, [_P] * 9 + [_I64] + [_P] * 11),
     "ironb_composite_fwd": (_INT, [_P] * 12 + [_I64] + [_P] * 5),
@@ -141,6 +141,23 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+_WGRAD_STREAMS = {}
+
+
+def wgrad_stream() -> Optional[int]:
+    """A second stream for the weight-gradient products of a backward call (ironb_sdf_getall_bwd / ironb_matnet_bwd fork to
+    it and join before returning): one per (device, calling stream), created on first use.  IRONB_WGRAD_STREAM=0 disables it."""
+    if os.environ.get("IRONB_WGRAD_STREAM", "1") == "0":
+        return None
+    cur = torch.cuda.current_stream()
+    key = (cur.device.index, cur.cuda_stream)
+    s = _WGRAD_STREAMS.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=cur.device)
+        _WGRAD_STREAMS[key] = s
+    return s.cuda_stream
 
 
 def ptr_array(ts: Sequence[Optional[torch.Tensor]]):

@@ -67,6 +67,26 @@ __device__ __forceinline__ float softplus_d1(float z, float beta) {
   return bz > 20.f ? 1.f : __fdiv_rn(1.f, 1.f + expf(-bz));
 }
 
+// The same two functions on the MUFU units, for the GEMM epilogues of the differentiable path (sdf.cu), where the libm
+// versions above (expf + log1pf + IEEE division: ~100 instructions per element, 64 elements per epilogue thread) cost more
+// than the whole tensor-core mainloop of a tile (profiles/r2e_launches.md):
+//   softplus: max(z, 0) + log2(1 + 2^(-|beta z| log2 e)) * ln2 / beta     -- the log term is <= ln2 / beta, so the 2^-22
+//             relative error of ex2 / lg2 is ~1.6e-9 absolute; beyond beta z > 20 it is exactly z (torch's threshold)
+//   sigmoid : t = 2^(-|beta z| log2 e);  1 / (1 + t)  or  t / (1 + t)      -- 2^-22 relative; exactly 1 beyond the threshold
+__device__ __forceinline__ float softplus_beta_fast(float z, float beta) {
+  float t, L;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(z * beta) * -1.4426950408889634f));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(L) : "f"(1.f + t));
+  return fmaf(L, __fdividef(0.6931471805599453f, beta), fmaxf(z, 0.f));
+}
+__device__ __forceinline__ float softplus_d1_fast(float z, float beta) {
+  const float bz = z * beta;
+  float t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(bz) * -1.4426950408889634f));
+  const float r = __fdividef(1.f, 1.f + t);
+  return bz >= 0.f ? r : t * r;
+}
+
 #define IRONB_SQRT2F 1.41421356237309515f  // float(np.sqrt(2)); the reference DIVIDES by it (fields.py:89)
 
 }  // namespace ironb

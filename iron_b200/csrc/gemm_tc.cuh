@@ -484,6 +484,30 @@ inline int launch_wgrad_auto(const float* A, int lda, const float* B, int ldb, i
   return launch_colsum(A, lda, M, csum_cols, csum_scale, csum, st, what);
 }
 
+// Fork / join between the chain's stream and the weight-gradient stream: a cycling pool of timing-free events (an event may
+// be re-recorded once the wait that used it has been ENQUEUED; under stream capture both calls become graph edges).
+struct EventPool {
+  cudaEvent_t ev[128];
+  int n = 0, next = 0;
+  cudaEvent_t get() {
+    if (n < 128) {
+      if (cudaEventCreateWithFlags(&ev[n], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      return ev[n++];
+    }
+    next = (next + 1) % 128;
+    return ev[next];
+  }
+};
+inline int fork_to(cudaStream_t from, cudaStream_t to) {     // `to` continues after everything enqueued on `from` so far
+  if (from == to) return IRONB_OK;
+  static thread_local EventPool pool;
+  cudaEvent_t e = pool.get();
+  if (e == nullptr) { set_error("cudaEventCreate failed"); return IRONB_EINVAL; }
+  IRONB_CUDA(cudaEventRecord(e, from));
+  IRONB_CUDA(cudaStreamWaitEvent(to, e, 0));
+  return IRONB_OK;
+}
+
 template <class Epi>
 int launch_gemm_nt_auto(const float* A, int lda, const float* B, int ldb, int M, int N, int K, const Epi& epi,
                         cudaStream_t st, const char* what) {

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) mat_dlast_kernel(const float* __restrict_
 
 struct MatWs {
   float* U[IRONB_MAX_LIN];
-  float* D[2];
+  float* D[IRONB_MAX_LIN + 1];   // delta_l per layer (D[l] = gradient w.r.t. the output of layer l; D[n_lin] unused) + the input gradient
   float* wg;
   __half *Uh[IRONB_MAX_LIN], *Ul[IRONB_MAX_LIN];   // fp16x2-split copies of U_l (gemm mode 2)
   int64_t floats;
@@ -191,8 +191,8 @@ MatWs carve_mat(const ironb_mlp_layout* L, int64_t M, float* base) {
   int mp = 0;
   for (int l = 0; l < L->n_lin; ++l) { mp = max(mp, L->in_pad[l]); mp = max(mp, L->out_pad[l]); }
   for (int l = 0; l < L->n_lin; ++l) w.U[l] = take(L->in_pad[l]);
-  w.D[0] = take(mp);
-  w.D[1] = take(mp);
+  for (int l = 0; l < L->n_lin; ++l) w.D[l] = take(L->out_pad[l]);
+  w.D[L->n_lin] = take(L->in_pad[0]);                 // d loss / d (assembled input)
   w.wg = base ? base + off : nullptr;
   off += (wgrad_scratch_floats(M, mp) + 63) / 64 * 64;
   if (gemm_mode() == 2) {
@@ -265,7 +265,7 @@ extern "C" int ironb_matnet_fwd(const ironb_mlp_layout* lay, const ironb_matnet_
 extern "C" int ironb_matnet_bwd(const ironb_mlp_layout* lay, const ironb_matnet_cfg* cfg, const float* packed,
                                 int64_t M, const float* out, const float* gout, void* ws, int64_t ws_bytes,
                                 float* dpacked, float* d_points, float* d_normals, float* d_view, float* d_feats,
-                                void* stream) {
+                                void* stream, void* wgrad_stream) {
   IRONB_REQUIRE(lay && cfg && lay->kind == 1, "matnet_bwd: bad layout");
   IRONB_REQUIRE(M >= 0 && M < (1ll << 31), "matnet_bwd: M out of range");
   if (M == 0) return IRONB_OK;
@@ -274,27 +274,31 @@ extern "C" int ironb_matnet_bwd(const ironb_mlp_layout* lay, const ironb_matnet_
   MatWs w = carve_mat(lay, M, reinterpret_cast<float*>(ws));
   IRONB_REQUIRE(ws_bytes >= w.floats * (int64_t)sizeof(float), "matnet_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
+  cudaStream_t wst = wgrad_stream ? as_stream(wgrad_stream) : st;    // weight gradients off the dgrad chain (see sdf.cu)
+  // the overlap pays only while one GEMM does not fill the GPU (a 16,384-row layer is already 512 CTAs = 3.5 waves)
+  if (M > 16384) wst = st;
+  int frc;
   const int last = lay->n_lin - 1;
   int64_t tot = M * lay->out_pad[last];
   mat_dlast_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(out, gout, M, lay->d_out, lay->out_pad[last],
                                                                   cfg->squeeze, cfg->out_scale, cfg->squeeze_scale,
-                                                                  w.D[last & 1]);
+                                                                  w.D[last]);
   IRONB_CHECK_LAUNCH("mat_dlast_kernel");
-  const float* D = w.D[last & 1];
   const bool need_in = d_points || d_normals || d_view || d_feats;
   for (int l = last; l >= 0; --l) {
+    const float* D = w.D[l];
+    if ((frc = fork_to(st, wst))) return frc;
     int rc = launch_wgrad_auto(D, lay->out_pad[l], w.U[l], lay->in_pad[l], (int)M, lay->out_pad[l], lay->in_pad[l],
-                               dpacked + lay->off_w[l], lay->in_pad[l], w.wg, st, "matnet wgrad (+ bias grad)",
+                               dpacked + lay->off_w[l], lay->in_pad[l], w.wg, wst, "matnet wgrad (+ bias grad)",
                                dpacked + lay->off_b[l], lay->out_dim[l], 1.f);
     if (rc) return rc;
-    float* Dn = w.D[(l + 1) & 1];
     if (l > 0) {
-      EpiReluBwd ep{w.U[l], Dn, lay->in_pad[l], lay->out_dim[l - 1]};
+      EpiReluBwd ep{w.U[l], w.D[l - 1], lay->in_pad[l], lay->out_dim[l - 1]};
       rc = launch_gemm_nt_auto(D, lay->out_pad[l], packed + lay->off_wt[l], lay->out_pad[l], (int)M, lay->in_pad[l],
                           lay->out_pad[l], ep, st, "matnet dgrad");
       if (rc) return rc;
-      D = Dn;
     } else if (need_in) {
+      float* Dn = w.D[lay->n_lin];
       EpiPlain ep{Dn, lay->in_pad[0]};
       rc = launch_gemm_nt_auto(D, lay->out_pad[0], packed + lay->off_wt[0], lay->out_pad[0], (int)M, lay->in_pad[0],
                           lay->out_pad[0], ep, st, "matnet input dgrad");
@@ -305,5 +309,6 @@ extern "C" int ironb_matnet_bwd(const ironb_mlp_layout* lay, const ironb_matnet_
       IRONB_CHECK_LAUNCH("disassemble_kernel");
     }
   }
+  if ((frc = fork_to(wst, st))) return frc;      // join: dpacked is complete on st
   return IRONB_OK;
 }

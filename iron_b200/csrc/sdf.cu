@@ -65,10 +65,10 @@ struct EpiFwdHidden {
       int n = n0 + j;
       if (n < n_true) {
         float z = acc[j] + __ldg(bias + n);
-        float a = softplus_beta(z, beta);
+        float a = softplus_beta_fast(z, beta);
         if (pre_skip) a = __fdiv_rn(a, IRONB_SQRT2F);
         zz[j] = z; uu[j] = a;
-        rr[j] = R ? softplus_d1(z, beta) * (__ldg(qrow + n) * qscale) : 0.f;
+        rr[j] = R ? softplus_d1_fast(z, beta) * (__ldg(qrow + n) * qscale) : 0.f;
       } else {
         zz[j] = 0.f; rr[j] = 0.f;
         int c = n - n_true;
@@ -130,7 +130,7 @@ struct EpiQ {
       int k = k0 + j;
       if (k < n_true_prev) {
         float qa = is_skip ? __fdiv_rn(acc[j], IRONB_SQRT2F) : acc[j];
-        rr[j] = softplus_d1(zz[j], beta) * qa;
+        rr[j] = softplus_d1_fast(zz[j], beta) * qa;
       } else {
         rr[j] = 0.f;
         int c = k - n_true_prev;
@@ -142,10 +142,12 @@ struct EpiQ {
   }
 };
 
-// part B: acc = rbar_l[m][n].  Overwrites R_l with zbarB_l and emits qbar_{l+1}.
+// part B: acc = rbar_l[m][n].  Emits zbarB_l and qbar_{l+1}.  (r_l is left intact: the weight gradient r_l^T qbar_l of the
+// same layer reads it from a second stream.)
 struct EpiB {
   const float* Z;    // Z_l
-  float* R;          // in: r_l, out: zbarB_l
+  const float* R;    // r_l
+  float* ZB;         // out: zbarB_l
   float* QBnext;     // [M][ld]
   const float* PB;   // pbar [M][Epad]
   int ld, n_true, pre_skip, Epad, E;
@@ -161,7 +163,7 @@ struct EpiB {
     for (int j = 0; j < 4; ++j) {
       int n = n0 + j;
       if (n < n_true) {
-        float s1 = softplus_d1(zz[j], beta);
+        float s1 = softplus_d1_fast(zz[j], beta);
         bool lin = zz[j] * beta > 20.f;
         zb[j] = lin ? 0.f : beta * (1.f - s1) * rr[j] * acc[j];
         float qa = s1 * acc[j];
@@ -172,7 +174,7 @@ struct EpiB {
         qb[j] = (pre_skip && c < E) ? __fdiv_rn(__ldg(PB + (int64_t)m * Epad + c), IRONB_SQRT2F) : 0.f;
       }
     }
-    *reinterpret_cast<float4*>(R + o) = make_float4(zb[0], zb[1], zb[2], zb[3]);
+    *reinterpret_cast<float4*>(ZB + o) = make_float4(zb[0], zb[1], zb[2], zb[3]);
     *reinterpret_cast<float4*>(QBnext + o) = make_float4(qb[0], qb[1], qb[2], qb[3]);
   }
 };
@@ -199,7 +201,7 @@ struct EpiA {
       int k = k0 + j;
       if (k < n_true_prev) {
         float ab = is_skip ? __fdiv_rn(acc[j], IRONB_SQRT2F) : acc[j];
-        dd[j] = softplus_d1(zz[j], beta) * ab + zb[j];
+        dd[j] = softplus_d1_fast(zz[j], beta) * ab + zb[j];
       } else {
         dd[j] = 0.f;
       }
@@ -271,7 +273,9 @@ struct SdfWs {
   float* U[IRONB_MAX_LIN];   // U[0] == e
   float* Z[IRONB_MAX_LIN];
   float* R[IRONB_MAX_LIN];
-  float* QB[2]; float* D[2];
+  float* QB[IRONB_MAX_LIN];  // qbar_l, l >= 1 (qbar_0 = P); one buffer per layer: the weight gradients read them later
+  float* D[IRONB_MAX_LIN];   // delta_l
+  float* ZB[IRONB_MAX_LIN];  // zbarB_l
   float* wg;                 // transposed-operand scratch of the tensor-core weight gradients
   __half *Uh[IRONB_MAX_LIN], *Ul[IRONB_MAX_LIN];   // fp16x2-split copies of U_l (gemm mode 2: forward-type tensor-core operands)
   __half *Rh[IRONB_MAX_LIN], *Rl[IRONB_MAX_LIN];   // ... and of R_l
@@ -315,8 +319,10 @@ SdfWs carve(const ironb_mlp_layout* L, int64_t M, bool full, float* base) {
     for (int l = 1; l <= last; ++l) w.U[l] = take(L->in_pad[l]);
     for (int l = 0; l < last; ++l) w.Z[l] = take(L->out_pad[l]);
     for (int l = 0; l < last; ++l) w.R[l] = take(L->out_pad[l]);
-    w.QB[0] = take(mp); w.QB[1] = take(mp);
-    w.D[0] = take(mp); w.D[1] = take(mp);
+    w.QB[0] = w.P;
+    for (int l = 1; l <= last; ++l) w.QB[l] = take(L->in_pad[l]);
+    for (int l = 0; l <= last; ++l) w.D[l] = take(L->out_pad[l]);
+    for (int l = 0; l < last; ++l) w.ZB[l] = take(L->out_pad[l]);
     w.wg = base ? base + off : nullptr;
     off += (wgrad_scratch_floats(M, mp) + 63) / 64 * 64;
     if (h16) {
@@ -422,7 +428,7 @@ extern "C" int ironb_sdf_getall_fwd(const ironb_mlp_layout* lay, const float* pa
 
 extern "C" int ironb_sdf_getall_bwd(const ironb_mlp_layout* lay, const float* packed, const float* x, int64_t M,
                                     const float* ybar, const float* fbar, const float* nbar, void* ws,
-                                    int64_t ws_bytes, float* dpacked, void* stream) {
+                                    int64_t ws_bytes, float* dpacked, void* stream, void* wgrad_stream) {
   (void)x;
   IRONB_REQUIRE(lay && lay->kind == 0, "sdf_getall_bwd: layout is not an SDF layout");
   IRONB_REQUIRE(M >= 0 && M < (1ll << 31), "sdf_getall_bwd: M out of range");
@@ -431,6 +437,14 @@ extern "C" int ironb_sdf_getall_bwd(const ironb_mlp_layout* lay, const float* pa
   SdfWs w = carve(lay, M, true, reinterpret_cast<float*>(ws));
   IRONB_REQUIRE(ws_bytes >= w.floats * (int64_t)sizeof(float), "sdf_getall_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
+  // The two back-propagation chains (part B, part A: one GEMM per layer, each waiting for the previous) run on `st`; the 17
+  // weight gradients (transpose + split-K GEMM each) only CONSUME what the chains produce, so they go to `wst` as soon as their
+  // operands exist and leave the chains' critical path (round 1 interleaved them on one stream: 34 launches of the step's
+  // longest dependency chain).  wgrad_stream == NULL keeps everything on `st`.
+  cudaStream_t wst = wgrad_stream ? as_stream(wgrad_stream) : st;
+  // the overlap pays only while one GEMM does not fill the GPU (a 16,384-row layer is already 512 CTAs = 3.5 waves)
+  if (M > 16384) wst = st;
+  int frc;
   const int last = lay->n_lin - 1;
   const int Epad = lay->in_pad[0], E = lay->pe_dim;
   const int mblocks = (int)ceil_div64(M, 256);
@@ -443,15 +457,16 @@ extern "C" int ironb_sdf_getall_bwd(const ironb_mlp_layout* lay, const float* pa
   if (has_n) {
     pbar_kernel<<<mblocks, 256, 0, st>>>(w.e, nbar, M, lay->multires, Epad, lay->scale, w.P);
     IRONB_CHECK_LAUNCH("pbar_kernel");
-    const float* qb = w.P;
     for (int l = 0; l < last; ++l) {
-      // dW_l += r_l^T qbar_l
+      const float* qb = w.QB[l];
+      // dW_l += r_l^T qbar_l   (weight-gradient stream; qbar_l is complete on st here)
+      if ((frc = fork_to(st, wst))) return frc;
       int rc = launch_wgrad_auto(w.R[l], lay->out_pad[l], qb, lay->in_pad[l], (int)M, lay->out_pad[l], lay->in_pad[l],
-                                 dpacked + lay->off_w[l], lay->in_pad[l], w.wg, st, "sdf bwd B wgrad");
+                                 dpacked + lay->off_w[l], lay->in_pad[l], w.wg, wst, "sdf bwd B wgrad");
       if (rc) return rc;
       EpiB ep;
-      ep.Z = w.Z[l]; ep.R = w.R[l];
-      ep.QBnext = w.QB[(l + 1) & 1];
+      ep.Z = w.Z[l]; ep.R = w.R[l]; ep.ZB = w.ZB[l];
+      ep.QBnext = w.QB[l + 1];
       ep.PB = w.P;
       ep.ld = lay->out_pad[l];
       ep.n_true = lay->out_dim[l];
@@ -461,10 +476,10 @@ extern "C" int ironb_sdf_getall_bwd(const ironb_mlp_layout* lay, const float* pa
       rc = launch_gemm_nt_auto(qb, lay->in_pad[l], packed + lay->off_w[l], lay->in_pad[l], (int)M, lay->out_pad[l],
                           lay->in_pad[l], ep, st, "sdf bwd B gemm");
       if (rc) return rc;
-      qb = w.QB[(l + 1) & 1];
     }
     // dW_last[0,:] += sum_m qbar_last / s
-    int rc = launch_colsum(qb, lay->in_pad[last], (int)M, lay->in_dim[last], inv_s, dpacked + lay->off_w[last], st,
+    if ((frc = fork_to(st, wst))) return frc;
+    int rc = launch_colsum(w.QB[last], lay->in_pad[last], (int)M, lay->in_dim[last], inv_s, dpacked + lay->off_w[last], wst,
                            "sdf bwd B colsum");
     if (rc) return rc;
   }
@@ -475,25 +490,26 @@ extern "C" int ironb_sdf_getall_bwd(const ironb_mlp_layout* lay, const float* pa
   if (has_yf) {
     int64_t tot = M * lay->out_pad[last];
     dlast_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(ybar, fbar, M, lay->d_out, lay->out_pad[last], inv_s,
-                                                                w.D[last & 1]);
+                                                                w.D[last]);
     IRONB_CHECK_LAUNCH("dlast_kernel");
-    D = w.D[last & 1];
+    D = w.D[last];
   } else {
-    // delta_last == 0: start one layer down, where delta equals zbarB (which sits in the R buffer)
+    // delta_last == 0: start one layer down, where delta equals zbarB
     lstart = last - 1;
-    D = w.R[lstart];
+    D = w.ZB[lstart];
   }
   for (int l = lstart; l >= 0; --l) {
     // dW_l += delta_l^T u_l, and db_l += column sums of delta_l (taken from the transposed tiles of the same launch)
+    if ((frc = fork_to(st, wst))) return frc;
     int rc = launch_wgrad_auto(D, lay->out_pad[l], w.U[l], lay->in_pad[l], (int)M, lay->out_pad[l], lay->in_pad[l],
-                               dpacked + lay->off_w[l], lay->in_pad[l], w.wg, st, "sdf bwd A wgrad",
+                               dpacked + lay->off_w[l], lay->in_pad[l], w.wg, wst, "sdf bwd A wgrad",
                                dpacked + lay->off_b[l], lay->out_dim[l], 1.f);
     if (rc) return rc;
     if (l == 0) break;
     EpiA ep;
     ep.Zprev = w.Z[l - 1];
-    ep.ZBprev = has_n ? w.R[l - 1] : nullptr;
-    ep.Dprev = w.D[(l - 1) & 1];
+    ep.ZBprev = has_n ? w.ZB[l - 1] : nullptr;
+    ep.Dprev = w.D[l - 1];
     ep.ld = lay->in_pad[l];
     ep.n_true_prev = lay->out_dim[l - 1];
     ep.is_skip = (l == lay->skip_layer);
@@ -501,7 +517,8 @@ extern "C" int ironb_sdf_getall_bwd(const ironb_mlp_layout* lay, const float* pa
     rc = launch_gemm_nt_auto(D, lay->out_pad[l], packed + lay->off_wt[l], lay->out_pad[l], (int)M, lay->in_pad[l],
                         lay->out_pad[l], ep, st, "sdf bwd A gemm");
     if (rc) return rc;
-    D = w.D[(l - 1) & 1];
+    D = w.D[l - 1];
   }
+  if ((frc = fork_to(wst, st))) return frc;      // join: dpacked is complete on st
   return IRONB_OK;
 }

@@ -170,7 +170,7 @@ class _SDFEval(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.ironb_sdf_getall_bwd(C.byref(lay), _lib.ptr(ctx.packed), _lib.ptr(ctx.x), M, _lib.ptr(gy),
                                                 _lib.ptr(gfeat), _lib.ptr(ggrad), _lib.ptr(ctx.ws), ctx.ws.numel(),
-                                                _lib.ptr(dpacked), _lib.stream()), "sdf_getall_bwd")
+                                                _lib.ptr(dpacked), _lib.stream(), _lib.wgrad_stream()), "sdf_getall_bwd")
         if prev_mode is not None:
             lib.ironb_set_gemm_mode(prev_mode)
         grads = net.unfold_grads(dpacked)
@@ -304,7 +304,7 @@ class _MatEval(torch.autograd.Function):
             _lib.check(lib.ironb_matnet_bwd(C.byref(lay), C.byref(cfg), _lib.ptr(ctx.packed), M, _lib.ptr(ctx.out),
                                             _lib.ptr(gout), _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.ptr(dpacked),
                                             _lib.ptr(d_points), _lib.ptr(d_normals), _lib.ptr(d_view), _lib.ptr(d_feats),
-                                            _lib.stream()), "matnet_bwd")
+                                            _lib.stream(), _lib.wgrad_stream()), "matnet_bwd")
         grads = net.unfold_grads(dpacked) if any(ng[5:]) else [None] * (len(ng) - 5)
         ctx.ws = None
         return (None, d_points, d_normals, d_view, d_feats, *grads)
