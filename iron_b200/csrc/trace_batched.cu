@@ -65,8 +65,8 @@ struct BArgs {
 constexpr int C_ST = 0;      // 0..2 rotating row counts (sphere tracing)
 constexpr int C_NUNF = 3, C_NROOT = 4, C_KMAX = 5;
 constexpr int C_SG = 8;      // 8..10 rotating group counts (sampler)
-constexpr int C_BR = 16;     // 16.. row count of bisection round j (0 = nobody works any more)
-constexpr int NCOUNTERS = 64;
+constexpr int C_BR = 16;     // 16.. row count of bisection round j (see the bisection kernels)
+constexpr int NCOUNTERS = 128;
 
 __device__ __forceinline__ void put_split(__half* __restrict__ ehi, __half* __restrict__ elo, int i, float v) {
   const __half h = __float2half_rn(v);
@@ -253,63 +253,110 @@ __global__ void __launch_bounds__(256) smp_update_kernel(BArgs A, int chunk) {
   }
 }
 
-// ---------------------------------------------------------------- bisection (:199-220)
+// ---------------------------------------------------------------- bisection (:199-220), two iterations per MLP round
+// The reference halves EVERY root of the call while any root still works (one batch-coupled loop, k_max iterations), then
+// evaluates the final midpoints once more.  Its iterations are strictly sequential -- but the midpoint of iteration k+1 is
+// one of only two values, (lo + mid)/2 or (mid + hi)/2, both computable before f(mid) is known.  A round therefore evaluates
+// THREE points per root (mid and both candidate next midpoints, formed by the reference's own expression, so the chosen one is
+// bit-identical to what the reference would compute) and advances the loop by two iterations; the "does any root still work"
+// test of the reference sits between the two iterations and is a device-wide flag between two tiny kernels.  The final
+// evaluation is whichever already-evaluated point the loop stops on.  k_max iterations cost ceil((k_max + 1) / 2) MLP rounds
+// instead of k_max + 1 (7 + 1 -> 4 at the training patch), at 1.5x the (few) bisection evaluations.
+//   c[C_BR + j]  rows of round j (n_root, or 0 = the loop and the final evaluation are done)
+//   c[C_BA + j]  1 if some root works when round j starts (i.e. iteration 2j + 1 takes place)
+//   c[C_BF + j]  1 if some root still works after iteration 2j + 1 (i.e. iteration 2j + 2 takes place)
+constexpr int BIS_MAX_ROUNDS = 24, C_BA = C_BR + BIS_MAX_ROUNDS, C_BF = C_BA + BIS_MAX_ROUNDS;   // 16.., 40.., 64..87
+
+__device__ __forceinline__ void bis_write_candidates(const BArgs& A, int i, int n_root, int r, float lo, float hi, float mid, int part) {
+  const float cand[3] = {mid, __fmul_rn(__fadd_rn(lo, mid), 0.5f), __fmul_rn(__fadd_rn(mid, hi), 0.5f)};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float x[3];
+    ray_point(A, r, cand[c], x);                                    // :205
+    write_pe(A, (size_t)c * n_root + i, x, part);
+  }
+}
+__device__ __forceinline__ void bis_finish(const BArgs& A, int i, float mid, float f) {   // :216-219, :75
+  const int r = A.root_ray[i];
+  float x[3];
+  ray_point(A, r, mid, x);
+  A.points[(size_t)r * 3] = x[0]; A.points[(size_t)r * 3 + 1] = x[1]; A.points[(size_t)r * 3 + 2] = x[2];
+  A.sdf[r] = f; A.dist[r] = mid; A.conv[r] = 1;
+}
+
 __global__ void __launch_bounds__(256) bis_prepare_kernel(BArgs A) {
   const int n_root = A.c[C_NROOT];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = tid / PE_T, part = tid % PE_T;
-  if (tid == 0 && A.stats) atomicAdd(A.stats + 4, (unsigned long long)n_root);
+  if (tid == 0) {
+    if (A.stats) atomicAdd(A.stats + 4, (unsigned long long)n_root);
+    A.c[C_BR] = n_root;                                               // round 0 always runs: it holds the final evaluation at least
+  }
   if (i >= n_root) return;
-  const float mid = __fmul_rn(__fadd_rn(A.root_lo[i], A.root_hi[i]), 0.5f);   // :203
+  const float lo = A.root_lo[i], hi = A.root_hi[i];
+  const float mid = __fmul_rn(__fadd_rn(lo, hi), 0.5f);                // :203
   if (part == 0) {
     A.root_mid[i] = mid;
-    if (A.root_work[i]) atomicMax(A.c + C_BR, n_root);              // while work.any()  (:204)
+    if (A.root_work[i]) atomicMax(A.c + C_BA, 1);                     // while work.any()  (:204)
   }
-  float x[3];
-  ray_point(A, A.root_ray[i], mid, x);                              // :205
-  write_pe(A, (size_t)i, x, part);
+  bis_write_candidates(A, i, n_root, A.root_ray[i], lo, hi, mid, part);
 }
 
-__global__ void __launch_bounds__(256) bis_update_kernel(BArgs A, int round) {
+// first half of a round: only the device-wide "does any root still work after iteration 2j + 1" flag
+__global__ void __launch_bounds__(256) bis_flag_kernel(BArgs A, int round) {
   const int rows = A.c[C_BR + round];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows || !A.c[C_BA + round] || !A.root_work[i]) return;
+  const float f1 = read_f(A, (size_t)i);
+  float lo = A.root_lo[i], hi = A.root_hi[i];
+  const float mid = A.root_mid[i];
+  if (f1 > 0.f) lo = mid; else hi = mid;
+  if (__fsub_rn(hi, lo) > A.two_thr) atomicMax(A.c + C_BF + round, 1);
+}
+
+__global__ void __launch_bounds__(256) bis_update_kernel(BArgs A, int round, int is_last) {
+  const int rows = A.c[C_BR + round];                                 // n_root, or 0 when everything is done
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = tid / PE_T, part = tid % PE_T;
+  // is_last: the host's schedule ends here (it covers the halvings the reference can need by construction); finish regardless
+  const int active = A.c[C_BA + round], more = is_last ? 0 : A.c[C_BF + round];
   if (tid == 0 && rows > 0) {
-    A.c[C_KMAX] = round + 1;
-    if (A.stats) { atomicAdd(A.stats + 2, (unsigned long long)rows); atomicAdd(A.stats + 6, (unsigned long long)((rows + 127) / 128)); }
+    A.c[C_KMAX] = active ? (more ? 2 * round + 2 : 2 * round + 1) : 2 * round;     // iterations the reference's loop has run
+    if (A.stats) { atomicAdd(A.stats + 2, (unsigned long long)rows * 3ull); atomicAdd(A.stats + 6, (unsigned long long)((rows * 3 + 127) / 128)); }
   }
   if (i >= rows) return;
-  const float f = read_f(A, i);
+  const float f1 = read_f(A, (size_t)i);
   float lo = A.root_lo[i], hi = A.root_hi[i], mid = A.root_mid[i];
-  const int was_work = A.root_work[i];
+  int work = A.root_work[i];
   __syncwarp(0xffu << (threadIdx.x & 24));                          // every lane of the item has read the state
-  if (f > 0.f) lo = mid; else hi = mid;                             // every ray of the call (:207-212)
-  mid = __fmul_rn(__fadd_rn(lo, hi), 0.5f);                         // :213
-  if (part == 0) {
-    A.root_lo[i] = lo; A.root_hi[i] = hi; A.root_mid[i] = mid;
-    const bool work = was_work && (__fsub_rn(hi, lo) > A.two_thr);  // :214
-    A.root_work[i] = work ? 1 : 0;
-    if (work) atomicMax(A.c + C_BR + round + 1, rows);
+  if (!active) {                       // the loop ended before this round: f1 is the final evaluation (:216-219)
+    if (part == 0) bis_finish(A, i, mid, f1);
+    return;
   }
-  float x[3];
-  ray_point(A, A.root_ray[i], mid, x);
-  write_pe(A, (size_t)i, x, part);
+  // iteration 2j + 1: every root of the call (:207-214)
+  const bool up = f1 > 0.f;
+  if (up) lo = mid; else hi = mid;
+  const float f2 = read_f(A, (size_t)(up ? 2 : 1) * rows + i);        // f at the new midpoint, evaluated speculatively
+  mid = __fmul_rn(__fadd_rn(lo, hi), 0.5f);
+  work = work && (__fsub_rn(hi, lo) > A.two_thr);
+  if (!more) {                         // no root works any more: the loop ended after this iteration, f2 is the final evaluation
+    if (part == 0) bis_finish(A, i, mid, f2);
+    return;
+  }
+  // iteration 2j + 2
+  if (f2 > 0.f) lo = mid; else hi = mid;
+  mid = __fmul_rn(__fadd_rn(lo, hi), 0.5f);
+  work = work && (__fsub_rn(hi, lo) > A.two_thr);
+  if (part == 0) {
+    A.root_lo[i] = lo; A.root_hi[i] = hi; A.root_mid[i] = mid; A.root_work[i] = work ? 1 : 0;
+    if (work) atomicMax(A.c + C_BA + round + 1, 1);
+    if (i == 0) A.c[C_BR + round + 1] = rows;                         // the next round holds more iterations or the final evaluation
+  }
+  bis_write_candidates(A, i, rows, A.root_ray[i], lo, hi, mid, part);
 }
 
-__global__ void __launch_bounds__(256) bis_final_kernel(BArgs A) {
-  const int n_root = A.c[C_NROOT];
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0 && A.stats) {
-    atomicMax(A.stats + 5, (unsigned long long)A.c[C_KMAX]);
-    if (n_root > 0) { atomicAdd(A.stats + 2, (unsigned long long)n_root); atomicAdd(A.stats + 6, (unsigned long long)((n_root + 127) / 128)); }
-  }
-  if (i >= n_root) return;
-  const int r = A.root_ray[i];
-  const float mid = A.root_mid[i];
-  float x[3];
-  ray_point(A, r, mid, x);                                          // :216-219
-  A.points[(size_t)r * 3] = x[0]; A.points[(size_t)r * 3 + 1] = x[1]; A.points[(size_t)r * 3 + 2] = x[2];
-  A.sdf[r] = read_f(A, i); A.dist[r] = mid; A.conv[r] = 1;               // :75
+__global__ void __launch_bounds__(32) bis_stats_kernel(BArgs A) {
+  if (threadIdx.x == 0 && A.stats) atomicMax(A.stats + 5, (unsigned long long)A.c[C_KMAX]);
 }
 
 struct BWs {
@@ -390,7 +437,7 @@ int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float*
   int bound = 1;
   for (double len = 2.0 / (n_steps - 1); len > 2.0 * thr && bound < 40; len *= 0.5) ++bound;
   bound += 2;
-  if (bound > NCOUNTERS - C_BR - 2) bound = NCOUNTERS - C_BR - 2;
+  if (bound > 2 * (BIS_MAX_ROUNDS - 2)) bound = 2 * (BIS_MAX_ROUNDS - 2);
   A.bound = bound;
   A.multires = lay->multires; A.Epad = Epad; A.H = H; A.scale = lay->scale;
   A.conv = conv; A.points = points; A.sdf = sdf; A.dist = dist;
@@ -457,17 +504,19 @@ int trace_batched(const ironb_mlp_layout* lay, const float* packed, const float*
       IRONB_CHECK_LAUNCH("smp_update_kernel");
     }
   }
-  // ---- bisection: the reference loop, then the final evaluation
+  // ---- bisection: two iterations of the reference loop per round, the final evaluation rides on the last round
   bis_prepare_kernel<<<nb, 256, 0, st>>>(A);
   IRONB_CHECK_LAUNCH("bis_prepare_kernel");
-  for (int j = 0; j < bound; ++j) {
-    if ((rc = mlp((int)N, w.c + C_BR + j, 1))) return rc;
-    bis_update_kernel<<<nb, 256, 0, st>>>(A, j);
+  const int rounds = (bound + 1) / 2 + 1 < BIS_MAX_ROUNDS - 1 ? (bound + 1) / 2 + 1 : BIS_MAX_ROUNDS - 1;
+  for (int j = 0; j < rounds; ++j) {
+    if ((rc = mlp((int)(3 * N), w.c + C_BR + j, 3))) return rc;
+    bis_flag_kernel<<<nb1, 256, 0, st>>>(A, j);
+    IRONB_CHECK_LAUNCH("bis_flag_kernel");
+    bis_update_kernel<<<nb, 256, 0, st>>>(A, j, j == rounds - 1 ? 1 : 0);
     IRONB_CHECK_LAUNCH("bis_update_kernel");
   }
-  if ((rc = mlp((int)N, w.c + C_NROOT, 1))) return rc;
-  bis_final_kernel<<<nb1, 256, 0, st>>>(A);
-  IRONB_CHECK_LAUNCH("bis_final_kernel");
+  bis_stats_kernel<<<1, 32, 0, st>>>(A);
+  IRONB_CHECK_LAUNCH("bis_stats_kernel");
   return IRONB_OK;
 }
 
