@@ -251,6 +251,31 @@ int ironb_composite_bwd(const float* light, const float* dist, const float* norm
                         float* d_light, float* d_dist, float* d_normal, float* d_kd, float* d_ks, float* d_alpha,
                         float* d_metallic_eta, float* d_metallic_k, float* d_dielectric_eta, void* stream);
 
+/* ---------------------------------------------------------------- glue of a shading step (csrc/glue.cu)
+ * The element-wise chains between the big kernels, one launch forward and one backward each (the reference issues them as
+ * separate ATen ops).  M rows; [M,3] / [M] contiguous fp32; any upstream gradient pointer may be NULL (= zeros).
+ *   unit_dist : n = g / (|g| + 1e-10), dist = |x - o|                          render_surface.py:135-146
+ *   reparam   : forward value == x; d f = -sum_c v_c / clamp(g.v, 1e-4) d x_c   models/raytracer.py:17-24
+ *   matpost   : kd = |a|, ks = mean_c |b_c| (|b| if is_metal), alpha = |c| + 0.01   models/rendering_func.py:5-16
+ *   eik_sum   : out += sum_m w_m (|g_m| - 1)^2  (w NULL = ones)                 render_surface.py:580-583, 601-603
+ *   roughrange: loss = weight * mean_{w_m != 0, r_m > value} (r_m - value), 0 if empty; acc = 2 zeroed floats   :609-613
+ *   mask_rows : dst_t[m][:] = src_t[m][:] * w[m] for n <= 8 row tensors       (dense shading: zero the non-hit pixels) */
+int ironb_unit_dist_fwd(const float* g, const float* x, const float* o, int64_t M, float* n, float* dist, void* stream);
+int ironb_unit_dist_bwd(const float* g, const float* x, const float* o, const float* dn, const float* ddist, int64_t M,
+                        float* dg, float* dx, void* stream);
+int ironb_reparam_bwd(const float* g, const float* v, const float* dx, int64_t M, float* df, void* stream);
+int ironb_matpost_fwd(const float* a, const float* b, const float* c, int64_t M, int is_metal, float* kd, float* ks, float* alpha,
+                      void* stream);
+int ironb_matpost_bwd(const float* a, const float* b, const float* c, const float* dkd, const float* dks, const float* dalpha,
+                      int64_t M, int is_metal, float* da, float* db, float* dc, void* stream);
+int ironb_eik_sum_fwd(const float* g, const float* w, int64_t M, float* out, void* stream);
+int ironb_eik_sum_bwd(const float* g, const float* w, const float* up, int64_t M, float* dg, void* stream);
+int ironb_roughrange_fwd(const float* r, const float* w, int64_t M, float value, float weight, float* acc, float* loss,
+                         void* stream);
+int ironb_roughrange_bwd(const float* r, const float* w, const float* acc, const float* up, int64_t M, float value, float weight,
+                         float* dr, void* stream);
+int ironb_mask_rows(const float* const* src, float* const* dst, const int* width, int n, const float* w, int64_t M, void* stream);
+
 /* ---------------------------------------------------------------- patch losses
  * One [C][H][W] image pair (C <= 4), addressed through ELEMENT strides {channel, row, column}, so the [1,3,H,W] view of
  * the renderer's [H,W,3] buffer is read in place.  Value and gradient w.r.t. the first image in one call; `ws` from

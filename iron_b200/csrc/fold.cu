@@ -48,8 +48,6 @@ __global__ void __launch_bounds__(256) fold_kernel(ironb_mlp_layout L, FoldArgs 
   // fp16x2-split copies for the tensor cores: hi = fp16(w), lo = fp16((w - hi) * 2^11); the lo block follows the hi block
   __half* Whi = L.off_h16[l] > 0 ? reinterpret_cast<__half*>(packed + L.off_h16[l]) + (int64_t)n * Kp : nullptr;
   __half* Wlo = Whi ? Whi + (int64_t)Np * Kp : nullptr;
-  __half* WThi = L.off_h16t[l] > 0 ? reinterpret_cast<__half*>(packed + L.off_h16t[l]) + n : nullptr;
-  __half* WTlo = WThi ? WThi + (int64_t)Np * Kp : nullptr;
   for (int k = lane; k < K; k += 32) {
     float w = v[k] * sc;
     W[k] = w;
@@ -57,9 +55,26 @@ __global__ void __launch_bounds__(256) fold_kernel(ironb_mlp_layout L, FoldArgs 
     const __half h = __float2half_rn(w);
     const __half lo = __float2half_rn((w - __half2float(h)) * 2048.f);
     if (Whi) { Whi[k] = h; Wlo[k] = lo; }
-    if (WThi) { WThi[(int64_t)k * Np] = h; WTlo[(int64_t)k * Np] = lo; }
   }
   if (lane == 0) packed[L.off_b[l] + n] = A.b[l] ? A.b[l][n] : 0.f;
+}
+
+// fp16x2-split copy of W_l^T for every layer of an SDF net: consecutive threads write consecutive halfs of a W^T row (the fold
+// kernel's warp-per-row layout would scatter 2-byte stores with a pitch of out_pad halfs); reads the fp32 W^T written above.
+__global__ void __launch_bounds__(256) fold_wt_h16_kernel(ironb_mlp_layout L, float* __restrict__ packed) {
+  const int l = blockIdx.y;
+  if (L.off_h16t[l] <= 0) return;
+  const int64_t n_el = (int64_t)L.in_pad[l] * L.out_pad[l];
+  const float* __restrict__ WT = packed + L.off_wt[l];
+  __half* __restrict__ hi = reinterpret_cast<__half*>(packed + L.off_h16t[l]);
+  __half* __restrict__ lo = hi + n_el;
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 2; i < n_el; i += (int64_t)gridDim.x * blockDim.x * 2) {
+    const float2 w = *reinterpret_cast<const float2*>(WT + i);
+    const __half2 h = __floats2half2_rn(w.x, w.y);
+    const float2 hf = __half22float2(h);
+    *reinterpret_cast<__half2*>(hi + i) = h;
+    *reinterpret_cast<__half2*>(lo + i) = __floats2half2_rn((w.x - hf.x) * 2048.f, (w.y - hf.y) * 2048.f);
+  }
 }
 
 __global__ void __launch_bounds__(256) fold_bwd_kernel(ironb_mlp_layout L, FoldArgs A, const float* __restrict__ dpacked) {
@@ -112,6 +127,10 @@ extern "C" int ironb_mlp_fold(const ironb_mlp_layout* lay, const float* const* v
   int blocks = (rows + 7) / 8;
   fold_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*lay, A, packed);
   IRONB_CHECK_LAUNCH("fold_kernel");
+  if (lay->kind == 0) {
+    fold_wt_h16_kernel<<<dim3(64, (unsigned)lay->n_lin), 256, 0, as_stream(stream)>>>(*lay, packed);
+    IRONB_CHECK_LAUNCH("fold_wt_h16_kernel");
+  }
   return IRONB_OK;
 }
 

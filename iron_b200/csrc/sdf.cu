@@ -37,11 +37,11 @@ __global__ void __launch_bounds__(256) pe_kernel(const float* __restrict__ x, in
     f *= 2.f;
   }
   for (; w < Epad; ++w) o[w] = 0.f;
-  if (ehi != nullptr) {
-    for (int i = 0; i < Epad; ++i) {
-      const __half h = __float2half_rn(o[i]);
-      ehi[m * Epad + i] = h;
-      elo[m * Epad + i] = __float2half_rn((o[i] - __half2float(h)) * 2048.f);
+  if (ehi != nullptr) {      // the row was just written by this thread: re-read it 4 floats at a time (Epad is a multiple of 8)
+    for (int i = 0; i < Epad; i += 4) {
+      const float4 v4 = *reinterpret_cast<const float4*>(o + i);
+      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+      h16::store_split4(ehi, elo, m * Epad + i, v);
     }
   }
 }

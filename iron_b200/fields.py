@@ -226,11 +226,11 @@ class SDFNetwork(_FoldedMLP):
                                                 C.byref(self.layout)), "sdf_layout")
 
     # -- evaluation -----------------------------------------------------------------------------------
-    def _eval(self, x: torch.Tensor, want_yf: bool, want_grad: bool):
+    def _eval(self, x: torch.Tensor, want_yf: bool, want_grad: bool, params=None):
         self._check_device(x)
         sh = list(x.shape[:-1])
         xf = _lib.f32c(x.detach().reshape(-1, 3))
-        y, feat, grad = _SDFEval.apply(self, xf, want_yf, want_grad, *self._param_list())
+        y, feat, grad = _SDFEval.apply(self, xf, want_yf, want_grad, *(params if params is not None else self._param_list()))
         y = y.reshape(sh + [1]) if want_yf else None
         feat = feat.reshape(sh + [feat.shape[-1]]) if want_yf else None
         grad = grad.reshape(sh + [3]) if want_grad else None
@@ -249,6 +249,31 @@ class SDFNetwork(_FoldedMLP):
     def gradient(self, x):
         """d sdf / d x  [..., 3]; differentiable w.r.t. the parameters (create_graph=True in the reference, :106-118)."""
         return self._eval(x, False, True)[2]
+
+    def gradient_aliased(self, x):
+        """gradient(x), differentiated w.r.t. ALIAS leaves of the parameters (same storage, separate autograd identity).
+
+        A stage-2 step uses the SDF parameters twice (hit points and eikonal samples), so autograd ends the backward pass with
+        one `p.grad += g` launch per parameter tensor (27 launches on the step's critical path).  With the second use
+        differentiated w.r.t. aliases, both gradient sets arrive separately and `add_alias_grads` merges them with one
+        multi-tensor launch.  Returns (gradient, aliases); call `add_alias_grads(aliases)` after `backward()`."""
+        aliases = [p.detach().requires_grad_(True) for p in self._param_list()]
+        return self._eval(x, False, True, params=aliases)[2], aliases
+
+    @torch.no_grad()
+    def add_alias_grads(self, aliases):
+        ps = self._param_list()
+        dst, src = [], []
+        for p, a in zip(ps, aliases):
+            if a.grad is None:
+                continue
+            if p.grad is None:
+                p.grad = a.grad
+            else:
+                dst.append(p.grad)
+                src.append(a.grad)
+        if dst:
+            torch._foreach_add_(dst, src)
 
     def get_all(self, x, is_training=True):
         """(sdf [...,1], feature [...,d_out-1], d sdf/d x [...,3]), detached when not training (:120-137)."""

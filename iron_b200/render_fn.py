@@ -3,6 +3,7 @@ three material networks, shade with the colocated-flash GGX model and scatter th
 zero-filled buffers.  `make_render_fn(renderer)` returns the callback `render_normal_and_color` expects."""
 import torch
 
+from . import _fused
 from .rendering_func import get_materials, get_materials_comp
 
 
@@ -31,11 +32,11 @@ def make_render_fn(renderer, is_metal=False):
         if points.shape[0] == 0:
             return {"color": z3(), "diffuse_color": z3(), "specular_color": z3(), "diffuse_albedo": z3(),
                     "specular_albedo": z3(), "specular_roughness": z3()[..., 0].clone(), "normal": z3()}
-        normals = normals / (normals.norm(dim=-1, keepdim=True) + 1e-10)
+        # n = g / (|g| + 1e-10) and |x - o| in one launch (render_surface.py:135-146)
+        normals, dist = _fused.unit_normal_and_distance(normals, points, ray_o)
         params = get_materials(network_dict=color_network_dict, points=points, normals=normals, features=features,
                                is_metal=is_metal)
-        res = renderer(color_network_dict["point_light_network"](), (points - ray_o).norm(dim=-1, keepdim=True),
-                       normals, -ray_d, params=params)
+        res = renderer(color_network_dict["point_light_network"](), dist, normals, -ray_d, params=params)
         if dense:
             idx = None
         return {

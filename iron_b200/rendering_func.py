@@ -2,6 +2,8 @@
 RenderingNetworks (fused CUDA forward/backward) plus the reference's post-ops (abs, channel mean, +0.01)."""
 import torch
 
+from . import _fused
+
 
 def get_materials(network_dict, points, normals, features, is_metal=False):
     """network_dict may carry `"_ironb_streams": [s1, s2]` (GraphedStage2Step sets it): the specular-albedo and roughness
@@ -9,36 +11,35 @@ def get_materials(network_dict, points, normals, features, is_metal=False):
     fills only 64 of the 148 SMs (256 output features), so two run side by side; autograd replays the same placement in
     the backward pass.  Same arithmetic either way."""
     streams = network_dict.get("_ironb_streams") if isinstance(network_dict, dict) else None
-
-    def diffuse():
-        return network_dict["diffuse_albedo_network"](points, normals, -normals, features).abs()
-
-    def specular():
-        sa = network_dict["specular_albedo_network"](points, normals, None, features).abs()
-        if not is_metal:
-            sa = torch.mean(sa, dim=-1, keepdim=True).expand_as(sa)
-        return sa
-
-    def roughness():
-        return network_dict["specular_roughness_network"](points, normals, None, features).abs() + 0.01
-
+    d_net, s_net, r_net = (network_dict[k] for k in ("diffuse_albedo_network", "specular_albedo_network",
+                                                      "specular_roughness_network"))
+    neg_n = -normals
     if streams and points.is_cuda:
         cur = torch.cuda.current_stream(points.device)
-        for net in ("diffuse_albedo_network", "specular_albedo_network", "specular_roughness_network"):
-            network_dict[net].folded()                    # folds happen on the current stream, before the fork
+        for net in (d_net, s_net, r_net):
+            net.folded()                                  # folds happen on the current stream, before the fork
         for st in streams[:2]:
             st.wait_stream(cur)
         with torch.cuda.stream(streams[0]):
-            specular_albedo = specular()
+            sa = s_net(points, normals, None, features)
         with torch.cuda.stream(streams[1]):
-            specular_roughness = roughness()
-        diffuse_albedo = diffuse()
+            sr = r_net(points, normals, None, features)
+        da = d_net(points, normals, neg_n, features)
         for st in streams[:2]:
             cur.wait_stream(st)
     else:
-        diffuse_albedo = diffuse()
-        specular_albedo = specular()
-        specular_roughness = roughness()
+        da = d_net(points, normals, neg_n, features)
+        sa = s_net(points, normals, None, features)
+        sr = r_net(points, normals, None, features)
+    if points.is_cuda and da.dim() == 2 and da.shape[-1] == 3 and sa.shape[-1] == 3 and sr.shape[-1] == 1:
+        # abs / channel mean / + 0.01 of all three heads in one launch (csrc/glue.cu); same values as the expressions below
+        diffuse_albedo, specular_albedo, specular_roughness = _fused.material_post(da, sa, sr, is_metal)
+    else:
+        diffuse_albedo = da.abs()
+        specular_albedo = sa.abs()
+        if not is_metal:
+            specular_albedo = torch.mean(specular_albedo, dim=-1, keepdim=True).expand_as(specular_albedo)
+        specular_roughness = sr.abs() + 0.01
     return {
         "diffuse_albedo": diffuse_albedo,
         "specular_albedo": specular_albedo,

@@ -5,6 +5,7 @@ from __future__ import annotations
 
 import torch
 
+from . import _fused
 from .image_losses import PyramidL2Loss, ssim_loss_fn
 from .raytracer import Camera, render_camera
 
@@ -23,9 +24,16 @@ def stage2_step(sdf_network, color_network_dict, raytracer, render_fn, camera, t
     eikonal_stream: a second CUDA stream for the eikonal query on the random points (render_surface.py:580-583).  It does
     not depend on the traced surface, so its forward can run next to the tracer (whose rounds leave most SMs idle once
     rays converge) and its backward next to the shading backward; same arithmetic, same summation order."""
+    aliases = []
+
     def eikonal_points_term():
-        eg = sdf_network.gradient(eik_points).view(-1, 3)             # render_surface.py:580-583
-        return eg.shape[0], ((eg.norm(dim=-1) - 1) ** 2).sum()
+        if hasattr(sdf_network, "gradient_aliased"):                  # second use of the parameters: see gradient_aliased
+            eg, al = sdf_network.gradient_aliased(eik_points)
+            aliases.append(al)
+        else:
+            eg = sdf_network.gradient(eik_points)
+        eg = eg.view(-1, 3)                                           # render_surface.py:580-583
+        return eg.shape[0], _fused.eikonal_sum(eg)                    # sum (|g| - 1)^2, one launch (csrc/glue.cu)
 
     if eikonal_stream is not None:
         cur = torch.cuda.current_stream()
@@ -49,23 +57,20 @@ def stage2_step(sdf_network, color_network_dict, raytracer, render_fn, camera, t
         pred_img = results["color"].permute(2, 0, 1).unsqueeze(0)
         gt_img = target.permute(2, 0, 1).unsqueeze(0)
         img = _pyramid_l2(pred_img, gt_img) + ssim_weight * ssim_loss_fn(pred_img, gt_img, mask.unsqueeze(0).unsqueeze(0))
-        rough = results["specular_roughness"]
-        sel = (mask & (rough > 0.5)).to(rough.dtype)
-        n_sel = sel.sum()
-        img = img + ((rough - 0.5) * sel).sum() / n_sel.clamp_min(1.0) * roughrange_weight
+        img = img + _fused.roughrange(results["specular_roughness"], mask.float(), 0.5, roughrange_weight)
         img = img * mask.any().to(img.dtype)
     else:
         img = ((results["color"] - target) ** 2).sum() / float(mask.numel())
-    hn = results["normal"].reshape(-1, 3)
-    hm = mask.reshape(-1, 1).float()
     n_hit = mask.sum()
-    eik = eik + (((hn.norm(dim=-1, keepdim=True) - 1) ** 2) * hm).sum()   # hit normals (:601-603), no host sync
+    eik = eik + _fused.eikonal_sum(results["normal"].reshape(-1, 3), mask.reshape(-1).float())   # hit normals (:601-603), no host sync
     if "edge_pos_neg_normal" in results:                                  # :604-607
         en = results["edge_pos_neg_normal"]
         eik_cnt += en.shape[0]
         eik = eik + ((en.norm(dim=-1) - 1) ** 2).sum()
     loss = img + eik / (eik_cnt + n_hit) * eik_weight
     loss.backward()
+    for al in aliases:
+        sdf_network.add_alias_grads(al)
     return loss.detach(), results
 
 
