@@ -390,7 +390,8 @@ def run_ours(args):
     # weak scaling over patches: every rank traces and shades ITS OWN crop of the view (rank 0 = the canonical
     # centre crop, the others tile around it: parallel.crop_for_rank), so the ranks' work differs like it does in training;
     # the per-rank step times are reported next to the max that defines `value`
-    ul = crop_corner(rank, S) if not os.environ.get("IRONB_BENCH_SAME_CROP") else crop_corner(0, S)
+    crop_rank = int(os.environ.get("IRONB_BENCH_CROP_RANK", rank))      # diagnostic: run another rank's crop on one GPU
+    ul = crop_corner(crop_rank, S) if not os.environ.get("IRONB_BENCH_SAME_CROP") else crop_corner(0, S)
     target_h = (torch.rand(S, S, 3, generator=torch.Generator().manual_seed(11 + rank)) * 0.5).pin_memory()
     eik_h = torch.empty(S * S // 2, 3).uniform_(-1.0, 1.0, generator=torch.Generator().manual_seed(12 + rank)).pin_memory()
 

@@ -90,6 +90,11 @@ float ironb_set_mlp_debias(float g);
  * tracer calls of at most ~8,192 rays -- the latency shape -- else 128 per CTA in clusters of H/128), 64 / 128 force one.
  * Returns the previous setting.  IRONB_MLP_RN sets it at start-up. */
 int ironb_set_mlp_rn(int rn);
+/* Debug builds (IRONB_NVCC_EXTRA=-DIRONB_DEBUG_HANG): every mbarrier wait of the tcgen05 kernels is bounded (~2 s); a wait that
+ * expires writes {tag, block, thread, parity, position} into this MAPPED PINNED host buffer (>= 4 KiB, zeroed; word 0 counts
+ * the records, record i starts at word 8 + 8 i) and traps, so a pipeline slip is a located fault instead of a silent hang.
+ * Returns 1 if the hooks are compiled in, 0 if not. */
+int ironb_debug_hang_buffer(void* mapped_host);
 /* C[M][ldc] = A[M][lda] * B[N][ldb]^T (fp32, K-major operands, N/K/ld multiples of 4): unit-test entry of both GEMMs. */
 int ironb_gemm_nt(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float* C, int ldc,
                   int mode, void* stream);

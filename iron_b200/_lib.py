@@ -49,6 +49,7 @@ _PROTOS = {
     "ironb_set_trace_mode": (_INT, [_INT]),
     "ironb_set_mlp_debias": (_F, [_F]),
     "ironb_set_mlp_rn": (_INT, [_INT]),
+    "ironb_debug_hang_buffer": (_INT, [_P]),
     "ironb_gemm_nt": (_INT, [_P, _INT, _P, _INT, _INT, _INT, _INT, _P, _INT, _INT, _P]),
     "ironb_gemm_nt_h16": (_INT, [_P, _P, _INT, _P, _P, _INT, _INT, _INT, _INT, _P, _INT, _P]),
     "ironb_gemm_tn_scratch_bytes": (_I64, [_INT, _INT, _INT]),

@@ -22,7 +22,7 @@ INCLUDE = os.path.join(HERE, "..", "include")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("IRONB_NVCC_EXTRA", "").split()      # e.g. -DIRONB_DEBUG_HANG: bounded mbarrier waits (gemm_tc.cuh)
 
 
 def nvcc() -> str:

@@ -105,7 +105,7 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
     for (int it = 0; it < nk; ++it) {
       const int s = it % HSTAGES;
       const uint32_t ph = (it / HSTAGES) & 1;
-      mbar_wait(empty(s), ph ^ 1);
+      mbar_wait(empty(s), ph ^ 1, 21, it);
       const uint32_t st = base + s * HSTAGE;
       if (leader) {
         mbar_arrive_expect_tx(full(s), HSTAGE);
@@ -122,7 +122,7 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
     for (int it = 0; it < nk; ++it) {
       const int s = it % HSTAGES;
       const uint32_t ph = (it / HSTAGES) & 1;
-      mbar_wait(full(s), ph);
+      mbar_wait(full(s), ph, 22, it);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t st = base + s * HSTAGE;
       const uint64_t a_hi = make_desc(st), b_hi = make_desc(st + HTILE);
@@ -143,7 +143,7 @@ gemm_h16_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
     __syncwarp();
   } else {
     // ================= epilogue (warps 2..9) =================
-    mbar_wait(acc_bar, 0);
+    mbar_wait(acc_bar, 0, 24, nk);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     constexpr int TLD = BN + 4;
     float* tile = reinterpret_cast<float*>(base_ptr);

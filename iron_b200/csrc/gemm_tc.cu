@@ -100,6 +100,10 @@ bool split_writes_hi() {
   }
   return m == 1;
 }
+bool split_strict() {
+  static const bool v = [] { const char* e = getenv("IRONB_SPLIT_STRICT"); return !(e && e[0] == '0'); }();
+  return v;
+}
 int set_mode(int mode) {
   int prev = mode_now();
   g_mode.store(mode <= 0 ? 0 : (mode == 1 ? 1 : 2), std::memory_order_relaxed);
@@ -162,4 +166,24 @@ extern "C" int ironb_gemm_tn(const float* A, int lda, const float* B, int ldb, i
     return launch_wgrad_tc(A, lda, B, ldb, M, Nd, Kd, C, ldc, reinterpret_cast<float*>(scratch), as_stream(stream), "gemm_tn (tcgen05)");
   }
   return launch_gemm_tn(A, lda, B, ldb, M, Nd, Kd, C, ldc, as_stream(stream), "gemm_tn (simt)");
+}
+
+namespace ironb {
+IRONB_DEFINE_HANG_SETTER(hang_set_gemm)
+int hang_set_sdf(unsigned long long*);
+int hang_set_matnet(unsigned long long*);
+int hang_set_mlp(unsigned long long*);
+}  // namespace ironb
+
+// Debug builds (-DIRONB_DEBUG_HANG): installs a MAPPED PINNED host buffer (>= 4 KiB, zeroed) that bounded mbarrier waits
+// report into before they trap (gemm_tc.cuh).  Returns 1 if the library was built with the hooks, 0 if not.
+extern "C" int ironb_debug_hang_buffer(void* mapped_host) {
+#ifdef IRONB_DEBUG_HANG
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(mapped_host);
+  int rc = ironb::hang_set_gemm(p) | ironb::hang_set_sdf(p) | ironb::hang_set_matnet(p) | ironb::hang_set_mlp(p);
+  return rc == 0 ? 1 : -1;
+#else
+  (void)mapped_host;
+  return 0;
+#endif
 }

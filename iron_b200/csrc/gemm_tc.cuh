@@ -55,8 +55,41 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// -DIRONB_DEBUG_HANG: every mbarrier wait is bounded.  A wait that polls for ~2 s writes a record {tag, block, thread,
+// parity, extra} through d_hang_buf (a pointer to MAPPED PINNED host memory, still readable after the context is lost) and
+// traps, so a protocol slip becomes a located fault instead of a silent 100 %-busy hang.  ironb_debug_hang_buffer() installs
+// the buffer in every translation unit (each has its own copy of the static symbol).  Tags: 1x gemm_nt_tc (11 empty,
+// 12 conv, 13 full, 14 acc, 15 conv of the other group), 2x gemm_h16 (21 empty, 22 full, 24 acc), 3x mlp_h16 (31 empty, 32 ready, 33 tmem_free, 34 full,
+// 35 stg_full, 36 acc_full, 37 stg_empty).
+#ifdef IRONB_DEBUG_HANG
+static __device__ unsigned long long* d_hang_buf = nullptr;
+__device__ __forceinline__ void hang_report(uint32_t tag, uint32_t parity, uint32_t extra) {
+  unsigned long long* b = d_hang_buf;
+  if (b != nullptr) {
+    const unsigned long long slot = atomicAdd(b, 1ull);
+    if (slot < 63) {
+      unsigned long long* r = b + 8 + slot * 8;
+      r[0] = tag; r[1] = blockIdx.x | ((unsigned long long)blockIdx.y << 20) | ((unsigned long long)blockIdx.z << 40);
+      r[2] = threadIdx.x; r[3] = parity; r[4] = extra; r[5] = gridDim.x | ((unsigned long long)gridDim.y << 20);
+      r[6] = clock64();
+      __threadfence_system();
+    }
+  }
+  __trap();
+}
+#endif
+#ifdef IRONB_DEBUG_HANG
+#define IRONB_DEFINE_HANG_SETTER(name) \
+  int name(unsigned long long* p) { return (int)cudaMemcpyToSymbol(::ironb::tc::d_hang_buf, &p, sizeof(p)); }
+#else
+#define IRONB_DEFINE_HANG_SETTER(name) \
+  int name(unsigned long long*) { return 0; }
+#endif
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag = 0, uint32_t extra = 0) {
   uint32_t ok;
+#ifdef IRONB_DEBUG_HANG
+  unsigned long long polls = 0;
+#endif
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -65,7 +98,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+#ifdef IRONB_DEBUG_HANG
+    if (!ok && ++polls > (1ull << 26)) hang_report(tag, parity, extra);
+#endif
   } while (!ok);
+  (void)tag; (void)extra;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
@@ -165,7 +202,7 @@ __device__ __forceinline__ void split_stage(float4* __restrict__ hi, float4* __r
 template <class Epi>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N, int K,
-                  Epi epi, const int* __restrict__ m_dev, int m_mul, int write_hi, int k_chunk, long long* dbg) {
+                  Epi epi, const int* __restrict__ m_dev, int m_mul, int write_hi, int k_chunk, long long* dbg, int strict) {
   const bool stamp = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   if (stamp && threadIdx.x == 0) dbg[0] = clock64();
   // Programmatic dependent launch: the next kernel of the stream may start its prologue now; this kernel touches global
@@ -225,7 +262,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     for (int it = 0; it < nk; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
-      mbar_wait(empty(s), ph ^ 1);
+      mbar_wait(empty(s), ph ^ 1, 11, it);
       const uint32_t st = base + s * STAGE_BYTES;
       if (leader) {
         mbar_arrive_expect_tx(full(s), HI_BYTES);
@@ -240,7 +277,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     for (int it = 0; it < nk; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
-      mbar_wait(conv(s), ph);
+      mbar_wait(conv(s), ph, 12, it);
       if (stamp && leader && it == 0) dbg[3] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t st = base + s * STAGE_BYTES;
@@ -272,7 +309,19 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     for (int it = grp; it < nk; it += NGRP) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
-      mbar_wait(full(s), ph);
+      // A parity wait is exact only if the barrier cannot be a whole phase BEHIND the one waited for: try_wait.parity also
+      // succeeds when `ph` is the parity of the phase that precedes the current one.  The two splitter groups take alternate
+      // iterations, so this group last saw stage s two uses ago; the use in between (iteration it - STAGES) belongs to the
+      // OTHER group.  If this group gets here before that iteration's TMA load has landed (loads of different stages can
+      // complete out of order under memory contention, e.g. next to another stream's grid), full(s) still sits in the phase
+      // of iteration it - STAGES and a wait on parity `ph` passes at once: the group would split a stage that is still being
+      // written, complete conv(s) a phase early and desynchronise the pipeline (wrong sums, a hang, or a TMA load landing
+      // in the shared memory of an exited CTA = "unspecified launch failure": the multi-stream fault of round 1, root cause).
+      // conv(s) of iteration it - STAGES completes only after that iteration's load has landed and cannot advance further
+      // without this group's own arrivals, so waiting for it first makes the wait on full(s) exact.  It costs nothing: the
+      // load of iteration `it` is only issued after the MMAs of it - STAGES, which need that conv(s) phase anyway.
+      if (strict && it >= STAGES) mbar_wait(conv(s), ph ^ 1, 15, it);
+      mbar_wait(full(s), ph, 13, it);
       if (stamp && t == 0 && it == 0) dbg[2] = clock64();
       float4* hi = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES);
       float4* lo = reinterpret_cast<float4*>(base_ptr + s * STAGE_BYTES + HI_BYTES);
@@ -283,7 +332,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     // epilogue, phase 1: TMEM (lane = tile row; warp%4 selects the 32-lane quarter, (warp-2)/4 the 64-column half) ->
     // registers (the three accumulators are added in fp32 RN) -> a row-major fp32 tile in the idle pipeline stages
     if (stamp && t == 0) dbg[5] = clock64();
-    mbar_wait(acc_bar, 0);
+    mbar_wait(acc_bar, 0, 14, nk);
     if (stamp && t == 0) dbg[6] = clock64();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     constexpr int TLD = BN + 4;                       // padded row pitch: conflict-free 128-bit rows
@@ -345,6 +394,7 @@ int make_map(CUtensorMap* map, const float* ptr, int rows, int K, int ld);
 int make_map_h(CUtensorMap* map, const void* ptr, int rows, int K, int ld, int box_rows = 128);   // fp16, 64 x box_rows box
 bool tc_enabled();
 bool pdl_enabled();       // programmatic dependent launch of the GEMM kernels (IRONB_PDL=1 switches it on; see gemm_tc.cu)
+bool split_strict();      // 1 (default): exact phase tracking of the splitter groups; IRONB_SPLIT_STRICT=0 restores the round-1 race (diagnostic)
 bool split_writes_hi();   // 0 (default): raw fp32 stays as the hi operand; 1 (IRONB_SPLIT_WRITE_HI=1): store the truncated hi back
 
 template <class Epi>
@@ -372,7 +422,7 @@ int launch_gemm_nt_tc_maps(const CUtensorMap& mA, const CUtensorMap& mB, int M, 
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;          // no attribute at all unless PDL is switched on
   long long* dbg = g_mlp_dbg ? g_mlp_dbg + 256 : nullptr;   // IRONB debug timeline (last launch wins)
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mA, mB, M, N, K, epi, m_dev, m_mul, write_hi, k_chunk, dbg);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, mA, mB, M, N, K, epi, m_dev, m_mul, write_hi, k_chunk, dbg, split_strict() ? 1 : 0);
   if (le != cudaSuccess) { (void)cudaGetLastError(); note_launch(); set_error("%s: %s", what, cudaGetErrorString(le)); return (int)le; }
   IRONB_CHECK_LAUNCH(what);
   return IRONB_OK;

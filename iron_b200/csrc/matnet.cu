@@ -312,3 +312,5 @@ extern "C" int ironb_matnet_bwd(const ironb_mlp_layout* lay, const ironb_matnet_
   if ((frc = fork_to(wst, st))) return frc;      // join: dpacked is complete on st
   return IRONB_OK;
 }
+
+namespace ironb { IRONB_DEFINE_HANG_SETTER(hang_set_matnet) }

@@ -117,8 +117,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                : "memory");
 }
 // wait on an mbarrier other CTAs of the cluster arrive on: acquire at cluster scope
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, uint32_t tag = 0, uint32_t extra = 0) {
   uint32_t ok;
+#ifdef IRONB_DEBUG_HANG
+  unsigned long long polls = 0;
+#endif
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -127,7 +130,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+#ifdef IRONB_DEBUG_HANG
+    if (!ok && ++polls > (1ull << 26)) hang_report(tag, parity, extra);
+#endif
   } while (!ok);
+  (void)tag; (void)extra;
 }
 // Remote arrive WITHOUT its own release: every release.cluster arrive costs a GPU-scope membar (~1k cycles, measured
 // 4 of them back to back), so the caller issues ONE fence.acq_rel.cluster and then these relaxed arrives.
@@ -223,7 +230,7 @@ __device__ __forceinline__ void epi_unit(const Args& a, const EpiCtx& c, int l, 
       }
     }
     if (!LAST) {
-      mbar_wait(c.stg_empty, (se_n & 1u) ^ 1u);           // the previous half's TMA store has read the staging buffer
+      mbar_wait(c.stg_empty, (se_n & 1u) ^ 1u, 37, (uint32_t)(l * 4 + s * 2 + h));           // the previous half's TMA store has read the staging buffer
       ++se_n;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {                       // two 16-byte chunks (8 halfs each) per operand
@@ -336,7 +343,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
         for (; ib < ahead; ++ib) {                        // weights do not depend on the previous layer: run ahead
           const uint32_t sidx = (it + ib) % NSTAGE, ph = ((it + ib) / NSTAGE) & 1u;
           const int kb = (l == 0) ? ib : HP * (ib % C) + (ib / C);
-          mbar_wait(empty(sidx), ph ^ 1u);
+          mbar_wait(empty(sidx), ph ^ 1u, 31, (uint32_t)(l * 64 + j * 32 + ib));
           const uint32_t st = base + sidx * STAGE;
           if (leader) {
             mbar_arrive_expect_tx(full(sidx), STAGE);
@@ -346,7 +353,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
         }
         if (wait_pt) {
           const int h = ia / C;
-          mbar_wait_cluster(ready(sp, h), (rdy_bits >> (sp * 2 + h)) & 1u);
+          mbar_wait_cluster(ready(sp, h), (rdy_bits >> (sp * 2 + h)) & 1u, 32, (uint32_t)(l * 4 + sp * 2 + h));
           rdy_bits ^= 1u << (sp * 2 + h);
         }
         const uint32_t sidx = (it + ia) % NSTAGE;
@@ -369,7 +376,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
       MLP16_UNIT_SLOTS
       const int K = a.kpad[l];
       const int nk = (K + BKH - 1) / BKH, ksteps = (K + 15) / 16;
-      mbar_wait(tmem_free(s), (free_n[s] & 1u) ^ 1u);
+      mbar_wait(tmem_free(s), (free_n[s] & 1u) ^ 1u, 33, (uint32_t)(l * 2 + j));
       ++free_n[s];
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t acc = tmem + (uint32_t)s * ncol_slot;
@@ -377,7 +384,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
       for (int i = 0; i < nk; ++i) {
         const uint32_t sidx = (it + i) % NSTAGE, ph = ((it + i) / NSTAGE) & 1u;
         if (stamp && leader && i == 0 && t0 == 0 && j == 0) a.dbg[l * 8 + 0] = clock64();
-        mbar_wait(full(sidx), ph);
+        mbar_wait(full(sidx), ph, 34, (uint32_t)(l * 64 + j * 32 + i));
         if (stamp && leader && i == 0 && t0 == 0 && j == 0) a.dbg[l * 8 + 1] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = base + sidx * STAGE;
@@ -415,7 +422,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
       const int m0 = (t0 + j * G) * RM;
       const CUtensorMap* mh = &maps.u[l & 1][0];
       const CUtensorMap* ml = &maps.u[l & 1][1];
-      mbar_wait(stg_full(h), sf_n & 1u);
+      mbar_wait(stg_full(h), sf_n & 1u, 35, (uint32_t)(l * 4 + j * 2 + h));
       ++sf_n;
       if (leader) {
         if (stamp && t0 == 0 && j == 0 && h == 0) a.dbg[l * 8 + 5] = clock64();
@@ -452,7 +459,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_h16_kernel(const __grid_constant__ 
       const bool mine = (lane >> 4) < HP;                   // RN = 64: lanes 16..31 hold no column
       const float mybias = mine ? __ldg(a.bias[l] + mycol) : 0.f;
       const float mywl = (last && mine) ? __ldg(a.w_last + mycol) : 0.f;
-      mbar_wait(acc_full(s), acc_n[s] & 1u);
+      mbar_wait(acc_full(s), acc_n[s] & 1u, 36, (uint32_t)(l * 2 + j));
       ++acc_n[s];
       const bool st = stamp && threadIdx.x == NCTRL * 32 && t0 == 0 && j == 0;
       if (st) a.dbg[l * 8 + 3] = clock64();
@@ -658,3 +665,5 @@ extern "C" int ironb_debug_mlp_timeline(long long* host_out, int n) {
   if (host_out && n > 0) cudaMemcpy(host_out, ironb::g_mlp_dbg, (size_t)(n < 512 ? n : 512) * sizeof(long long), cudaMemcpyDeviceToHost);
   return 1;
 }
+
+namespace ironb { IRONB_DEFINE_HANG_SETTER(hang_set_mlp) }

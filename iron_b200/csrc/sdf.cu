@@ -522,3 +522,5 @@ extern "C" int ironb_sdf_getall_bwd(const ironb_mlp_layout* lay, const float* pa
   if ((frc = fork_to(wst, st))) return frc;      // join: dpacked is complete on st
   return IRONB_OK;
 }
+
+namespace ironb { IRONB_DEFINE_HANG_SETTER(hang_set_sdf) }
