@@ -114,11 +114,14 @@ class ClockSampler:
 
 
 def crop_corner(rank: int, patch: int):
-    """Per-rank crop of the 512x512 view: rank 0 = the canonical centre crop, others tile around it."""
-    offs = [(0, 0), (1, 0), (-1, 0), (0, 1), (0, -1), (1, 1), (-1, -1), (1, -1)]
-    dx, dy = offs[rank % 8]
-    c = 256 - patch // 2
-    return (min(max(c + dx * patch, 0), 512 - patch), min(max(c + dy * patch, 0), 512 - patch))
+    """Per-rank crop of the 512x512 view: rank 0 = the canonical centre crop; the other ranks take DISTINCT windows
+    shifted by patch/8 pixels around it (parallel.crop_for_rank).  Weak scaling needs the same work per GPU at every N, and the
+    fixture object covers only ~145 pixels of the view: at the 64x64 training patch the shifted windows stay inside the
+    silhouette like the centre crop (every ray hits), while windows TILED around the centre (IRONB_BENCH_CROP_STRIDE=<patch>)
+    straddle the silhouette and cost about twice the centre crop -- that measures load imbalance, not scaling."""
+    from iron_b200.parallel import crop_for_rank
+    stride = int(os.environ.get("IRONB_BENCH_CROP_STRIDE", max(patch // 8, 1)))
+    return crop_for_rank(rank, patch, stride=stride)
 
 
 # ------------------------------------------------------------------------------------------ CPU oracle arm
@@ -311,7 +314,7 @@ def workload_config(args, patch):
                         f"colocated-flash fixture view, trace+shade+loss+backward",
             "sdf_mlp": f"8x{args.hidden}, PE L=6, skip@4, softplus(100), weight-norm", "material_mlps": "3 x (4x256, ReLU)",
             "rays_per_gpu": patch * patch, "eikonal_points": patch * patch // 2,
-            "sharding": "every rank traces/shades its own crop of the view (rank 0: the centre crop, the others tile around it), own target/eikonal seeds", "parallelism": f"dp{args.gpus} (rays sharded, weights replicated)",
+            "sharding": "every rank traces/shades its own crop of the view (rank 0: the centre crop, the others distinct windows patch/8 pixels apart around it = the same work per GPU; IRONB_BENCH_CROP_STRIDE=<patch> tiles them), own target/eikonal seeds; gradients packed into one flat buffer by the graph, one in-place all-reduce", "parallelism": f"dp{args.gpus} (rays sharded, weights replicated)",
             "l2": "256 MiB flush between steps, outside the per-step CUDA-event pairs",
             "init": "seed-0 geometric init, light=32",
             "loss": ("PyramidL2 + 1.0 * SSIM(masked) + 0.1 * roughness range + 0.1 * eikonal: the reference's training loss, "
@@ -362,7 +365,7 @@ def run_ours(args):
 
     import iron_b200 as ib
     from iron_b200 import _lib
-    from iron_b200.parallel import allreduce_gradients
+    from iron_b200.parallel import allreduce_flat, allreduce_gradients
     from oracle import iron_oracle as O   # fixture constants only (camera K / W2C); nothing is computed with it here
     lib = _lib.load()
     if args.tracer != "default":
@@ -387,9 +390,9 @@ def run_ours(args):
     tracer.collect_stats = True
     K_h = torch.tensor(O.FIXTURE_K, dtype=torch.float64).reshape(4, 4).float().pin_memory()
     W2C_h = torch.tensor(O.FIXTURE_W2C, dtype=torch.float64).reshape(4, 4).float().pin_memory()
-    # weak scaling over patches: every rank traces and shades ITS OWN crop of the view (rank 0 = the canonical
-    # centre crop, the others tile around it: parallel.crop_for_rank), so the ranks' work differs like it does in training;
-    # the per-rank step times are reported next to the max that defines `value`
+    # weak scaling over patches: every rank traces and shades ITS OWN crop of the view with its own target and
+    # eikonal samples (rank 0 = the canonical centre crop, the others distinct windows around it: crop_corner); the per-rank
+    # step times are reported next to the max that defines `value`
     crop_rank = int(os.environ.get("IRONB_BENCH_CROP_RANK", rank))      # diagnostic: run another rank's crop on one GPU
     ul = crop_corner(crop_rank, S) if not os.environ.get("IRONB_BENCH_SAME_CROP") else crop_corner(0, S)
     target_h = (torch.rand(S, S, 3, generator=torch.Generator().manual_seed(11 + rank)) * 0.5).pin_memory()
@@ -414,7 +417,8 @@ def run_ours(args):
     if use_graph:
         tracer.collect_stats = os.environ.get("IRONB_BENCH_STATS", "1") != "0"
         gs = ib.GraphedStage2Step(sdf, nets, tracer, render_fn, K_h, W2C_h, (S, S), S * S // 2, crop_ul=ul,
-                                  time_tracer=os.environ.get("IRONB_BENCH_TIME_TRACER", "1") != "0", image_loss=args.loss)
+                                  time_tracer=os.environ.get("IRONB_BENCH_TIME_TRACER", "1") != "0", image_loss=args.loss,
+                                  flat_grads=world > 1, grad_scale=1.0 / world)
         stage("graph captured")
         gs.step(target=target_h, eik_points=eik_h)
         torch.cuda.synchronize()
@@ -423,8 +427,8 @@ def run_ours(args):
     def step(cam_, target_, eik_, time_trace=False):
         if gs is not None:           # inputs are already in the graph's static buffers (cam_/target_/eik_ are those values)
             gs.graph.replay()
-            if world > 1:
-                allreduce_gradients(params, world)
+            if world > 1:          # the graph's tail packed the gradients (x 1/world) into one buffer: one in-place all-reduce
+                allreduce_flat(gs.flat_grad, world)
             return gs.loss, gs.results
         for p in params:
             p.grad = None
@@ -544,7 +548,7 @@ def run_ours(args):
         if gs is not None:     # H2D into the graph's static buffers (patch, samples, camera matrices), replay, all-reduce
             gs.step(target=target_h, eik_points=eik_h, K=K_h, W2C=W2C_h)
             if world > 1:
-                allreduce_gradients(params, world)
+                allreduce_flat(gs.flat_grad, world)
             return gs.loss
         # the camera is built from the HOST matrices (inverted on the host; K, W2C and their inverses are uploaded from
         # pinned memory), the target patch and the eikonal samples are copied from pinned host buffers

@@ -280,6 +280,11 @@ int ironb_roughrange_fwd(const float* r, const float* w, int64_t M, float value,
 int ironb_roughrange_bwd(const float* r, const float* w, const float* acc, const float* up, int64_t M, float value, float weight,
                          float* dr, void* stream);
 int ironb_mask_rows(const float* const* src, float* const* dst, const int* width, int n, const float* w, int64_t M, void* stream);
+/* Gradient bucket of the data-parallel step (the reference is single-GPU, no interface replaced):
+ * flat[off[t] .. off[t] + off[n + t]) = scale * src[t][:] for t < n, zeros where src[t] is NULL.  src_dev (n pointers) and
+ * off_dev (n element offsets followed by n element counts) are DEVICE arrays, so the launch can be a CUDA-graph node.  max_numel sizes the grid. */
+int ironb_pack_tensors(const float* const* src_dev, const int64_t* off_dev, int n, int64_t max_numel, float* flat, float scale,
+                       void* stream);
 
 /* ---------------------------------------------------------------- patch losses
  * One [C][H][W] image pair (C <= 4), addressed through ELEMENT strides {channel, row, column}, so the [1,3,H,W] view of

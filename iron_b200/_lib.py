@@ -89,6 +89,7 @@ _PROTOS = {
     "ironb_roughrange_fwd": (_INT, [_P, _P, _I64, _F, _F, _P, _P, _P]),
     "ironb_roughrange_bwd": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _P, _P]),
     "ironb_mask_rows": (_INT, [_PP, _PP, C.POINTER(C.c_int), _INT, _P, _I64, _P]),
+    "ironb_pack_tensors": (_INT, [_P, _P, _INT, _I64, _P, _F, _P]),
     "ironb_patch_loss_workspace_bytes": (_I64, [_INT, _INT, _INT]),
     "ironb_pyramid_l2": (_INT, [_P, _PI64, _P, _PI64, _INT, _INT, _INT, _P, _P, _PI64, _P, _I64, _P]),
     "ironb_ssim_loss": (_INT, [_P, _PI64, _P, _PI64, _P, _INT, _INT, _INT, _F, _INT, _F, _F, _F, _P, _P, _PI64, _P, _I64, _P]),

@@ -180,6 +180,32 @@ __global__ void __launch_bounds__(256) mask_rows_kernel(MaskArgs A, const float*
   }
 }
 
+// Gradient bucket of the data-parallel step: tensor t (src[t], numel = off[n + t], src may be null = no gradient) is
+// copied to flat[off[t] ..): blockIdx.y = tensor, grid-stride over its elements (float4 when both sides are 16-byte aligned).
+__global__ void __launch_bounds__(256) pack_tensors_kernel(const float* const* __restrict__ src, const int64_t* __restrict__ off,
+                                                           float* __restrict__ flat, float scale) {
+  const int t = blockIdx.y;
+  const float* __restrict__ s = src[t];
+  const int64_t o = off[t], n = off[gridDim.y + t];
+  float* __restrict__ d = flat + o;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if (s == nullptr) {
+    for (int64_t i = tid; i < n; i += nth) d[i] = 0.f;
+    return;
+  }
+  if ((((uintptr_t)s | (uintptr_t)d) & 15u) == 0) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += nth) {
+      float4 v = reinterpret_cast<const float4*>(s)[i];
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      reinterpret_cast<float4*>(d)[i] = v;
+    }
+    for (int64_t i = (n4 << 2) + tid; i < n; i += nth) d[i] = s[i] * scale;
+  } else {
+    for (int64_t i = tid; i < n; i += nth) d[i] = s[i] * scale;
+  }
+}
+
 inline unsigned blocks_for(int64_t M) { return (unsigned)ceil_div64(M, 256); }
 // reductions: one block up to 4,096 rows (a fixed summation order: the training patch reproduces bit for bit), else atomics
 inline unsigned red_blocks(int64_t M) { int64_t b = ceil_div64(M, 4096); return (unsigned)(b < 1 ? 1 : (b > 296 ? 296 : b)); }
@@ -273,5 +299,20 @@ extern "C" int ironb_mask_rows(const float* const* src, float* const* dst, const
   for (int t = 0; t < n; ++t) { A.src[t] = src[t]; A.dst[t] = dst[t]; A.width[t] = width[t]; }
   mask_rows_kernel<<<blocks_for(M), 256, 0, as_stream(stream)>>>(A, w, M);
   IRONB_CHECK_LAUNCH("mask_rows_kernel");
+  return IRONB_OK;
+}
+
+/* flat[off[t] .. off[t] + off[n + t]) = scale * src[t][:] for t < n (src[t] == NULL: zeros).  src (n pointers) and off (n element
+ * offsets, then n element counts) live in DEVICE memory, so the launch can sit in a CUDA graph and the table can be refreshed by a copy.  The
+ * gradient bucket of the data-parallel step: one launch instead of cat + div + copy-back around the all-reduce. */
+extern "C" int ironb_pack_tensors(const float* const* src_dev, const int64_t* off_dev, int n, int64_t max_numel, float* flat,
+                                  float scale, void* stream) {
+  if (n <= 0) return IRONB_OK;
+  IRONB_REQUIRE(src_dev && off_dev && flat && n <= 65535, "pack_tensors: bad arguments");
+  int64_t bx = ceil_div64(max_numel, 256 * 8);
+  if (bx < 1) bx = 1;
+  if (bx > 128) bx = 128;
+  pack_tensors_kernel<<<dim3((unsigned)bx, (unsigned)n), 256, 0, as_stream(stream)>>>(src_dev, off_dev, flat, scale);
+  IRONB_CHECK_LAUNCH("pack_tensors_kernel");
   return IRONB_OK;
 }

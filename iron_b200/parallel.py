@@ -19,14 +19,17 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
-def crop_for_rank(rank: int, patch: int, width: int = 512, height: int = 512) -> Tuple[int, int]:
-    """Upper-left corner of rank's patch: rank 0 is the canonical centre crop, the others tile around it."""
+def crop_for_rank(rank: int, patch: int, width: int = 512, height: int = 512, stride: int = 0) -> Tuple[int, int]:
+    """Upper-left corner of rank's patch: rank 0 is the canonical centre crop, the others are distinct windows `stride` pixels
+    apart around it (stride 0 / default = patch: the windows tile; a smaller stride gives overlapping windows that stay near
+    the centre, i.e. comparable work per rank)."""
     offs = [(0, 0), (1, 0), (-1, 0), (0, 1), (0, -1), (1, 1), (-1, -1), (1, -1)]
     dx, dy = offs[rank % 8]
     ring = rank // 8 + 1
+    step = stride if stride > 0 else patch
     cx, cy = width // 2 - patch // 2, height // 2 - patch // 2
-    x = min(max(cx + dx * patch * ring, 0), width - patch)
-    y = min(max(cy + dy * patch * ring, 0), height - patch)
+    x = min(max(cx + dx * step * ring, 0), width - patch)
+    y = min(max(cy + dy * step * ring, 0), height - patch)
     return x, y
 
 
@@ -35,6 +38,16 @@ def collect_params(modules: Iterable[torch.nn.Module]) -> List[torch.nn.Paramete
     for m in modules:
         out += [p for p in m.parameters() if p.requires_grad]
     return out
+
+
+def allreduce_flat(flat: torch.Tensor, world: int) -> int:
+    """In-place SUM all-reduce of a flat gradient bucket whose producer already scaled it by 1 / world
+    (GraphedStage2Step(flat_grads=True, grad_scale=1 / world): `.grad` of every parameter is a view of it).  One collective,
+    no cat / div / copy-back passes; returns the number of elements exchanged."""
+    if world <= 1:
+        return 0
+    dist.all_reduce(flat)
+    return int(flat.numel())
 
 
 def allreduce_gradients(params: Sequence[torch.nn.Parameter], world: int, average: bool = True) -> int:

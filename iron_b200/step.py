@@ -97,7 +97,7 @@ class GraphedStage2Step:
 
     def __init__(self, sdf_network, color_network_dict, raytracer, render_fn, K, W2C, target_shape, n_eik, crop_ul=None,
                  full_size=(512, 512), eik_weight=0.1, warmup=3, time_tracer=False, overlap_eikonal=True, optimizer=None,
-                 image_loss="l2", ssim_weight=1.0, roughrange_weight=0.1):
+                 image_loss="l2", ssim_weight=1.0, roughrange_weight=0.1, flat_grads=False, grad_scale=1.0):
         import torch.cuda
         self.sdf, self.nets, self.raytracer, self.render_fn = sdf_network, color_network_dict, raytracer, render_fn
         self.eik_weight = eik_weight
@@ -127,12 +127,11 @@ class GraphedStage2Step:
         prio = int(__import__("os").environ.get("IRONB_GRAPH_MAIN_PRIORITY", "0"))
         side = torch.cuda.Stream(device=dev, priority=prio)   # the critical path (tracer -> shading -> backward)
         _env = __import__("os").environ
-        # KNOWN ISSUE (unresolved): with the eikonal branch on its own stream, replays at 65,536 rays /
-        # 32,768 eikonal points fault intermittently ("unspecified launch failure"; both tensor-core tracers; not with the
-        # material streams alone).  At 4,096 rays thousands of replays ran clean.  The overlap only pays when the tracer
-        # leaves SMs idle, i.e. for small patches, so it is limited to those (IRONB_GRAPH_EIK_STREAM=1 forces it on).
-        small = H * W <= 16384
-        want_eik = _env.get("IRONB_GRAPH_EIK_STREAM", "1" if small else "0") != "0"
+        # The eikonal query does not depend on the traced surface, so it runs on its own stream at every patch size
+        # (IRONB_GRAPH_EIK_STREAM=0 keeps it on the main stream).  Round 1 limited the fork to <= 16,384 rays because larger
+        # patches faulted; the cause was a phase-tracking race in the 3xTF32 GEMM's splitter groups that only memory contention
+        # from a second stream exposed (csrc/gemm_tc.cuh, profiles/r2j_multistream_fault_rootcause.md), fixed in round 2.
+        want_eik = _env.get("IRONB_GRAPH_EIK_STREAM", "1") != "0"
         self._eik_stream = torch.cuda.Stream(device=dev) if overlap_eikonal and want_eik else None
         self._mat_streams = ([torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
                              if overlap_eikonal and _env.get("IRONB_GRAPH_MAT_STREAMS", "1") != "0" else None)
@@ -170,14 +169,41 @@ class GraphedStage2Step:
         folded_nets = [sdf_network] + [m for m in color_network_dict.values() if hasattr(m, "folded")]
         for m in folded_nets:
             m._fold_captured = False                         # fold once per capture, at the first use
+        # flat_grads: the tail of the graph packs every gradient tensor (scaled by grad_scale, e.g. 1 / world_size) into ONE
+        # static fp32 buffer with one launch; `.grad` of every parameter is then a view of it, so the data-parallel exchange
+        # is a single in-place all-reduce of `flat_grad` (parallel.allreduce_flat) with no cat / div / copy-back passes.
+        self.flat_grad = None
+        if flat_grads:
+            assert optimizer is None, "flat_grads packs AFTER the backward; step the optimiser after the all-reduce"
+            offs = [0]
+            for p in self.params:
+                offs.append(offs[-1] + (p.numel() + 3) // 4 * 4)             # 16-byte aligned slots: float4 copies
+            self.flat_grad = torch.zeros(offs[-1], dtype=torch.float32, device=dev)
+            self._gnum = [p.numel() for p in self.params]
+            self._goffs = offs[:-1]
+            self._goff = torch.tensor(offs[:-1] + self._gnum, dtype=torch.int64, device=dev)     # offsets, then counts
+            self._gtab = torch.zeros(len(self.params), dtype=torch.int64, device=dev)   # source pointers, filled after capture
         try:
             with torch.cuda.graph(self.graph, stream=side):      # same stream as the warm-up (AccumulateGrad nodes)
                 self.loss, self.results = self._eager()
+                if flat_grads:
+                    lib = _lib.load()
+                    _lib.check(lib.ironb_pack_tensors(self._gtab.data_ptr(), self._goff.data_ptr(), len(self.params),
+                                                      max(self._gnum), self.flat_grad.data_ptr(), float(grad_scale),
+                                                      _lib.stream()), "pack_tensors")
         finally:
             raytracer.forward = orig_forward
             for m in folded_nets:
                 m._fold_captured = False
         self._grads = {id(p): p.grad for p in self.params}    # the graph's static gradient tensors
+        if flat_grads:
+            # the pack node reads the table at replay time: the static gradient tensors exist only now
+            self._raw_grads = [p.grad for p in self.params]       # keep them alive (graph pool memory)
+            tab = torch.tensor([0 if g is None else g.data_ptr() for g in self._raw_grads], dtype=torch.int64)
+            self._gtab.copy_(tab)
+            offs = self._goffs
+            self._grads = {id(p): self.flat_grad[o:o + p.numel()].view_as(p) for p, o in zip(self.params, offs)}
+            torch.cuda.synchronize(dev)
         self.kernels_per_replay = int(_lib.load().ironb_launch_count() - n0)   # this library's kernel nodes in the graph
 
     def close(self):
@@ -187,6 +213,7 @@ class GraphedStage2Step:
         self._tracer_events = None
         self.loss, self.results = None, None
         self._grads = {}
+        self._raw_grads, self.flat_grad = None, None
         if self.graph is not None:
             self.graph.reset()
             self.graph = None

@@ -50,6 +50,32 @@ def test_gradient_allreduce_world2():
         assert torch.allclose(a, (za + zb) / 2, atol=1e-6)
 
 
+def _flat_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from iron_b200.parallel import allreduce_flat
+    # what GraphedStage2Step(flat_grads=True, grad_scale=1 / world) leaves behind: one bucket, pre-scaled, .grad = views
+    local = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    flat = local / world
+    views = [flat[0:4].view(2, 2), flat[4:10]]
+    n = allreduce_flat(flat, world)
+    out[rank] = (n, flat.clone(), [v.clone() for v in views])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_world2():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_flat_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        (n0, f0, v0), (n1, f1, v1) = out[0], out[1]
+    assert n0 == n1 == 10 and torch.equal(f0, f1)
+    assert torch.allclose(f0, torch.arange(10, dtype=torch.float32) * 1.5)      # mean of x1 and x2
+    assert torch.equal(v0[0], f0[0:4].view(2, 2)) and torch.equal(v0[1], f0[4:10])   # the views saw the in-place exchange
+
+
 def test_shard_range_partitions_exactly():
     from iron_b200.parallel import crop_for_rank, shard_range
     for n in (0, 1, 7, 4096, 65537):
@@ -65,3 +91,5 @@ def test_shard_range_partitions_exactly():
     corners = {crop_for_rank(r, 64) for r in range(8)}
     assert len(corners) == 8 and crop_for_rank(0, 64) == (224, 224)
     assert all(0 <= x <= 448 and 0 <= y <= 448 for x, y in corners)
+    near = {crop_for_rank(r, 64, stride=8) for r in range(8)}                  # the bench's equal-work windows
+    assert len(near) == 8 and all(abs(x - 224) <= 8 and abs(y - 224) <= 8 for x, y in near)

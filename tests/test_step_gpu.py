@@ -341,6 +341,19 @@ def test_graphed_step_bench_configuration_matches_eager():
         assert worst <= 1e-5, worst
     print(f"bench configuration: loss {graph_runs[0][0]:.7f} / {float(l_ref):.7f}, 5 replays, gradients within 1e-5")
     gs.close()
+    # the data-parallel variant: the graph's tail packs every gradient (x grad_scale = 1 / world) into ONE flat bucket and
+    # .grad becomes a view of it, so the exchange is a single in-place all-reduce (parallel.allreduce_flat)
+    gf = ib.GraphedStage2Step(sdf, nets, ib.RayTracer(), rf, Kh, Wh, (S, S), eik.shape[0], crop_ul=ul, flat_grads=True,
+                              grad_scale=0.5)
+    for _ in range(2):
+        gf.step(target=target.pin_memory(), eik_points=eik.pin_memory())
+    torch.cuda.synchronize()
+    lo, hi = gf.flat_grad.data_ptr(), gf.flat_grad.data_ptr() + gf.flat_grad.numel() * 4
+    for k, p in params:
+        assert lo <= p.grad.data_ptr() < hi, k                               # a view of the bucket
+        assert rel_l2(p.grad.cpu().numpy() * 2.0, g_ref[k].cpu().numpy()) <= 1e-5, k
+    assert gf.flat_grad.numel() >= sum(p.numel() for _, p in params)
+    gf.close()
 
 
 def test_eager_steps_with_fused_adam_match_torch_adam(golden):
