@@ -115,12 +115,12 @@ class ClockSampler:
 
 def crop_corner(rank: int, patch: int):
     """Per-rank crop of the 512x512 view: rank 0 = the canonical centre crop; the other ranks take DISTINCT windows
-    shifted by patch/8 pixels around it (parallel.crop_for_rank).  Weak scaling needs the same work per GPU at every N, and the
+    shifted by patch/16 pixels around it (parallel.crop_for_rank).  Weak scaling needs the same work per GPU at every N, and the
     fixture object covers only ~145 pixels of the view: at the 64x64 training patch the shifted windows stay inside the
     silhouette like the centre crop (every ray hits), while windows TILED around the centre (IRONB_BENCH_CROP_STRIDE=<patch>)
     straddle the silhouette and cost about twice the centre crop -- that measures load imbalance, not scaling."""
     from iron_b200.parallel import crop_for_rank
-    stride = int(os.environ.get("IRONB_BENCH_CROP_STRIDE", max(patch // 8, 1)))
+    stride = int(os.environ.get("IRONB_BENCH_CROP_STRIDE", max(patch // 16, 1)))
     return crop_for_rank(rank, patch, stride=stride)
 
 
@@ -314,7 +314,7 @@ def workload_config(args, patch):
                         f"colocated-flash fixture view, trace+shade+loss+backward",
             "sdf_mlp": f"8x{args.hidden}, PE L=6, skip@4, softplus(100), weight-norm", "material_mlps": "3 x (4x256, ReLU)",
             "rays_per_gpu": patch * patch, "eikonal_points": patch * patch // 2,
-            "sharding": "every rank traces/shades its own crop of the view (rank 0: the centre crop, the others distinct windows patch/8 pixels apart around it = the same work per GPU; IRONB_BENCH_CROP_STRIDE=<patch> tiles them), own target/eikonal seeds; gradients packed into one flat buffer by the graph, one in-place all-reduce", "parallelism": f"dp{args.gpus} (rays sharded, weights replicated)",
+            "sharding": "every rank traces/shades its own crop of the view (rank 0: the centre crop, the others distinct windows patch/16 pixels apart around it = comparable work per GPU, rank_compute_ms_per_step shows what is left; IRONB_BENCH_CROP_STRIDE=<patch> tiles them), own target/eikonal seeds; gradients packed into one flat buffer by the graph, one in-place all-reduce", "parallelism": f"dp{args.gpus} (rays sharded, weights replicated)",
             "l2": "256 MiB flush between steps, outside the per-step CUDA-event pairs",
             "init": "seed-0 geometric init, light=32",
             "loss": ("PyramidL2 + 1.0 * SSIM(masked) + 0.1 * roughness range + 0.1 * eikonal: the reference's training loss, "
@@ -424,9 +424,15 @@ def run_ours(args):
         torch.cuda.synchronize()
         stage("first replay done")
 
+    mid_evs = []
+
     def step(cam_, target_, eik_, time_trace=False):
         if gs is not None:           # inputs are already in the graph's static buffers (cam_/target_/eik_ are those values)
             gs.graph.replay()
+            if time_trace and world > 1:      # end of this rank's own work: what follows is the exchange (+ waiting for peers)
+                mid = torch.cuda.Event(enable_timing=True)
+                mid.record()
+                mid_evs.append(mid)
             if world > 1:          # the graph's tail packed the gradients (x 1/world) into one buffer: one in-place all-reduce
                 allreduce_flat(gs.flat_grad, world)
             return gs.loss, gs.results
@@ -534,10 +540,16 @@ def run_ours(args):
     hits = int(res["convergent_mask"].sum().item())
     t = torch.tensor([my_ms], dtype=torch.float64, device=dev)
     rank_ms = [my_ms / args.steps]
+    rank_compute_ms = None
     if world > 1:
         allt = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allt, t)
         rank_ms = [float(x.item()) / args.steps for x in allt]
+        if len(mid_evs) == len(evs):      # replay only (own crop, before the all-reduce): shows the load imbalance between crops
+            tc_ = torch.tensor([sum(a.elapsed_time(m) for (a, _), m in zip(evs, mid_evs))], dtype=torch.float64, device=dev)
+            allc = [torch.zeros_like(tc_) for _ in range(world)]
+            dist.all_gather(allc, tc_)
+            rank_compute_ms = [round(float(x.item()) / args.steps, 4) for x in allc]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     rays_total = S * S * world * args.steps
@@ -626,7 +638,7 @@ def run_ours(args):
                        "root_rays": stats[4] / args.steps, "k_max": stats[5], "hits": hits, "rays": S * S,
                        "implementation": tracer_impl},
             "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps, "grad_params": n_params,
-            "rank_ms_per_step": [round(x, 4) for x in rank_ms], "rank_crop_ul": [list(crop_corner(r, S)) for r in range(world)],
+            "rank_ms_per_step": [round(x, 4) for x in rank_ms], "rank_compute_ms_per_step": rank_compute_ms, "rank_crop_ul": [list(crop_corner(r, S)) for r in range(world)],
             "loss": loss_host,
             "step_ms": [round(x, 3) for x in step_ms], "tracer_ms": [round(x, 3) for x in tr_ms],
             "tracer_ms_source": ("one sample per replay of the e2e loop (external CUDA-event pair inside the graph)"
