@@ -113,6 +113,9 @@ int ironb_gemm_tn(const float* A, int lda, const float* B, int ldb, int M, int N
 int ironb_sdf_layout(int d_in, int d_out, int d_hidden, int n_layers, int skip_layer, int multires,
                      float scale, float beta, ironb_mlp_layout* out);
 int ironb_matnet_layout(int in_dim0, int d_out, int d_hidden, int n_layers, ironb_mlp_layout* out);
+/* The same with RenderingNetwork(skip_in=[s]) (models/fields.py:179-187, 226-227: layer s reads cat(h, input) / sqrt 2; the
+ * stage-1 colour network uses n_layers = 8, skip_in = [4]); skip_layer < 0 = none. */
+int ironb_matnet_layout_skip(int in_dim0, int d_out, int d_hidden, int n_layers, int skip_layer, ironb_mlp_layout* out);
 
 /* ---------------------------------------------------------------- weight norm
  * W = v * (g / ||v||_row)  (old-style nn.utils.weight_norm, dim=0).  v/g/b: arrays of n_lin device
@@ -280,6 +283,26 @@ int ironb_roughrange_fwd(const float* r, const float* w, int64_t M, float value,
 int ironb_roughrange_bwd(const float* r, const float* w, const float* acc, const float* up, int64_t M, float value, float weight,
                          float* dr, void* stream);
 int ironb_mask_rows(const float* const* src, float* const* dst, const int* width, int n, const float* w, int64_t M, void* stream);
+/* ---------------------------------------------------------------- stage-1 NeuS volume renderer (csrc/neus.cu)
+ * The per-ray part of NeuSRenderer.render_core (models/renderer.py:248-351): SDF values / SDF gradients / colours at the n
+ * section midpoints of N rays (row-major [N][n], [N][n][3]) -> composited colour [N][3], weights [N][n_tot], cdf [N][n],
+ * inside_sphere [N][n] and the eikonal term gradient_error [1]; acc [2] keeps the two eikonal sums for the backward.
+ * bg_alpha [N][n_tot] / bg_color [N][n_tot][3]: the background NeRF's alpha and colour (render_core_outside, :156-190), NULL
+ * without a background model (then n_tot == n); bg_rgb [3]: fixed background colour or NULL; inv_s [1] on the device. */
+int ironb_neus_composite_fwd(const float* ray_o, const float* ray_d, const float* mid_z, const float* dists, const float* sdf,
+                             const float* grad, const float* color, const float* inv_s, const float* bg_alpha,
+                             const float* bg_color, const float* bg_rgb, int64_t N, int n, int n_tot, float cos_anneal_ratio,
+                             float* out_color, float* weights, float* cdf, float* inside, float* acc, float* gradient_error,
+                             void* stream);
+/* Backward of the above (replaces autograd through :277-322): upstream d_color [N][3], d_weights [N][n_tot] or NULL,
+ * d_gradient_error [1] or NULL -> d_sdf [N][n], d_grad [N][n][3], d_colors [N][n][3], d_inv_s [1], and with a background
+ * d_bg_alpha [N][n_tot], d_bg_color [N][n_tot][3].  The forward quantities are recomputed from the same inputs. */
+int ironb_neus_composite_bwd(const float* ray_o, const float* ray_d, const float* mid_z, const float* dists, const float* sdf,
+                             const float* grad, const float* color, const float* inv_s, const float* bg_alpha,
+                             const float* bg_color, const float* bg_rgb, int64_t N, int n, int n_tot, float cos_anneal_ratio,
+                             const float* weights, const float* acc, const float* d_color, const float* d_weights,
+                             const float* d_gradient_error, float* d_sdf, float* d_grad, float* d_colors, float* d_inv_s,
+                             float* d_bg_alpha, float* d_bg_color, void* stream);
 /* Gradient bucket of the data-parallel step (the reference is single-GPU, no interface replaced):
  * flat[off[t] .. off[t] + off[n + t]) = scale * src[t][:] for t < n, zeros where src[t] is NULL.  src_dev (n pointers) and
  * off_dev (n element offsets followed by n element counts) are DEVICE arrays, so the launch can be a CUDA-graph node.  max_numel sizes the grid. */

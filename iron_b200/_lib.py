@@ -56,6 +56,7 @@ _PROTOS = {
     "ironb_gemm_tn": (_INT, [_P, _INT, _P, _INT, _INT, _INT, _INT, _P, _INT, _INT, _P, _P]),
     "ironb_sdf_layout": (_INT, [_INT, _INT, _INT, _INT, _INT, _INT, _F, _F, _LAY]),
     "ironb_matnet_layout": (_INT, [_INT, _INT, _INT, _INT, _LAY]),
+    "ironb_matnet_layout_skip": (_INT, [_INT, _INT, _INT, _INT, _INT, _LAY]),
     "ironb_mlp_fold": (_INT, [_LAY, _PP, _PP, _PP, _P, _P]),
     "ironb_mlp_fold_bwd": (_INT, [_LAY, _PP, _PP, _P, _PP, _PP, _PP, _P]),
     "ironb_sdf_getall_workspace_bytes": (_I64, [_LAY, _I64, _INT, _INT]),
@@ -89,6 +90,8 @@ _PROTOS = {
     "ironb_roughrange_fwd": (_INT, [_P, _P, _I64, _F, _F, _P, _P, _P]),
     "ironb_roughrange_bwd": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _P, _P]),
     "ironb_mask_rows": (_INT, [_PP, _PP, C.POINTER(C.c_int), _INT, _P, _I64, _P]),
+    "ironb_neus_composite_fwd": (_INT, [_P] * 11 + [_I64, _INT, _INT, _F] + [_P] * 6 + [_P]),
+    "ironb_neus_composite_bwd": (_INT, [_P] * 11 + [_I64, _INT, _INT, _F] + [_P] * 11 + [_P]),
     "ironb_pack_tensors": (_INT, [_P, _P, _INT, _I64, _P, _F, _P]),
     "ironb_patch_loss_workspace_bytes": (_I64, [_INT, _INT, _INT]),
     "ironb_pyramid_l2": (_INT, [_P, _PI64, _P, _PI64, _INT, _INT, _INT, _P, _P, _PI64, _P, _I64, _P]),

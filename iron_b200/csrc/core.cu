@@ -102,24 +102,32 @@ extern "C" int ironb_sdf_layout(int d_in, int d_out, int d_hidden, int n_layers,
   return IRONB_OK;
 }
 
-// RenderingNetwork.__init__ (models/fields.py:163-195): dims = [in_dim0] + [H]*n_layers + [d_out], no skip.
-extern "C" int ironb_matnet_layout(int in_dim0, int d_out, int d_hidden, int n_layers, ironb_mlp_layout* out) {
+// RenderingNetwork.__init__ (models/fields.py:163-195): dims = [in_dim0] + [H]*n_layers + [d_out]; a skip layer s (at most
+// one, 1 <= s <= n_layers) takes cat(h, input) / sqrt(2), i.e. its fan-in is H + in_dim0 while the layer before it still emits
+// H features (:179-187) -- unlike the SDF net, whose layer before the skip shrinks.
+extern "C" int ironb_matnet_layout_skip(int in_dim0, int d_out, int d_hidden, int n_layers, int skip_layer,
+                                        ironb_mlp_layout* out) {
   IRONB_REQUIRE(out != nullptr, "matnet_layout: null out");
   IRONB_REQUIRE(n_layers + 1 <= IRONB_MAX_LIN && n_layers >= 0, "matnet_layout: n_layers out of range");
   IRONB_REQUIRE(in_dim0 > 0 && d_out > 0 && d_hidden > 0, "matnet_layout: bad dims");
+  IRONB_REQUIRE(skip_layer < 0 || (skip_layer >= 1 && skip_layer <= n_layers && d_hidden % 8 == 0),
+                "matnet_layout: skip layer must be in [1, n_layers] and d_hidden a multiple of 8");
   memset(out, 0, sizeof(*out));
   out->n_lin = n_layers + 1;
   out->kind = 1;
   out->d_in = 3;
-  out->skip_layer = -1;
+  out->skip_layer = skip_layer < 0 ? -1 : skip_layer;
   out->d_hidden = d_hidden;
   out->d_out = d_out;
   out->scale = 1.f;
   out->beta = 0.f;
   for (int l = 0; l < out->n_lin; ++l) {
-    out->in_dim[l] = (l == 0) ? in_dim0 : d_hidden;
+    out->in_dim[l] = (l == 0) ? in_dim0 : d_hidden + (l == out->skip_layer ? in_dim0 : 0);
     out->out_dim[l] = (l == out->n_lin - 1) ? d_out : d_hidden;
   }
   finish_layout(out);
   return IRONB_OK;
+}
+extern "C" int ironb_matnet_layout(int in_dim0, int d_out, int d_hidden, int n_layers, ironb_mlp_layout* out) {
+  return ironb_matnet_layout_skip(in_dim0, d_out, d_hidden, n_layers, -1, out);
 }

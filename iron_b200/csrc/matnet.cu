@@ -1,6 +1,8 @@
 // RenderingNetwork (the three material MLPs of the 'ggx' configuration) forward and backward.
 // models/fields.py:203-239: input = cat(PE(points), [PE(view_dirs)], [normals], features) -> (Linear, ReLU) x n_layers
-// -> Linear -> output_scale * (x + output_bias) -> [squeeze_out_scale * sigmoid].  skip_in = () only.
+// -> Linear -> output_scale * (x + output_bias) -> [squeeze_out_scale * sigmoid].  At most one skip layer s (:226-227: layer s
+// reads cat(h, input) / sqrt 2; the stage-1 colour network has n_layers = 8, skip_in = [4]): the layer before it writes its H
+// outputs, scaled, into the first H columns of a row of width in_pad[s]; skip_fill_kernel appends the scaled input.
 // One fp32 tile GEMM per layer (gemm.cuh); ReLU / output transform fused into the epilogues, the input
 // concatenation + positional encodings and their backward are two small elementwise kernels.
 #include "gemm_h16.cuh"
@@ -103,12 +105,13 @@ struct EpiRelu {
   float* Unext;
   int ld, n_true;
   __half *Uh, *Ul;      // fp16x2-split copy of Unext or null
+  float scale;          // 1, or 1/sqrt(2) for the layer that feeds the skip layer
   __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[4]) const {
     float u[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int n = n0 + j;
-      u[j] = n < n_true ? fmaxf(acc[j] + __ldg(bias + n), 0.f) : 0.f;
+      u[j] = n < n_true ? fmaxf(acc[j] + __ldg(bias + n), 0.f) * scale : 0.f;
     }
     *reinterpret_cast<float4*>(Unext + (int64_t)m * ld + n0) = make_float4(u[0], u[1], u[2], u[3]);
     if (Uh) h16::store_split4(Uh, Ul, (int64_t)m * ld + n0, u);
@@ -132,6 +135,49 @@ struct EpiMatOut {
   }
 };
 
+// Columns [H, ld) of the skip layer's input row: the assembled network input / sqrt 2, zero padding after it.
+__global__ void __launch_bounds__(256) skip_fill_kernel(const float* __restrict__ U0, int ld0, int in0, int64_t M, int H, int ld,
+                                                        float* __restrict__ Us, __half* __restrict__ Ush,
+                                                        __half* __restrict__ Usl) {
+  const int w = ld - H;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M * w) return;
+  const int64_t m = i / w;
+  const int j = (int)(i - m * w);
+  const float v = j < in0 ? U0[m * ld0 + j] * 0.70710678118654752f : 0.f;
+  const int64_t o = m * ld + H + j;
+  Us[o] = v;
+  if (Ush != nullptr) {
+    const __half h = __float2half_rn(v);
+    Ush[o] = h;
+    Usl[o] = __float2half_rn((v - __half2float(h)) * 2048.f);
+  }
+}
+
+// The dgrad out of the skip layer: columns [0, H) are the gradient of the previous layer's (scaled) ReLU output, columns
+// [H, ld) the gradient that reaches the network input through the skip connection (kept in S for the input dgrad).
+struct EpiReluBwdSkip {
+  const float* Uthis;   // U_s [M][ld]: relu(h) / sqrt 2 in the first H columns
+  float* Dprev;         // D_{s-1} [M][ld]
+  float* S;             // [M][ld0] or null
+  int ld, H, ld0;
+  __device__ __forceinline__ void operator()(int m, int k0, const float (&acc)[4]) const {
+    const int64_t o = (int64_t)m * ld + k0;
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    if (k0 < H) {
+      const float4 u4 = *reinterpret_cast<const float4*>(Uthis + o);
+      const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d[j] = uu[j] > 0.f ? acc[j] * 0.70710678118654752f : 0.f;
+    } else if (S != nullptr && k0 - H < ld0) {
+      *reinterpret_cast<float4*>(S + (int64_t)m * ld0 + (k0 - H)) =
+          make_float4(acc[0] * 0.70710678118654752f, acc[1] * 0.70710678118654752f, acc[2] * 0.70710678118654752f,
+                      acc[3] * 0.70710678118654752f);
+    }
+    *reinterpret_cast<float4*>(Dprev + o) = make_float4(d[0], d[1], d[2], d[3]);
+  }
+};
+
 // delta_{l-1} = (u_l > 0) ? ubar : 0     (ReLU backward on the stored post-activation)
 struct EpiReluBwd {
   const float* Uthis;   // U_l [M][ld]  (post-ReLU output of layer l-1)
@@ -151,8 +197,15 @@ struct EpiReluBwd {
 struct EpiPlain {
   float* C;
   int ld;
+  const float* add;     // [M][ld] or null: the skip connection's share of the input gradient
   __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[4]) const {
-    *reinterpret_cast<float4*>(C + (int64_t)m * ld + n0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    const int64_t o = (int64_t)m * ld + n0;
+    float4 v = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if (add != nullptr) {
+      const float4 a = *reinterpret_cast<const float4*>(add + o);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    *reinterpret_cast<float4*>(C + o) = v;
   }
 };
 
@@ -179,6 +232,7 @@ struct MatWs {
   float* U[IRONB_MAX_LIN];
   float* D[IRONB_MAX_LIN + 1];   // delta_l per layer (D[l] = gradient w.r.t. the output of layer l; D[n_lin] unused) + the input gradient
   float* wg;
+  float* S;                      // skip connection's share of the input gradient [M][in_pad0] (skip nets only)
   __half *Uh[IRONB_MAX_LIN], *Ul[IRONB_MAX_LIN];   // fp16x2-split copies of U_l (gemm mode 2)
   int64_t floats;
 };
@@ -193,6 +247,7 @@ MatWs carve_mat(const ironb_mlp_layout* L, int64_t M, float* base) {
   for (int l = 0; l < L->n_lin; ++l) w.U[l] = take(L->in_pad[l]);
   for (int l = 0; l < L->n_lin; ++l) w.D[l] = take(L->out_pad[l]);
   w.D[L->n_lin] = take(L->in_pad[0]);                 // d loss / d (assembled input)
+  if (L->skip_layer >= 1) w.S = take(L->in_pad[0]);
   w.wg = base ? base + off : nullptr;
   off += (wgrad_scratch_floats(M, mp) + 63) / 64 * 64;
   if (gemm_mode() == 2) {
@@ -245,14 +300,24 @@ extern "C" int ironb_matnet_fwd(const ironb_mlp_layout* lay, const ironb_matnet_
   IRONB_CHECK_LAUNCH("assemble_kernel");
   auto whi = [&](int l) { return reinterpret_cast<const __half*>(packed + lay->off_h16[l]); };
   auto wlo = [&](int l) { return whi(l) + (int64_t)lay->out_pad[l] * lay->in_pad[l]; };
+  const int skip = lay->skip_layer;
   for (int l = 0; l < last; ++l) {
+    const bool feeds_skip = (l + 1 == skip);          // writes H scaled columns of the wider skip-layer row
+    const int N = feeds_skip ? round_up(lay->out_dim[l], 8) : lay->out_pad[l];
     EpiRelu ep{packed + lay->off_b[l], w.U[l + 1], lay->out_pad[l], lay->out_dim[l], h16m ? w.Uh[l + 1] : nullptr,
-               h16m ? w.Ul[l + 1] : nullptr};
-    int rc = h16m ? h16::launch_gemm_h16(w.Uh[l], w.Ul[l], lay->in_pad[l], whi(l), wlo(l), lay->in_pad[l], (int)M, lay->out_pad[l],
+               h16m ? w.Ul[l + 1] : nullptr, feeds_skip ? 0.70710678118654752f : 1.f};
+    int rc = h16m ? h16::launch_gemm_h16(w.Uh[l], w.Ul[l], lay->in_pad[l], whi(l), wlo(l), lay->in_pad[l], (int)M, N,
                                          lay->in_pad[l], ep, st, "matnet fwd gemm (h16)")
-                  : launch_gemm_nt_auto(w.U[l], lay->in_pad[l], packed + lay->off_w[l], lay->in_pad[l], (int)M, lay->out_pad[l],
+                  : launch_gemm_nt_auto(w.U[l], lay->in_pad[l], packed + lay->off_w[l], lay->in_pad[l], (int)M, N,
                                         lay->in_pad[l], ep, st, "matnet fwd gemm");
     if (rc) return rc;
+    if (feeds_skip) {
+      const int H = round_up(lay->out_dim[l], 8), ld = lay->in_pad[skip];
+      skip_fill_kernel<<<(unsigned)ceil_div64(M * (ld - H), 256), 256, 0, st>>>(w.U[0], lay->in_pad[0], lay->in_dim[0], M, H, ld,
+                                                                               w.U[skip], h16m ? w.Uh[skip] : nullptr,
+                                                                               h16m ? w.Ul[skip] : nullptr);
+      IRONB_CHECK_LAUNCH("skip_fill_kernel");
+    }
   }
   EpiMatOut ep{packed + lay->off_b[last], out, lay->d_out, cfg->squeeze, cfg->out_bias, cfg->out_scale,
                cfg->squeeze_scale};
@@ -285,23 +350,32 @@ extern "C" int ironb_matnet_bwd(const ironb_mlp_layout* lay, const ironb_matnet_
                                                                   w.D[last]);
   IRONB_CHECK_LAUNCH("mat_dlast_kernel");
   const bool need_in = d_points || d_normals || d_view || d_feats;
+  const int skip = lay->skip_layer;
   for (int l = last; l >= 0; --l) {
     const float* D = w.D[l];
+    // true output width (rounded to 8): the layer feeding a skip layer has out_pad = the skip row width, its gradient columns
+    // beyond H are zero
+    const int No = round_up(lay->out_dim[l], 8);
     if ((frc = fork_to(st, wst))) return frc;
-    int rc = launch_wgrad_auto(D, lay->out_pad[l], w.U[l], lay->in_pad[l], (int)M, lay->out_pad[l], lay->in_pad[l],
+    int rc = launch_wgrad_auto(D, lay->out_pad[l], w.U[l], lay->in_pad[l], (int)M, No, lay->in_pad[l],
                                dpacked + lay->off_w[l], lay->in_pad[l], w.wg, wst, "matnet wgrad (+ bias grad)",
                                dpacked + lay->off_b[l], lay->out_dim[l], 1.f);
     if (rc) return rc;
-    if (l > 0) {
+    if (l > 0 && l == skip) {
+      EpiReluBwdSkip ep{w.U[l], w.D[l - 1], need_in ? w.S : nullptr, lay->in_pad[l], round_up(lay->out_dim[l - 1], 8), lay->in_pad[0]};
+      rc = launch_gemm_nt_auto(D, lay->out_pad[l], packed + lay->off_wt[l], lay->out_pad[l], (int)M, lay->in_pad[l], No, ep, st,
+                               "matnet dgrad (skip layer)");
+      if (rc) return rc;
+    } else if (l > 0) {
       EpiReluBwd ep{w.U[l], w.D[l - 1], lay->in_pad[l], lay->out_dim[l - 1]};
       rc = launch_gemm_nt_auto(D, lay->out_pad[l], packed + lay->off_wt[l], lay->out_pad[l], (int)M, lay->in_pad[l],
-                          lay->out_pad[l], ep, st, "matnet dgrad");
+                          No, ep, st, "matnet dgrad");
       if (rc) return rc;
     } else if (need_in) {
       float* Dn = w.D[lay->n_lin];
-      EpiPlain ep{Dn, lay->in_pad[0]};
+      EpiPlain ep{Dn, lay->in_pad[0], skip >= 1 ? w.S : nullptr};
       rc = launch_gemm_nt_auto(D, lay->out_pad[0], packed + lay->off_wt[0], lay->out_pad[0], (int)M, lay->in_pad[0],
-                          lay->out_pad[0], ep, st, "matnet input dgrad");
+                          No, ep, st, "matnet input dgrad");
       if (rc) return rc;
       int64_t thr = M * 32;
       disassemble_kernel<<<(unsigned)ceil_div64(thr, 256), 256, 0, st>>>(*cfg, pl, w.U[0], Dn, M, lay->in_pad[0],

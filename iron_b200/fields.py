@@ -336,14 +336,16 @@ class _MatEval(torch.autograd.Function):
 
 
 class RenderingNetwork(_FoldedMLP):
-    """models/fields.py:141-239 (skip_in=() only, which is what every 'ggx' network uses)."""
+    """models/fields.py:141-239.  skip_in: () (every 'ggx' / 'comp2' network) or ONE layer (the stage-1 colour network:
+    n_layers = 8, skip_in = [4])."""
 
     def __init__(self, d_feature, mode, d_in, d_out, d_hidden, n_layers, weight_norm=True, multires=0,
                  multires_view=0, squeeze_out=True, squeeze_out_scale=1.0, output_bias=0.0, output_scale=1.0,
                  skip_in=()):
         super().__init__()
-        if len(tuple(skip_in)) != 0:
-            raise NotImplementedError("iron_b200.RenderingNetwork: skip_in must be empty")
+        skip_in = tuple(skip_in)
+        if len(skip_in) > 1 or any(not (1 <= int(l) <= n_layers) for l in skip_in):
+            raise NotImplementedError("iron_b200.RenderingNetwork: at most one skip layer, in [1, n_layers]")
         if mode not in _MODES:
             raise ValueError(f"unknown mode {mode!r}")
         self.mode = mode
@@ -360,9 +362,14 @@ class RenderingNetwork(_FoldedMLP):
             self.embedview_fn = embedview_fn
             dims[0] += input_ch - 3
         self.num_layers = len(dims)
-        self.skip_in = ()
-        for l in range(0, self.num_layers - 1):
-            lin = nn.Linear(dims[l], dims[l + 1])
+        self.skip_in = skip_in
+        in0 = dims[0]
+        for l in range(0, self.num_layers - 1):                 # :179-181: the skip layer reads cat(h, input)
+            if l in self.skip_in:
+                dims[l] += in0
+        for l in range(0, self.num_layers - 1):                 # :183-187 (same nn.Linear shapes = same RNG consumption)
+            out_dim = dims[l + 1] - in0 if (l + 1) in self.skip_in else dims[l + 1]
+            lin = nn.Linear(dims[l], out_dim)
             setattr(self, "lin" + str(l), _WNLinear(lin.weight.data, lin.bias.data, weight_norm))
         self.output_bias = output_bias
         self.output_scale = output_scale
@@ -373,11 +380,12 @@ class RenderingNetwork(_FoldedMLP):
                                   float(squeeze_out_scale))
         lib = _lib.load()
         kernel_in = lib.ironb_matnet_in_dim(C.byref(self.cfg))
-        if kernel_in != dims[0]:
+        if kernel_in != in0:
             raise ValueError(f"RenderingNetwork: d_in={d_in} is inconsistent with mode {mode!r} "
-                             f"(kernel input width {kernel_in}, ctor width {dims[0]})")
+                             f"(kernel input width {kernel_in}, ctor width {in0})")
         self.layout = _lib.MlpLayout()
-        _lib.check(lib.ironb_matnet_layout(dims[0], d_out, d_hidden, n_layers, C.byref(self.layout)), "matnet_layout")
+        _lib.check(lib.ironb_matnet_layout_skip(in0, d_out, d_hidden, n_layers, int(skip_in[0]) if skip_in else -1,
+                                                C.byref(self.layout)), "matnet_layout")
 
     def forward(self, points, normals, view_dirs, feature_vectors):
         self._check_device(points)

@@ -154,11 +154,16 @@ def material_in_dim(cfg: dict, d_feature: int = 256) -> int:
 
 
 def make_material_params(cfg: dict, d_feature: int = 256, d_hidden: int = 256, n_layers: int = 4) -> Params:
-    """Default nn.Linear init + weight_norm, models/fields.py:163-195 (no skip)."""
+    """Default nn.Linear init + weight_norm, models/fields.py:163-195 (cfg["skip_in"]: layers that read cat(h, input))."""
     dims = [material_in_dim(cfg, d_feature)] + [d_hidden] * n_layers + [cfg["d_out"]]
+    skip_in = tuple(cfg.get("skip_in", ()))
+    in0 = dims[0]
+    for l in range(len(dims) - 1):          # :179-181
+        if l in skip_in:
+            dims[l] += in0
     p: Params = {}
-    for l in range(len(dims) - 1):
-        w, b = _fresh_linear(dims[l], dims[l + 1])
+    for l in range(len(dims) - 1):          # :183-187
+        w, b = _fresh_linear(dims[l], dims[l + 1] - in0 if (l + 1) in skip_in else dims[l + 1])
         p[f"lin{l}.bias"] = b.clone()
         p[f"lin{l}.weight_g"] = w.norm(dim=1, keepdim=True).clone()
         p[f"lin{l}.weight_v"] = w.clone()
@@ -352,7 +357,7 @@ def sdf_get_all_backward_closed_form(p: Params, saved, ybar: Tensor, fbar: Tenso
 
 def material_forward(p: Params, cfg: dict, points: Tensor, normals: Tensor,
                      view_dirs: Optional[Tensor], feats: Tensor) -> Tensor:
-    """models/fields.py:203-239 (modes 'idr' and 'no_view_dir'; no skip)."""
+    """models/fields.py:203-239 (modes 'idr' and 'no_view_dir'; cfg["skip_in"]: x = cat(x, input) / sqrt 2 before layer l, :226-227)."""
     pts = posenc(points, cfg["multires"]) if cfg["multires"] > 0 else points
     if cfg["mode"] == "idr":
         vd = posenc(view_dirs, cfg["multires_view"]) if cfg["multires_view"] > 0 else view_dirs
@@ -362,12 +367,15 @@ def material_forward(p: Params, cfg: dict, points: Tensor, normals: Tensor,
     else:
         raise ValueError(cfg["mode"])
     L = n_lin(p)
+    h0 = h
     for l in range(L):
+        if l in tuple(cfg.get("skip_in", ())):
+            h = torch.cat([h, h0], dim=-1) / np.sqrt(2)
         h = wn_linear(p, l, h)
         if l < L - 1:
             h = torch.relu(h)
-    h = cfg["output_scale"] * (h + cfg["output_bias"])
-    if cfg["squeeze_out"]:
+    h = cfg.get("output_scale", 1.0) * (h + cfg.get("output_bias", 0.0))
+    if cfg.get("squeeze_out", True):
         h = torch.sigmoid(h)  # squeeze_out_scale = 1.0
     return h
 
@@ -1103,3 +1111,186 @@ def adam_step(p, g, m, v, t, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=
     denom = np.sqrt(v) / np.float32(bc2 ** 0.5) + np.float32(eps)
     p = p - step_size * (m / denom)
     return p.astype(np.float32), m.astype(np.float32), v.astype(np.float32)
+
+
+# --------------------------------------------------------------------------
+# stage-1 NeuS volume renderer                 models/renderer.py:43-73, 128-453
+# (second half).  Stateless restatement: parameter dicts in, tensors out.
+# --------------------------------------------------------------------------
+NEUS_COLOR_CFG = dict(d_in=9, d_out=3, multires=10, multires_view=4, mode="idr", squeeze_out=True, output_bias=0.0,
+                      output_scale=1.0, skip_in=(4,))          # confs/*_iron.conf rendering_network
+
+
+def sample_pdf(bins: Tensor, weights: Tensor, n_samples: int) -> Tensor:
+    """models/renderer.py:43-73 with det=True (the only mode up_sample uses, :231)."""
+    weights = weights + 1e-5
+    pdf = weights / torch.sum(weights, -1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+    u = torch.linspace(0.0 + 0.5 / n_samples, 1.0 - 0.5 / n_samples, steps=n_samples, dtype=bins.dtype)
+    u = u.expand(list(cdf.shape[:-1]) + [n_samples]).contiguous()
+    inds = torch.searchsorted(cdf, u, right=True)
+    below = torch.clamp(inds - 1, min=0)
+    above = torch.clamp(inds, max=cdf.shape[-1] - 1)
+    cdf_b, cdf_a = torch.gather(cdf, -1, below), torch.gather(cdf, -1, above)
+    bins_b, bins_a = torch.gather(bins, -1, below), torch.gather(bins, -1, above)
+    denom = cdf_a - cdf_b
+    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    return bins_b + (u - cdf_b) / denom * (bins_a - bins_b)
+
+
+def nerf_forward(p: Params, pts: Tensor, views: Tensor, multires: int = 10, multires_view: int = 4, skips=(4,)):
+    """models/fields.py:241-322 (use_viewdirs=True): the background model; keys = the module's state dict."""
+    x = posenc(pts, multires) if multires > 0 else pts
+    v = posenc(views, multires_view) if multires_view > 0 else views
+    h = x
+    i = 0
+    while f"pts_linears.{i}.weight" in p:
+        h = torch.relu(h @ p[f"pts_linears.{i}.weight"].t() + p[f"pts_linears.{i}.bias"])
+        if i in skips:
+            h = torch.cat([x, h], -1)
+        i += 1
+    alpha = h @ p["alpha_linear.weight"].t() + p["alpha_linear.bias"]
+    feat = h @ p["feature_linear.weight"].t() + p["feature_linear.bias"]
+    h = torch.relu(torch.cat([feat, v], -1) @ p["views_linears.0.weight"].t() + p["views_linears.0.bias"])
+    return alpha, h @ p["rgb_linear.weight"].t() + p["rgb_linear.bias"]
+
+
+def _cumprod_weights(alpha: Tensor) -> Tensor:
+    ones = torch.ones([alpha.shape[0], 1], dtype=alpha.dtype)
+    return alpha * torch.cumprod(torch.cat([ones, 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+
+
+def neus_up_sample(rays_o, rays_d, z_vals, sdf, n_importance: int, inv_s: float) -> Tensor:
+    """:192-232."""
+    B, n = z_vals.shape
+    pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]
+    radius = torch.linalg.norm(pts, ord=2, dim=-1)
+    inside = (radius[:, :-1] < 1.0) | (radius[:, 1:] < 1.0)
+    sdf = sdf.reshape(B, n)
+    prev_sdf, next_sdf = sdf[:, :-1], sdf[:, 1:]
+    prev_z, next_z = z_vals[:, :-1], z_vals[:, 1:]
+    mid_sdf = (prev_sdf + next_sdf) * 0.5
+    cos_val = (next_sdf - prev_sdf) / (next_z - prev_z + 1e-5)
+    prev_cos = torch.cat([torch.zeros([B, 1], dtype=z_vals.dtype), cos_val[:, :-1]], dim=-1)
+    cos_val = torch.min(torch.stack([prev_cos, cos_val], dim=-1), dim=-1)[0]
+    cos_val = cos_val.clip(-1e3, 0.0) * inside
+    dist = next_z - prev_z
+    prev_cdf = torch.sigmoid((mid_sdf - cos_val * dist * 0.5) * inv_s)
+    next_cdf = torch.sigmoid((mid_sdf + cos_val * dist * 0.5) * inv_s)
+    alpha = (prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)
+    return sample_pdf(z_vals, _cumprod_weights(alpha), n_importance).detach()
+
+
+def neus_cat_z_vals(sdf_fn, rays_o, rays_d, z_vals, new_z_vals, sdf, last: bool):
+    """:234-246."""
+    B, n = z_vals.shape
+    pts = rays_o[:, None, :] + rays_d[:, None, :] * new_z_vals[..., :, None]
+    z_vals = torch.cat([z_vals, new_z_vals], dim=-1)
+    z_vals, index = torch.sort(z_vals, dim=-1)
+    if not last:
+        new_sdf = sdf_fn(pts.reshape(-1, 3)).reshape(B, new_z_vals.shape[1])
+        sdf = torch.gather(torch.cat([sdf, new_sdf], dim=-1), -1, index)
+    return z_vals, sdf
+
+
+def neus_render_core_outside(nerf_p: Params, rays_o, rays_d, z_vals, sample_dist: float):
+    """:140-190 (n_outside > 0: 4-D inverted-sphere points)."""
+    B, n = z_vals.shape
+    dists = z_vals[..., 1:] - z_vals[..., :-1]
+    dists = torch.cat([dists, torch.full_like(dists[..., :1], sample_dist)], -1)
+    mid = z_vals + dists * 0.5
+    pts = rays_o[:, None, :] + rays_d[:, None, :] * mid[..., :, None]
+    dc = torch.linalg.norm(pts, ord=2, dim=-1, keepdim=True).clip(1.0, 1e10)
+    pts = torch.cat([pts / dc, 1.0 / dc], dim=-1).reshape(-1, 4)
+    dirs = rays_d[:, None, :].expand(B, n, 3).reshape(-1, 3)
+    density, color = nerf_forward(nerf_p, pts, dirs)
+    alpha = 1.0 - torch.exp(-torch.nn.functional.softplus(density.reshape(B, n)) * dists)
+    return alpha, color.reshape(B, n, 3)
+
+
+def neus_render_core(sdf_p: Params, color_p: Params, variance: Tensor, rays_o, rays_d, z_vals, sample_dist: float,
+                     background_alpha=None, background_sampled_color=None, background_rgb=None, cos_anneal_ratio: float = 0.0,
+                     color_cfg: dict = NEUS_COLOR_CFG, sdf_kw: Optional[dict] = None):
+    """:248-351."""
+    sdf_kw = sdf_kw or {}
+    B, n = z_vals.shape
+    dists = z_vals[..., 1:] - z_vals[..., :-1]
+    dists = torch.cat([dists, torch.full_like(dists[..., :1], sample_dist)], -1)
+    mid = z_vals + dists * 0.5
+    pts = (rays_o[:, None, :] + rays_d[:, None, :] * mid[..., :, None]).reshape(-1, 3)
+    dirs = rays_d[:, None, :].expand(B, n, 3).reshape(-1, 3)
+    out = sdf_forward(sdf_p, pts, **sdf_kw)
+    sdf, feat = out[:, :1], out[:, 1:]
+    gradients = sdf_gradient(sdf_p, pts, **sdf_kw)
+    sampled_color = material_forward(color_p, color_cfg, pts, gradients, dirs, feat).reshape(B, n, 3)
+    inv_s = torch.exp(variance * 10.0).reshape(1, 1).clip(1e-6, 1e6).expand(B * n, 1)
+    true_cos = (dirs * gradients).sum(-1, keepdim=True)
+    iter_cos = -(torch.relu(-true_cos * 0.5 + 0.5) * (1.0 - cos_anneal_ratio) + torch.relu(-true_cos) * cos_anneal_ratio)
+    est_next = sdf + iter_cos * dists.reshape(-1, 1) * 0.5
+    est_prev = sdf - iter_cos * dists.reshape(-1, 1) * 0.5
+    prev_cdf = torch.sigmoid(est_prev * inv_s)
+    next_cdf = torch.sigmoid(est_next * inv_s)
+    alpha = ((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).reshape(B, n).clip(0.0, 1.0)
+    pts_norm = torch.linalg.norm(pts, ord=2, dim=-1, keepdim=True).reshape(B, n)
+    inside = (pts_norm < 1.0).float().detach()
+    relax = (pts_norm < 1.2).float().detach()
+    if background_alpha is not None:
+        alpha = alpha * inside + background_alpha[:, :n] * (1.0 - inside)
+        alpha = torch.cat([alpha, background_alpha[:, n:]], dim=-1)
+        sampled_color = sampled_color * inside[:, :, None] + background_sampled_color[:, :n] * (1.0 - inside)[:, :, None]
+        sampled_color = torch.cat([sampled_color, background_sampled_color[:, n:]], dim=1)
+    weights = _cumprod_weights(alpha)
+    weights_sum = weights.sum(dim=-1, keepdim=True)
+    color = (sampled_color * weights[:, :, None]).sum(dim=1)
+    if background_rgb is not None:
+        color = color + background_rgb * (1.0 - weights_sum)
+    gerr = (torch.linalg.norm(gradients.reshape(B, n, 3), ord=2, dim=-1) - 1.0) ** 2
+    gerr = (relax * gerr).sum() / (relax.sum() + 1e-5)
+    return {"color": color, "sdf": sdf, "dists": dists, "gradients": gradients.reshape(B, n, 3), "s_val": 1.0 / inv_s,
+            "mid_z_vals": mid, "weights": weights, "cdf": prev_cdf.reshape(B, n), "gradient_error": gerr, "inside_sphere": inside}
+
+
+def neus_render(sdf_p: Params, color_p: Params, variance: Tensor, nerf_p: Optional[Params], rays_o, rays_d, near, far,
+                n_samples: int = 64, n_importance: int = 64, n_outside: int = 0, up_sample_steps: int = 4,
+                t_rand: Optional[Tensor] = None, t_rand_outside: Optional[Tensor] = None, background_rgb=None,
+                cos_anneal_ratio: float = 0.0, color_cfg: dict = NEUS_COLOR_CFG, sdf_kw: Optional[dict] = None):
+    """:353-453.  t_rand [B,1] / t_rand_outside [B,n_outside]: the uniform numbers the reference draws at :378 / :384 when
+    perturb > 0 (None = perturb off)."""
+    sdf_kw = sdf_kw or {}
+    B = len(rays_o)
+    sample_dist = 2.0 / n_samples
+    z_vals = near + (far - near) * torch.linspace(0.0, 1.0, n_samples)[None, :]
+    z_out = None
+    if n_outside > 0:
+        z_out = torch.linspace(1e-3, 1.0 - 1.0 / (n_outside + 1.0), n_outside)
+    if t_rand is not None:
+        z_vals = z_vals + (t_rand - 0.5) * 2.0 / n_samples
+        if n_outside > 0:
+            mids = 0.5 * (z_out[..., 1:] + z_out[..., :-1])
+            upper = torch.cat([mids, z_out[..., -1:]], -1)
+            lower = torch.cat([z_out[..., :1], mids], -1)
+            z_out = lower[None, :] + (upper - lower)[None, :] * t_rand_outside
+    if n_outside > 0:
+        z_out = far / torch.flip(z_out, dims=[-1]) + 1.0 / n_samples
+    sdf_fn = lambda x: sdf_forward(sdf_p, x, **sdf_kw)[:, :1]
+    n = n_samples
+    if n_importance > 0:
+        with torch.no_grad():
+            pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]
+            sdf = sdf_fn(pts.reshape(-1, 3)).reshape(B, n_samples)
+            for i in range(up_sample_steps):
+                new_z = neus_up_sample(rays_o, rays_d, z_vals, sdf, n_importance // up_sample_steps, 64 * 2 ** i)
+                z_vals, sdf = neus_cat_z_vals(sdf_fn, rays_o, rays_d, z_vals, new_z, sdf, last=(i + 1 == up_sample_steps))
+        n = n_samples + n_importance
+    bg_alpha = bg_color = None
+    if n_outside > 0:
+        z_feed, _ = torch.sort(torch.cat([z_vals, z_out], dim=-1), dim=-1)
+        bg_alpha, bg_color = neus_render_core_outside(nerf_p, rays_o, rays_d, z_feed, sample_dist)
+    ret = neus_render_core(sdf_p, color_p, variance, rays_o, rays_d, z_vals, sample_dist, bg_alpha, bg_color, background_rgb,
+                           cos_anneal_ratio, color_cfg, sdf_kw)
+    w = ret["weights"]
+    return {"color_fine": ret["color"], "s_val": ret["s_val"].reshape(B, n).mean(dim=-1, keepdim=True), "cdf_fine": ret["cdf"],
+            "weight_sum": w.sum(dim=-1, keepdim=True), "weight_max": torch.max(w, dim=-1, keepdim=True)[0],
+            "gradients": ret["gradients"], "weights": w, "gradient_error": ret["gradient_error"],
+            "inside_sphere": ret["inside_sphere"], "z_vals": z_vals}

@@ -347,3 +347,46 @@ def test_composite_renderer_forward_backward(golden):
     for k, gr in zip(["light", "dist", "normal"] + names, grads):
         ref = g["g." + k]
         close(gr.numpy(), ref, 1e-6 * max(np.abs(ref).max(), 1e-12), 2e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------- stage-1 NeuS
+def _neus_loss(out, target, mask):
+    """render_volume.py:262-283: L1 colour + 0.1 eikonal + 0.1 BCE mask (the weights make_golden_neus.py used)."""
+    color_loss = (out["color_fine"] - target).abs().sum() / target.shape[0]
+    mask_loss = torch.nn.functional.binary_cross_entropy(out["weight_sum"].clip(1e-3, 1.0 - 1e-3), mask)
+    return color_loss + 0.1 * out["gradient_error"] + 0.1 * mask_loss
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_neus_render_matches_the_reference_renderer(golden, case):
+    """oracle.neus_render (restated models/renderer.py:128-453, incl. the colour network's skip layer and the background NeRF)
+    against the REAL NeuSRenderer: outputs and the stage-1 loss gradients of every parameter."""
+    g = golden("neus")
+    pre = case + "."
+    grp = lambda m: {k[len(pre + "w." + m + "."):]: T(v).requires_grad_(True) for k, v in g.items() if k.startswith(pre + "w." + m + ".")}
+    sdf_p, color_p, nerf_p = grp("sdf"), grp("color"), grp("nerf")
+    var = grp("dev")["variance"]
+    n_outside, perturb, has_bg, anneal = g[pre + "cfg"]
+    kw = dict(n_samples=16, n_importance=16, n_outside=int(n_outside), up_sample_steps=4, cos_anneal_ratio=float(anneal),
+              background_rgb=torch.ones(1, 3) if has_bg else None)
+    if perturb > 0:
+        kw.update(t_rand=T(g[pre + "t_rand"]), t_rand_outside=T(g[pre + "t_rand_out"]))
+    out = O.neus_render(sdf_p, color_p, var, nerf_p if n_outside > 0 else None, T(g[pre + "o"]), T(g[pre + "d"]),
+                        T(g[pre + "near"]), T(g[pre + "far"]), **kw)
+    for k in ("color_fine", "weights", "weight_sum", "weight_max", "cdf_fine", "gradients", "s_val", "inside_sphere"):
+        close(out[k].detach().numpy(), g[pre + k], 2e-6, 1e-5)
+    close(out["gradient_error"].detach().numpy(), g[pre + "gradient_error"], 1e-7, 1e-5)
+    loss = _neus_loss(out, T(g[pre + "target"]), T(g[pre + "mask"]))
+    assert abs(float(loss) - float(g[pre + "loss"])) <= 1e-5 * abs(float(g[pre + "loss"]))
+    named = [("sdf." + k, v) for k, v in sdf_p.items()] + [("color." + k, v) for k, v in color_p.items()] + [("dev.variance", var)]
+    if n_outside > 0:
+        named += [("nerf." + k, v) for k, v in nerf_p.items()]
+    grads = torch.autograd.grad(loss, [v for _, v in named], allow_unused=True)
+    checked = 0
+    for (k, _), got in zip(named, grads):
+        if pre + "g." + k not in g:
+            continue
+        ref = g[pre + "g." + k]
+        close(got.numpy(), ref, 2e-5 * max(np.abs(ref).max(), 1e-6), 1e-4)
+        checked += 1
+    assert checked >= 50
