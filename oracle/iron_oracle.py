@@ -1293,4 +1293,4 @@ def neus_render(sdf_p: Params, color_p: Params, variance: Tensor, nerf_p: Option
     return {"color_fine": ret["color"], "s_val": ret["s_val"].reshape(B, n).mean(dim=-1, keepdim=True), "cdf_fine": ret["cdf"],
             "weight_sum": w.sum(dim=-1, keepdim=True), "weight_max": torch.max(w, dim=-1, keepdim=True)[0],
             "gradients": ret["gradients"], "weights": w, "gradient_error": ret["gradient_error"],
-            "inside_sphere": ret["inside_sphere"], "z_vals": z_vals}
+            "inside_sphere": ret["inside_sphere"], "z_vals": z_vals, "z_vals_outside": z_out}

@@ -72,3 +72,42 @@ def test_rendering_network_modes_vs_oracle(gemm_mode):
         for k, r in zip(names, rg[3:]):
             got = dict(net.named_parameters())[k].grad.cpu().numpy()
             assert rel_l2(got, r.numpy()) < TOL_GRAD_REL, (nm, k, rel_l2(got, r.numpy()))
+
+
+@pytest.mark.parametrize("M", [333, 4100])
+def test_rendering_network_with_skip_layer_vs_oracle(gemm_mode, M):
+    """The stage-1 colour network (confs/*_iron.conf: n_layers = 8, skip_in = [4], multires = 10, multires_view = 4, 'idr'):
+    layer 4 reads cat(h, input) / sqrt 2 (models/fields.py:226-227), so part of the input gradient arrives through the skip."""
+    import iron_b200
+    from oracle import iron_oracle as O
+    from util import oracle_params
+    cfg = O.NEUS_COLOR_CFG
+    torch.manual_seed(6)
+    net = iron_b200.RenderingNetwork(d_feature=256, mode="idr", d_in=9, d_out=3, d_hidden=256, n_layers=8, skip_in=[4],
+                                     weight_norm=True, multires=10, multires_view=4, squeeze_out=True)
+    assert tuple(net.lin4.weight_v.shape) == (256, 256 + 349) and tuple(net.lin3.weight_v.shape) == (256, 256)
+    p = {k: v.requires_grad_(True) for k, v in oracle_params(net).items()}
+    net = net.to(DEV)
+    gen = torch.Generator().manual_seed(8)
+    pts = (torch.rand(M, 3, generator=gen) - 0.5).requires_grad_(True)
+    nrm = (torch.randn(M, 3, generator=gen)).requires_grad_(True)            # SDF gradients: not unit length
+    view = torch.nn.functional.normalize(torch.randn(M, 3, generator=gen), dim=-1).requires_grad_(True)
+    fts = (torch.randn(M, 256, generator=gen) * 0.3).requires_grad_(True)
+    up = torch.randn(M, 3, generator=gen)
+    ref = O.material_forward(p, cfg, pts, nrm, view, fts)
+    names = sorted(p)
+    rg = torch.autograd.grad((ref * up).sum(), [pts, nrm, view, fts] + [p[k] for k in names])
+    c = [t.detach().clone().to(DEV).requires_grad_(True) for t in (pts, nrm, view, fts)]
+    out = net(c[0], c[1], c[2], c[3])
+    (out * up.to(DEV)).sum().backward()
+    vt = 1.0 if gemm_mode == "ffma" else 10.0
+    assert_close(out.detach().cpu().numpy(), ref.detach().numpy(), 2e-6 * vt, 2e-5 * vt, what="skip net out")
+    for a, b, k in zip(c, rg[:4], ("points", "normals", "view", "feats")):
+        # d_points sums 10 octaves of 2^k (cos du_sin - sin du_cos): the 3xTF32 input gradient's ~1e-6 relative error is
+        # amplified by up to 2^9 (stage 1 never asks for it: the section points carry no gradient)
+        # ... and the other input gradients pass nine 3xTF32 products: a few 1e-4 of the largest entry
+        at = (2e-5 if gemm_mode == "ffma" else (2e-3 if k == "points" else 5e-4)) * float(b.abs().max())
+        assert_close(a.grad.cpu().numpy(), b.numpy(), at, 1e-3, what=f"skip net d_{k}")
+    for k, r in zip(names, rg[4:]):
+        got = dict(net.named_parameters())[k].grad.cpu().numpy()
+        assert rel_l2(got, r.numpy()) < TOL_GRAD_REL, (k, rel_l2(got, r.numpy()))
