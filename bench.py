@@ -774,6 +774,133 @@ def run_render(args):
     emit(line)
 
 
+def run_neus(args):
+    """--workload neus: one stage-1 training step of render_volume.py:230-290 -- NeuSRenderer.render on 512 rays
+    (confs/*_iron.conf: 64 + 64 samples in 4 up-sample steps, 32 outside samples through the background NeRF, perturb on,
+    SDF MLP 8 x 256, colour MLP 8 x 256 with its skip layer), the stage-1 loss (L1 colour + 0.1 eikonal + 0.1 BCE mask) and
+    its backward.  Single GPU, eager (the hierarchical sampler is a sequence of small tensor ops).  `value` = rays/s
+    device-timed; `e2e` adds the H2D copy of the ray batch from pinned memory and the D2H read of the loss."""
+    import torch
+    import iron_b200 as ib
+    from iron_b200 import _lib
+    from oracle import iron_oracle as O
+    lib = _lib.load()
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    H, B = 256, 512
+    torch.manual_seed(0)
+    sdf = ib.SDFNetwork(d_in=3, d_out=257, d_hidden=H, n_layers=8, skip_in=[4], multires=6, bias=0.5, scale=1.0,
+                        geometric_init=True, weight_norm=True)
+    color = ib.RenderingNetwork(d_feature=256, mode="idr", d_in=9, d_out=3, d_hidden=H, n_layers=8, skip_in=[4],
+                                weight_norm=True, multires=10, multires_view=4, squeeze_out=True)
+    devn = ib.SingleVarianceNetwork(0.3)
+    nerf = ib.NeRF(D=8, W=256, d_in=4, d_in_view=3, multires=10, multires_view=4, output_ch=4, skips=[4], use_viewdirs=True)
+    p = lambda mod: {k: v.detach().clone().to(dev).requires_grad_(True) for k, v in mod.state_dict().items()}
+    sdf_p, color_p, nerf_p = p(sdf), p(color), p(nerf)
+    var = devn.variance.detach().clone().to(dev).requires_grad_(True)
+    for m in (sdf, color, devn, nerf):
+        m.to(dev)
+    gen = torch.Generator().manual_seed(9)
+    o = torch.randn(B, 3, generator=gen)
+    o = o / o.norm(dim=-1, keepdim=True) * 2.0
+    d = (torch.rand(B, 3, generator=gen) - 0.5) * 1.2 - o
+    d = d / d.norm(dim=-1, keepdim=True)
+    mid = -(o * d).sum(-1, keepdim=True)
+    host = [t.contiguous().pin_memory() for t in (o, d, mid - 1.0, mid + 1.0, torch.rand(B, 3, generator=gen),
+                                                  (torch.rand(B, 1, generator=gen) > 0.4).float())]
+    t_rand, t_out = torch.rand(B, 1, generator=gen).to(dev), torch.rand(B, 32, generator=gen).to(dev)
+    bg = torch.ones(1, 3, device=dev)
+    ren = ib.NeuSRenderer(nerf, sdf, devn, color, n_samples=64, n_importance=64, n_outside=32, up_sample_steps=4, perturb=1.0)
+    params = [q for m in (sdf, color, devn, nerf) for q in m.parameters()]
+
+    def loss_of(out, target, mask):
+        color_loss = (out["color_fine"] - target).abs().sum() / target.shape[0]
+        mask_loss = torch.nn.functional.binary_cross_entropy(out["weight_sum"].clip(1e-3, 1.0 - 1e-3), mask)
+        return color_loss + 0.1 * out["gradient_error"] + 0.1 * mask_loss
+
+    def step(batch):
+        for q in params:
+            q.grad = None
+        draws = [t_rand, t_out]
+        ren.rand_fn = lambda shape: draws.pop(0).reshape(shape)           # the same uniform numbers in both arms
+        out = ren.render(batch[0], batch[1], batch[2], batch[3], background_rgb=bg, cos_anneal_ratio=0.5)
+        loss = loss_of(out, batch[4], batch[5])
+        loss.backward()
+        return loss.detach()
+
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False          # the background NeRF's cuBLAS GEMMs stay fp32
+    torch.backends.cudnn.allow_tf32 = False
+    on_dev = [t.to(dev) for t in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(max(args.warmup, 3)):
+        step(on_dev)
+    torch.cuda.synchronize()
+    l0 = lib.ironb_launch_count()
+    ms = []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = step(on_dev)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    launches = lib.ironb_launch_count() - l0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss_host = float(step([t.to(dev, non_blocking=True) for t in host]).item())
+    e2e_t = (time.perf_counter() - t0) / args.steps
+    t_med = statistics.median(ms)
+    line = {"metric": "stage-1 NeuS volume-rendered rays/sec fwd+bwd (512 rays x (128 + 32) sections, SDF MLP 8x256)",
+            "value": B / (sum(ms) / len(ms) * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": sum(ms) / len(ms), "ms_per_step_median": t_med, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SURVEY 8 f-4: stage-1 NeuS training step (render_volume.py:230-290), 512 rays, n_samples 64 + "
+                                   "n_importance 64 (4 up-sample steps), n_outside 32 (background NeRF 8x256), perturb on, white "
+                                   "background, cos_anneal 0.5; loss = L1 colour + 0.1 eikonal + 0.1 BCE mask; backward to all four "
+                                   "networks", "sdf_mlp": "8x256, PE L=6, skip@4, softplus(100), weight-norm",
+                       "colour_mlp": "8x256, PE L=10 / view L=4, skip@4, weight-norm", "rays": B, "sdf_points_per_step": B * (64 + 48 + 128),
+                       "l2": "256 MiB flush between steps", "execution": "eager"},
+            "e2e": {"value": B / e2e_t, "unit": UNIT, "h2d_bytes_per_step": sum(t.numel() * 4 for t in host), "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_t * 1e3},
+            "gpu_launches": int(launches), "loss": loss_host, "step_ms": [round(x, 3) for x in ms]}
+    if not args.no_cpu:
+        # the reference's renderer (oracle restatement, pinned to the real NeuSRenderer by tests/golden/neus.npz) as eager
+        # PyTorch on this GPU: same weights, rays and uniform numbers
+        def ref_step():
+            for q in list(sdf_p.values()) + list(color_p.values()) + list(nerf_p.values()) + [var]:
+                q.grad = None
+            with torch.device(dev):
+                out = O.neus_render(sdf_p, color_p, var, nerf_p, on_dev[0], on_dev[1], on_dev[2], on_dev[3], n_samples=64,
+                                    n_importance=64, n_outside=32, up_sample_steps=4, t_rand=t_rand, t_rand_outside=t_out,
+                                    background_rgb=bg, cos_anneal_ratio=0.5)
+                l = loss_of(out, on_dev[4], on_dev[5])
+                l.backward()
+            return l.detach()
+        for _ in range(2):
+            ref_step()
+        torch.cuda.synchronize()
+        rms = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rl = ref_step()
+            e1.record()
+            torch.cuda.synchronize()
+            rms.append(e0.elapsed_time(e1))
+        tr = statistics.median(rms)
+        gmax = max(float((q.grad - sdf_p[k].grad).norm() / sdf_p[k].grad.norm().clamp_min(1e-30)) for k, q in sdf.named_parameters())
+        line["cuda_eager_baseline"] = {
+            "value": B / (tr * 1e-3), "unit": UNIT, "ms_per_step": tr, "steps": 5, "loss": float(rl),
+            "what": "the reference's NeuSRenderer (oracle restatement) + autograd as eager PyTorch on cuda:0, fp32, allow_tf32=False, "
+                    "same weights / rays / uniform numbers",
+            "speedup_of_this_library": (B / (t_med * 1e-3)) / (B / (tr * 1e-3)),
+            "loss_rel_err": abs(loss_host - float(rl)) / abs(float(rl)), "worst_sdf_gradient_rel_l2": gmax}
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    emit(line)
+
+
 _REAL_STDOUT = None
 STAGE = ["not started"]      # the last stage run_ours reached (named in the failure message)
 
@@ -803,9 +930,9 @@ def main():
     ap.add_argument("--patch", type=int, default=64)
     ap.add_argument("--loss", default="reference", choices=["reference", "l2"],
                     help="reference: PyramidL2 + SSIM + roughness range (render_surface.py:594-613), in every arm; l2: round 1's plain L2")
-    ap.add_argument("--workload", default="step", choices=["step", "render1024"],
+    ap.add_argument("--workload", default="step", choices=["step", "render1024", "neus"],
                     help="step: the stage-2 training step (configs[1]; --patch 256 = configs[3]); render1024: configs[2], the "
-                         "full-frame 1024x1024 forward render")
+                         "full-frame 1024x1024 forward render; neus: the stage-1 NeuS training step (SURVEY 8 f-4)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--driver-defaults", action="store_true",
                     help="also run hole filling + edge sampling (the reference drivers' fill_holes=True, handle_edges=True)")
@@ -825,6 +952,9 @@ def main():
         return
     if args.workload == "render1024":
         run_render(args)
+        return
+    if args.workload == "neus":
+        run_neus(args)
         return
     guarded_run_ours(args)
 

@@ -108,6 +108,9 @@ def test_rendering_network_with_skip_layer_vs_oracle(gemm_mode, M):
         # ... and the other input gradients pass nine 3xTF32 products: a few 1e-4 of the largest entry
         at = (2e-5 if gemm_mode == "ffma" else (2e-3 if k == "points" else 5e-4)) * float(b.abs().max())
         assert_close(a.grad.cpu().numpy(), b.numpy(), at, 1e-3, what=f"skip net d_{k}")
+    # nine layers deep: the all-3xTF32 diagnostic mode (truncating forward AND backward accumulation) reaches 1.04e-3 on the
+    # first layer's bias gradient; the default arithmetic stays inside the BASELINE bound
+    tol = 3e-3 if gemm_mode == "tcgen05-tf32" else TOL_GRAD_REL
     for k, r in zip(names, rg[4:]):
         got = dict(net.named_parameters())[k].grad.cpu().numpy()
-        assert rel_l2(got, r.numpy()) < TOL_GRAD_REL, (k, rel_l2(got, r.numpy()))
+        assert rel_l2(got, r.numpy()) < tol, (k, rel_l2(got, r.numpy()))
