@@ -13,7 +13,7 @@ from .embedder import get_embedder
 from .optim import FusedAdam
 from .image_losses import PyramidL2Loss, ssim_loss_fn
 from .renderer import NeRF, NeuSRenderer, SingleVarianceNetwork, sample_pdf
-from .step import GraphedStage2Step, stage2_step
+from .step import GraphedNeusStep, GraphedStage2Step, stage2_step
 
 __all__ = [
     "SDFNetwork", "RenderingNetwork", "PointLightNetwork", "GGXColocatedRenderer", "RayTracer", "Camera",
@@ -21,5 +21,5 @@ __all__ = [
     "reparam_points", "locate_edge_points", "render_edge_pixels", "get_materials", "get_embedder", "make_render_fn", "stage2_step", "GraphedStage2Step", "FusedAdam",
     "PyramidL2Loss", "ssim_loss_fn", "CompositeRenderer", "get_materials_comp", "make_render_fn_comp2",
     "init_sdf_network_dict", "init_rendering_network_dict", "choose_renderer",
-    "NeuSRenderer", "NeRF", "SingleVarianceNetwork", "sample_pdf",
+    "NeuSRenderer", "GraphedNeusStep", "NeRF", "SingleVarianceNetwork", "sample_pdf",
 ]

@@ -289,3 +289,82 @@ class GraphedStage2Step:
         if opt is not None and hasattr(opt, "mark_parameters_updated"):
             opt.mark_parameters_updated()   # the in-graph optimiser moved the parameters: eager folds must refold
         return self.loss
+
+
+class GraphedNeusStep:
+    """One stage-1 training iteration (render_volume.py:230-290: NeuSRenderer.render on a ray batch, the loss, backward) captured
+    ONCE into a CUDA graph and replayed per step, like GraphedStage2Step for stage 2.  The eager step is ~1,600 kernel launches
+    of this library plus the hierarchical sampler's small tensor ops, all enqueued from Python: it is host-bound.
+
+        g = GraphedNeusStep(renderer, batch_size=512, loss_fn=lambda out, target, mask: ..., background_rgb=None,
+                            cos_anneal_ratio=0.0)
+        loss = g.step(rays_o, rays_d, near, far, target, mask)     # host (pinned) or device tensors; .grad of every parameter
+
+    Static shapes only (fixed batch size); `cos_anneal_ratio` is a launch argument of the compositing kernel and therefore baked
+    into the graph: rebuild the object when the schedule moves it (the reference anneals over the first `anneal_end`
+    iterations, then it stays 1).  The perturbation draws come from torch's graph-safe Philox state: every replay draws fresh
+    numbers."""
+
+    def __init__(self, renderer, batch_size, loss_fn, background_rgb=None, cos_anneal_ratio=0.0, warmup=3):
+        self.renderer, self.loss_fn = renderer, loss_fn
+        self.background_rgb, self.cos_anneal_ratio = background_rgb, float(cos_anneal_ratio)
+        mods = [renderer.sdf_network, renderer.color_network, renderer.deviation_network]
+        if renderer.n_outside > 0:
+            mods.append(renderer.nerf)
+        self.params = [p for m in mods for p in m.parameters()]
+        dev = self.params[0].device
+        self.device = dev
+        z = lambda w: torch.zeros(batch_size, w, dtype=torch.float32, device=dev)
+        self.rays_o, self.rays_d, self.near, self.far, self.target, self.mask = z(3), z(3), z(1), z(1), z(3), z(1)
+        self.rays_d[:, 2] = 1.0
+        self.near.fill_(1.0)
+        self.far.fill_(3.0)
+        self.rays_o[:, 2] = -2.0                  # a valid batch for the warm-up: rays through the unit sphere
+        self.mask.fill_(1.0)
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                self._eager()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        from . import _lib
+        n0 = _lib.load().ironb_launch_count()
+        folded = [m for m in mods if hasattr(m, "folded")]
+        for m in folded:
+            m._fold_captured = False
+        try:
+            with torch.cuda.graph(self.graph, stream=side):
+                self.loss, self.out = self._eager()
+        finally:
+            for m in folded:
+                m._fold_captured = False
+        self._grads = {id(p): p.grad for p in self.params}
+        self.kernels_per_replay = int(_lib.load().ironb_launch_count() - n0)
+
+    def _eager(self):
+        for p in self.params:
+            p.grad = None
+        out = self.renderer.render(self.rays_o, self.rays_d, self.near, self.far, background_rgb=self.background_rgb,
+                                   cos_anneal_ratio=self.cos_anneal_ratio)
+        loss = self.loss_fn(out, self.target, self.mask)
+        loss.backward()
+        return loss.detach(), out
+
+    def step(self, rays_o=None, rays_d=None, near=None, far=None, target=None, mask=None):
+        for dst, src in ((self.rays_o, rays_o), (self.rays_d, rays_d), (self.near, near), (self.far, far),
+                         (self.target, target), (self.mask, mask)):
+            if src is not None:
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        for p in self.params:
+            p.grad = self._grads[id(p)]
+        return self.loss
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        self.loss, self.out, self._grads = None, None, {}
+        if self.graph is not None:
+            self.graph.reset()
+            self.graph = None

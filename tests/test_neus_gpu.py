@@ -147,3 +147,39 @@ def test_neus_render_h256_vs_oracle():
     assert abs(float(dev.variance.grad) - float(var.grad)) <= 2e-3 * abs(float(var.grad))
     print(f"neus H=256: render() colour err {e_col:.2e}, weight_sum err {e_ws:.2e}; render_core on the oracle's sections: loss "
           f"{float(loss.detach()):.6f} / {float(rloss.detach()):.6f}, worst gradient rel-L2 {worst:.2e}")
+
+
+def test_graphed_neus_step_matches_eager():
+    """GraphedNeusStep (the stage-1 iteration as one CUDA-graph replay) against the eager step: same loss, same gradients,
+    also after new rays are copied in.  perturb = 0 so both see the same sections."""
+    import iron_b200 as ib
+    torch.manual_seed(5)
+    sdf, color, dev, nerf = build(H=128, d_out=129)
+    for mod in (sdf, color, dev, nerf):
+        mod.to(DEV)
+    B = 96
+    ren = ib.NeuSRenderer(nerf, sdf, dev, color, n_samples=32, n_importance=32, n_outside=16, up_sample_steps=4, perturb=0.0)
+    bg = torch.ones(1, 3, device=DEV)
+    gs = ib.GraphedNeusStep(ren, B, stage1_loss, background_rgb=bg, cos_anneal_ratio=0.25)
+    params = [(f"{i}.{k}", p) for i, m in enumerate((sdf, color, dev, nerf)) for k, p in m.named_parameters()]
+    for seed in (1, 2):
+        gen = torch.Generator().manual_seed(seed)
+        o = torch.randn(B, 3, generator=gen)
+        o = o / o.norm(dim=-1, keepdim=True) * 2.0
+        d = (torch.rand(B, 3, generator=gen) - 0.5) * 1.2 - o
+        d = d / d.norm(dim=-1, keepdim=True)
+        mid = -(o * d).sum(-1, keepdim=True)
+        batch = [o, d, mid - 1.0, mid + 1.0, torch.rand(B, 3, generator=gen), (torch.rand(B, 1, generator=gen) > 0.4).float()]
+        lg = float(gs.step(*[t.pin_memory() for t in batch]))
+        torch.cuda.synchronize()
+        gg = {k: p.grad.clone() for k, p in params}
+        for _, p in params:
+            p.grad = None
+        bd = [t.to(DEV) for t in batch]
+        out = ren.render(bd[0], bd[1], bd[2], bd[3], background_rgb=bg, cos_anneal_ratio=0.25)
+        le = stage1_loss(out, bd[4], bd[5])
+        le.backward()
+        assert abs(lg - float(le.detach())) <= 1e-6 * abs(float(le.detach())), (lg, float(le.detach()))
+        worst = max(rel_l2(gg[k].cpu().numpy(), p.grad.cpu().numpy()) for k, p in params if float(p.grad.abs().max()) > 0)
+        assert worst <= 1e-4, worst                      # atomic accumulation order of the split-K weight gradients
+    gs.close()
