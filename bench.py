@@ -833,6 +833,11 @@ def run_neus(args):
     torch.backends.cudnn.allow_tf32 = False
     on_dev = [t.to(dev) for t in host]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    gs = None
+    if args.exec_mode == "graph":
+        # built BEFORE any eager backward through these parameters (their AccumulateGrad nodes remember the stream they were
+        # created on; a node created on the legacy stream cannot be captured)
+        gs = ib.GraphedNeusStep(ren, B, loss_of, background_rgb=bg, cos_anneal_ratio=0.5)
     for _ in range(max(args.warmup, 3)):
         step(on_dev)
     torch.cuda.synchronize()
@@ -856,11 +861,9 @@ def run_neus(args):
     t_med = statistics.median(ms)
     eager_ms, eager_e2e = list(ms), e2e_t
     graph_info = None
-    if args.exec_mode == "graph":
+    if gs is not None:
         # the same step as ONE CUDA-graph replay (iron_b200.GraphedNeusStep); the perturbation draws then come from torch's
         # graph-safe generator (fresh numbers per replay), so this arm's loss differs from the eager arm's by the draws
-        ren.rand_fn = None
-        gs = ib.GraphedNeusStep(ren, B, loss_of, background_rgb=bg, cos_anneal_ratio=0.5)
         for _ in range(max(args.warmup, 3)):
             gs.step(*on_dev)
         torch.cuda.synchronize()

@@ -300,7 +300,8 @@ class GraphedNeusStep:
                             cos_anneal_ratio=0.0)
         loss = g.step(rays_o, rays_d, near, far, target, mask)     # host (pinned) or device tensors; .grad of every parameter
 
-    Static shapes only (fixed batch size); `cos_anneal_ratio` is a launch argument of the compositing kernel and therefore baked
+    Build it before any eager backward through the same parameters (like GraphedStage2Step: their AccumulateGrad nodes
+    remember the stream they were created on).  Static shapes only (fixed batch size); `cos_anneal_ratio` is a launch argument of the compositing kernel and therefore baked
     into the graph: rebuild the object when the schedule moves it (the reference anneals over the first `anneal_end`
     iterations, then it stays 1).  The perturbation draws come from torch's graph-safe Philox state: every replay draws fresh
     numbers."""
