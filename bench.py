@@ -113,13 +113,40 @@ class ClockSampler:
         return out
 
 
+def shard_mode() -> str:
+    """How the ranks' inputs differ (IRONB_BENCH_SHARD): "views" (default) = every rank renders the canonical centre crop of
+    ITS OWN view, the fixture camera orbited about the y-axis in steps of 45 degrees ("extra views by rotating W2C
+    about the y-axis in 8 steps") -- distinct rays, targets and eikonal samples per GPU, and, because the seed-0 object is
+    close to a sphere, the same amount of tracing work per GPU, which is what weak scaling is defined on; "windows" = one
+    view, distinct crop windows around the centre (crop_corner), whose work differs by up to +-5 % (patch/16 stride) or 2x
+    (tiled: IRONB_BENCH_CROP_STRIDE=<patch>)."""
+    m = os.environ.get("IRONB_BENCH_SHARD", "views")
+    return m if m in ("views", "windows") else "views"
+
+
+def view_w2c(rank: int):
+    """W2C of rank's view as a [4,4] float64 numpy array: the fixture pose with the WORLD rotated by rank x 45 degrees about y,
+    i.e. the camera orbits the object at its elevation and distance (rank 0 = the canonical fixture view)."""
+    import numpy as np
+    from oracle import iron_oracle as O   # fixture constants only
+    W = np.array(O.FIXTURE_W2C, dtype=np.float64).reshape(4, 4)
+    if shard_mode() != "views" or rank % 8 == 0:
+        return W
+    th = 2.0 * np.pi * (rank % 8) / 8.0
+    R = np.eye(4)
+    R[0, 0], R[0, 2], R[2, 0], R[2, 2] = np.cos(th), np.sin(th), -np.sin(th), np.cos(th)
+    return W @ R
+
+
 def crop_corner(rank: int, patch: int):
-    """Per-rank crop of the 512x512 view: rank 0 = the canonical centre crop; the other ranks take DISTINCT windows
+    """Per-rank crop of the 512x512 view ("windows" sharding; with "views" every rank takes the centre crop): rank 0 = the canonical centre crop; the other ranks take DISTINCT windows
     shifted by patch/16 pixels around it (parallel.crop_for_rank).  Weak scaling needs the same work per GPU at every N, and the
     fixture object covers only ~145 pixels of the view: at the 64x64 training patch the shifted windows stay inside the
     silhouette like the centre crop (every ray hits), while windows TILED around the centre (IRONB_BENCH_CROP_STRIDE=<patch>)
     straddle the silhouette and cost about twice the centre crop -- that measures load imbalance, not scaling."""
     from iron_b200.parallel import crop_for_rank
+    if shard_mode() == "views" and "IRONB_BENCH_CROP_STRIDE" not in os.environ:
+        rank = 0
     stride = int(os.environ.get("IRONB_BENCH_CROP_STRIDE", max(patch // 16, 1)))
     return crop_for_rank(rank, patch, stride=stride)
 
@@ -314,7 +341,7 @@ def workload_config(args, patch):
                         f"colocated-flash fixture view, trace+shade+loss+backward",
             "sdf_mlp": f"8x{args.hidden}, PE L=6, skip@4, softplus(100), weight-norm", "material_mlps": "3 x (4x256, ReLU)",
             "rays_per_gpu": patch * patch, "eikonal_points": patch * patch // 2,
-            "sharding": "every rank traces/shades its own crop of the view (rank 0: the centre crop, the others distinct windows patch/16 pixels apart around it = comparable work per GPU, rank_compute_ms_per_step shows what is left; IRONB_BENCH_CROP_STRIDE=<patch> tiles them), own target/eikonal seeds; gradients packed into one flat buffer by the graph, one in-place all-reduce", "parallelism": f"dp{args.gpus} (rays sharded, weights replicated)",
+            "sharding": "every rank traces/shades its own rays (rank 0: the canonical centre crop, the others the centre crop of their OWN view (camera orbited about y in 45-degree steps, SURVEY 8d) = distinct rays, the same work per GPU; rank_compute_ms_per_step shows what imbalance is left; IRONB_BENCH_SHARD=windows: distinct crop windows of one view; IRONB_BENCH_CROP_STRIDE=<patch> tiles them), own target/eikonal seeds; gradients packed into one flat buffer by the graph, one in-place all-reduce", "parallelism": f"dp{args.gpus} (rays sharded, weights replicated)",
             "l2": "256 MiB flush between steps, outside the per-step CUDA-event pairs",
             "init": "seed-0 geometric init, light=32",
             "loss": ("PyramidL2 + 1.0 * SSIM(masked) + 0.1 * roughness range + 0.1 * eikonal: the reference's training loss, "
@@ -388,12 +415,12 @@ def run_ours(args):
     render_fn = ib.make_render_fn(rend)
     tracer = ib.RayTracer()
     tracer.collect_stats = True
+    # weak scaling over patches: every rank traces and shades ITS OWN rays with its own target and eikonal samples
+    # (shard_mode: the centre crop of its own view, or its own crop window of one view); rank 0 is always the canonical
+    # configs[1] input.  The per-rank step and compute times are reported next to the max that defines `value`.
+    crop_rank = int(os.environ.get("IRONB_BENCH_CROP_RANK", rank))      # diagnostic: run another rank's input on one GPU
     K_h = torch.tensor(O.FIXTURE_K, dtype=torch.float64).reshape(4, 4).float().pin_memory()
-    W2C_h = torch.tensor(O.FIXTURE_W2C, dtype=torch.float64).reshape(4, 4).float().pin_memory()
-    # weak scaling over patches: every rank traces and shades ITS OWN crop of the view with its own target and
-    # eikonal samples (rank 0 = the canonical centre crop, the others distinct windows around it: crop_corner); the per-rank
-    # step times are reported next to the max that defines `value`
-    crop_rank = int(os.environ.get("IRONB_BENCH_CROP_RANK", rank))      # diagnostic: run another rank's crop on one GPU
+    W2C_h = torch.from_numpy(view_w2c(crop_rank)).float().pin_memory()
     ul = crop_corner(crop_rank, S) if not os.environ.get("IRONB_BENCH_SAME_CROP") else crop_corner(0, S)
     target_h = (torch.rand(S, S, 3, generator=torch.Generator().manual_seed(11 + rank)) * 0.5).pin_memory()
     eik_h = torch.empty(S * S // 2, 3).uniform_(-1.0, 1.0, generator=torch.Generator().manual_seed(12 + rank)).pin_memory()
@@ -639,6 +666,7 @@ def run_ours(args):
                        "implementation": tracer_impl},
             "wall_ms_per_step_incl_flush": wall * 1e3 / args.steps, "grad_params": n_params,
             "rank_ms_per_step": [round(x, 4) for x in rank_ms], "rank_compute_ms_per_step": rank_compute_ms, "rank_crop_ul": [list(crop_corner(r, S)) for r in range(world)],
+            "rank_view_deg": [45.0 * (r % 8) if shard_mode() == "views" else 0.0 for r in range(world)],
             "loss": loss_host,
             "step_ms": [round(x, 3) for x in step_ms], "tracer_ms": [round(x, 3) for x in tr_ms],
             "tracer_ms_source": ("one sample per replay of the e2e loop (external CUDA-event pair inside the graph)"
