@@ -116,8 +116,9 @@ class ClockSampler:
 def shard_mode() -> str:
     """How the ranks' inputs differ (IRONB_BENCH_SHARD): "views" (default) = every rank renders the canonical centre crop of
     ITS OWN view, the fixture camera orbited about the y-axis in steps of 45 degrees ("extra views by rotating W2C
-    about the y-axis in 8 steps") -- distinct rays, targets and eikonal samples per GPU, and, because the seed-0 object is
-    close to a sphere, the same amount of tracing work per GPU, which is what weak scaling is defined on; "windows" = one
+    about the y-axis in 8 steps") -- distinct rays, targets and eikonal samples per GPU with comparable work (the seed-0
+    object is close to a sphere; measured on one GPU the other views cost 3.5-4.0 ms against the canonical view's 4.1 ms, so
+    rank 0 stays the slowest and the N-GPU step time is the canonical step plus the exchange); "windows" = one
     view, distinct crop windows around the centre (crop_corner), whose work differs by up to +-5 % (patch/16 stride) or 2x
     (tiled: IRONB_BENCH_CROP_STRIDE=<patch>)."""
     m = os.environ.get("IRONB_BENCH_SHARD", "views")
@@ -341,7 +342,7 @@ def workload_config(args, patch):
                         f"colocated-flash fixture view, trace+shade+loss+backward",
             "sdf_mlp": f"8x{args.hidden}, PE L=6, skip@4, softplus(100), weight-norm", "material_mlps": "3 x (4x256, ReLU)",
             "rays_per_gpu": patch * patch, "eikonal_points": patch * patch // 2,
-            "sharding": "every rank traces/shades its own rays (rank 0: the canonical centre crop, the others the centre crop of their OWN view (camera orbited about y in 45-degree steps, SURVEY 8d) = distinct rays, the same work per GPU; rank_compute_ms_per_step shows what imbalance is left; IRONB_BENCH_SHARD=windows: distinct crop windows of one view; IRONB_BENCH_CROP_STRIDE=<patch> tiles them), own target/eikonal seeds; gradients packed into one flat buffer by the graph, one in-place all-reduce", "parallelism": f"dp{args.gpus} (rays sharded, weights replicated)",
+            "sharding": "every rank traces/shades its own rays (rank 0: the canonical centre crop, the others the centre crop of their OWN view (camera orbited about y in 45-degree steps, SURVEY 8d) = distinct rays, comparable work per GPU (3.5-4.1 ms, the canonical view is the most expensive); rank_compute_ms_per_step shows what imbalance is left; IRONB_BENCH_SHARD=windows: distinct crop windows of one view; IRONB_BENCH_CROP_STRIDE=<patch> tiles them), own target/eikonal seeds; gradients packed into one flat buffer by the graph, one in-place all-reduce", "parallelism": f"dp{args.gpus} (rays sharded, weights replicated)",
             "l2": "256 MiB flush between steps, outside the per-step CUDA-event pairs",
             "init": "seed-0 geometric init, light=32",
             "loss": ("PyramidL2 + 1.0 * SSIM(masked) + 0.1 * roughness range + 0.1 * eikonal: the reference's training loss, "
