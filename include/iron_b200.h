@@ -287,22 +287,37 @@ int ironb_mask_rows(const float* const* src, float* const* dst, const int* width
  * The per-ray part of NeuSRenderer.render_core (models/renderer.py:248-351): SDF values / SDF gradients / colours at the n
  * section midpoints of N rays (row-major [N][n], [N][n][3]) -> composited colour [N][3], weights [N][n_tot], cdf [N][n],
  * inside_sphere [N][n] and the eikonal term gradient_error [1]; acc [2] keeps the two eikonal sums for the backward.
- * bg_alpha [N][n_tot] / bg_color [N][n_tot][3]: the background NeRF's alpha and colour (render_core_outside, :156-190), NULL
- * without a background model (then n_tot == n); bg_rgb [3]: fixed background colour or NULL; inv_s [1] on the device. */
+ * bg_density [N][n_tot] / bg_dists [N][n_tot] / bg_color [N][n_tot][3]: the background NeRF's raw density, the lengths of its
+ * sections and its colour (render_core_outside, :145-170: alpha = 1 - exp(-softplus(density) dist) is formed in the kernel),
+ * NULL without a background model (then n_tot == n); bg_rgb [3]: fixed background colour or NULL; inv_s [1] on the device. */
 int ironb_neus_composite_fwd(const float* ray_o, const float* ray_d, const float* mid_z, const float* dists, const float* sdf,
-                             const float* grad, const float* color, const float* inv_s, const float* bg_alpha,
-                             const float* bg_color, const float* bg_rgb, int64_t N, int n, int n_tot, float cos_anneal_ratio,
-                             float* out_color, float* weights, float* cdf, float* inside, float* acc, float* gradient_error,
-                             void* stream);
+                             const float* grad, const float* color, const float* inv_s, const float* bg_density,
+                             const float* bg_dists, const float* bg_color, const float* bg_rgb, int64_t N, int n, int n_tot,
+                             float cos_anneal_ratio, float* out_color, float* weights, float* cdf, float* inside, float* acc,
+                             float* gradient_error, void* stream);
 /* Backward of the above (replaces autograd through :277-322): upstream d_color [N][3], d_weights [N][n_tot] or NULL,
  * d_gradient_error [1] or NULL -> d_sdf [N][n], d_grad [N][n][3], d_colors [N][n][3], d_inv_s [1], and with a background
- * d_bg_alpha [N][n_tot], d_bg_color [N][n_tot][3].  The forward quantities are recomputed from the same inputs. */
+ * d_bg_density [N][n_tot], d_bg_color [N][n_tot][3].  The forward quantities are recomputed from the same inputs. */
 int ironb_neus_composite_bwd(const float* ray_o, const float* ray_d, const float* mid_z, const float* dists, const float* sdf,
-                             const float* grad, const float* color, const float* inv_s, const float* bg_alpha,
-                             const float* bg_color, const float* bg_rgb, int64_t N, int n, int n_tot, float cos_anneal_ratio,
-                             const float* weights, const float* acc, const float* d_color, const float* d_weights,
-                             const float* d_gradient_error, float* d_sdf, float* d_grad, float* d_colors, float* d_inv_s,
-                             float* d_bg_alpha, float* d_bg_color, void* stream);
+                             const float* grad, const float* color, const float* inv_s, const float* bg_density,
+                             const float* bg_dists, const float* bg_color, const float* bg_rgb, int64_t N, int n, int n_tot,
+                             float cos_anneal_ratio, const float* weights, const float* acc, const float* d_color,
+                             const float* d_weights, const float* d_gradient_error, float* d_sdf, float* d_grad,
+                             float* d_colors, float* d_inv_s, float* d_bg_density, float* d_bg_color, void* stream);
+/* Sections of a ray batch (:254-262, :145-160): dists [N][n] (last = sample_dist), mid [N][n], the section midpoints pts
+ * [N][n][3] (outside != 0: the background model's inverted-sphere points, [N][n][4]) and, if dirs != NULL, the per-point view
+ * directions [N][n][3]. */
+int ironb_neus_sections(const float* ray_o, const float* ray_d, const float* z, int64_t N, int n, float sample_dist, int outside,
+                        float* dists, float* mid, float* pts, float* dirs, void* stream);
+/* One hierarchical-sampling step, NeuSRenderer.up_sample + sample_pdf(det=True) (:192-232, :43-73): from n ascending samples
+ * z [N][n] with SDF values sdf [N][n] and a fixed sharpness inv_s to m new samples new_z [N][m] at the quantiles of the interval
+ * weights' CDF, and (new_pts != NULL) their points o + d z [N][m][3].  n <= 256. */
+int ironb_neus_upsample(const float* ray_o, const float* ray_d, const float* z, const float* sdf, int64_t N, int n, int m,
+                        float inv_s, float* new_z, float* new_pts, void* stream);
+/* cat_z_vals (:234-246): merges the ascending lists z [N][n] and new_z [N][m] into out_z [N][n+m]; out_sdf != NULL: the SDF values
+ * (sdf [N][n], new_sdf [N][m]) travel with their samples. */
+int ironb_neus_merge(const float* z, const float* sdf, int n, const float* new_z, const float* new_sdf, int m, int64_t N,
+                     float* out_z, float* out_sdf, void* stream);
 /* Gradient bucket of the data-parallel step (the reference is single-GPU, no interface replaced):
  * flat[off[t] .. off[t] + off[n + t]) = scale * src[t][:] for t < n, zeros where src[t] is NULL.  src_dev (n pointers) and
  * off_dev (n element offsets followed by n element counts) are DEVICE arrays, so the launch can be a CUDA-graph node.  max_numel sizes the grid. */

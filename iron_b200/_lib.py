@@ -90,8 +90,11 @@ _PROTOS = {
     "ironb_roughrange_fwd": (_INT, [_P, _P, _I64, _F, _F, _P, _P, _P]),
     "ironb_roughrange_bwd": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _P, _P]),
     "ironb_mask_rows": (_INT, [_PP, _PP, C.POINTER(C.c_int), _INT, _P, _I64, _P]),
-    "ironb_neus_composite_fwd": (_INT, [_P] * 11 + [_I64, _INT, _INT, _F] + [_P] * 6 + [_P]),
-    "ironb_neus_composite_bwd": (_INT, [_P] * 11 + [_I64, _INT, _INT, _F] + [_P] * 11 + [_P]),
+    "ironb_neus_composite_fwd": (_INT, [_P] * 12 + [_I64, _INT, _INT, _F] + [_P] * 6 + [_P]),
+    "ironb_neus_composite_bwd": (_INT, [_P] * 12 + [_I64, _INT, _INT, _F] + [_P] * 11 + [_P]),
+    "ironb_neus_sections": (_INT, [_P, _P, _P, _I64, _INT, _F, _INT, _P, _P, _P, _P, _P]),
+    "ironb_neus_upsample": (_INT, [_P, _P, _P, _P, _I64, _INT, _INT, _F, _P, _P, _P]),
+    "ironb_neus_merge": (_INT, [_P, _P, _INT, _P, _P, _INT, _I64, _P, _P, _P]),
     "ironb_pack_tensors": (_INT, [_P, _P, _INT, _I64, _P, _F, _P]),
     "ironb_patch_loss_workspace_bytes": (_I64, [_INT, _INT, _INT]),
     "ironb_pyramid_l2": (_INT, [_P, _PI64, _P, _PI64, _INT, _INT, _INT, _P, _P, _PI64, _P, _I64, _P]),

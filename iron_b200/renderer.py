@@ -106,25 +106,44 @@ def sample_pdf(bins, weights, n_samples, det=False):
     return bins_b + t * (bins_a - bins_b)
 
 
+def _cf(t):
+    return _lib.f32c(t)
+
+
+def ray_sections(rays_o, rays_d, z_vals, sample_dist, outside=False, want_dirs=True):
+    """(dists [N,n], mid_z [N,n], pts [N*n, 3 or 4], dirs [N*n,3] or None) of a ray batch in one launch (`ironb_neus_sections`):
+    section lengths (last = sample_dist), midpoints, the midpoints' positions -- for the background model the inverted-sphere
+    points (x / max(|x|,1), 1 / max(|x|,1)) -- and the per-point view directions (models/renderer.py:254-262, :145-160)."""
+    N, n = z_vals.shape
+    dev = z_vals.device
+    z = _cf(z_vals)
+    dists = torch.empty(N, n, dtype=torch.float32, device=dev)
+    mid = torch.empty(N, n, dtype=torch.float32, device=dev)
+    pts = torch.empty(N * n, 4 if outside else 3, dtype=torch.float32, device=dev)
+    dirs = torch.empty(N * n, 3, dtype=torch.float32, device=dev) if want_dirs else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().ironb_neus_sections(_lib.ptr(_cf(rays_o)), _lib.ptr(_cf(rays_d)), _lib.ptr(z), N, n, float(sample_dist),
+                                                   int(outside), _lib.ptr(dists), _lib.ptr(mid), _lib.ptr(pts), _lib.ptr(dirs),
+                                                   _lib.stream()), "neus_sections")
+    return dists, mid, pts, dirs
+
+
 class _NeusComposite(torch.autograd.Function):
-    """(color, weights, cdf, inside_sphere, gradient_error) of render_core from per-section inputs; csrc/neus.cu."""
+    """(color, weights, cdf, inside_sphere, gradient_error) of render_core from per-section inputs; csrc/neus.cu.  The background
+    enters as the NeRF's raw density + section lengths + colour; its alpha is formed inside the kernel."""
 
     @staticmethod
-    def forward(ctx, rays_o, rays_d, mid_z, dists, sdf, grad, color, inv_s, bg_alpha, bg_color, bg_rgb, anneal):
+    def forward(ctx, rays_o, rays_d, mid_z, dists, sdf, grad, color, inv_s, bg_density, bg_dists, bg_color, bg_rgb, anneal):
         lib = _lib.load()
         N, n = mid_z.shape
-        n_tot = bg_alpha.shape[1] if bg_alpha is not None else n
+        n_tot = bg_density.shape[1] if bg_density is not None else n
         dev = mid_z.device
-        f = _lib.f32c
-        args = [f(rays_o), f(rays_d), f(mid_z), f(dists), f(sdf.reshape(N, n)), f(grad.reshape(N, n, 3)), f(color.reshape(N, n, 3)),
-                f(inv_s.reshape(1)), None if bg_alpha is None else f(bg_alpha), None if bg_color is None else f(bg_color),
-                None if bg_rgb is None else f(bg_rgb.reshape(3))]
-        out_color = torch.empty(N, 3, dtype=torch.float32, device=dev)
-        weights = torch.empty(N, n_tot, dtype=torch.float32, device=dev)
-        cdf = torch.empty(N, n, dtype=torch.float32, device=dev)
-        inside = torch.empty(N, n, dtype=torch.float32, device=dev)
-        acc = torch.empty(2, dtype=torch.float32, device=dev)
-        gerr = torch.empty((), dtype=torch.float32, device=dev)
+        opt = lambda t: None if t is None else _cf(t)
+        args = [_cf(rays_o), _cf(rays_d), _cf(mid_z), _cf(dists), _cf(sdf.reshape(N, n)), _cf(grad.reshape(N, n, 3)),
+                _cf(color.reshape(N, n, 3)), _cf(inv_s.reshape(1)), opt(bg_density), opt(bg_dists), opt(bg_color),
+                None if bg_rgb is None else _cf(bg_rgb.reshape(3))]
+        new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        out_color, weights, cdf, inside, acc, gerr = new(N, 3), new(N, n_tot), new(N, n), new(N, n), new(2), new(())
         with torch.cuda.device(dev):
             _lib.check(lib.ironb_neus_composite_fwd(*[_lib.ptr(a) for a in args], N, n, n_tot, float(anneal), _lib.ptr(out_color),
                                                     _lib.ptr(weights), _lib.ptr(cdf), _lib.ptr(inside), _lib.ptr(acc),
@@ -144,27 +163,26 @@ class _NeusComposite(torch.autograd.Function):
         dev = weights.device
         args = ctx.args
         has_bg = args[8] is not None
-        d_sdf = torch.empty(N, n, dtype=torch.float32, device=dev)
-        d_grad = torch.empty(N, n, 3, dtype=torch.float32, device=dev)
-        d_colors = torch.empty(N, n, 3, dtype=torch.float32, device=dev)
-        d_inv_s = torch.empty(1, dtype=torch.float32, device=dev)
-        d_bga = torch.empty(N, n_tot, dtype=torch.float32, device=dev) if has_bg else None
-        d_bgc = torch.empty(N, n_tot, 3, dtype=torch.float32, device=dev) if has_bg else None
-        g = lambda t: None if t is None else _lib.f32c(t)
+        new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        d_sdf, d_grad, d_colors, d_inv_s = new(N, n), new(N, n, 3), new(N, n, 3), new(1)
+        d_bgd = new(N, n_tot) if has_bg else None
+        d_bgc = new(N, n_tot, 3) if has_bg else None
+        opt = lambda t: None if t is None else _cf(t)
         with torch.cuda.device(dev):
             _lib.check(lib.ironb_neus_composite_bwd(*[_lib.ptr(a) for a in args], N, n, n_tot, ctx.anneal, _lib.ptr(weights),
-                                                    _lib.ptr(acc), _lib.ptr(g(d_color)), _lib.ptr(g(d_weights)),
-                                                    _lib.ptr(None if d_gerr is None else g(d_gerr).reshape(1)), _lib.ptr(d_sdf),
-                                                    _lib.ptr(d_grad), _lib.ptr(d_colors), _lib.ptr(d_inv_s), _lib.ptr(d_bga),
+                                                    _lib.ptr(acc), _lib.ptr(opt(d_color)), _lib.ptr(opt(d_weights)),
+                                                    _lib.ptr(None if d_gerr is None else _cf(d_gerr).reshape(1)), _lib.ptr(d_sdf),
+                                                    _lib.ptr(d_grad), _lib.ptr(d_colors), _lib.ptr(d_inv_s), _lib.ptr(d_bgd),
                                                     _lib.ptr(d_bgc), _lib.stream()), "neus_composite_bwd")
         s_sdf, s_grad, s_color, s_inv = ctx.shapes
         return (None, None, None, None, d_sdf.reshape(s_sdf), d_grad.reshape(s_grad), d_colors.reshape(s_color),
-                d_inv_s.reshape(s_inv), d_bga, d_bgc, None, None)
+                d_inv_s.reshape(s_inv), d_bgd, None, d_bgc, None, None)
 
 
 class NeuSRenderer:
     """models/renderer.py:128-453: same constructor, `render(rays_o, rays_d, near, far, perturb_overwrite=-1,
-    background_rgb=None, cos_anneal_ratio=0.0)` and return keys."""
+    background_rgb=None, cos_anneal_ratio=0.0)` and return keys; `up_sample`, `cat_z_vals`, `render_core`,
+    `render_core_outside` keep their signatures."""
 
     def __init__(self, nerf, sdf_network, deviation_network, color_network, n_samples, n_importance, n_outside, up_sample_steps,
                  perturb):
@@ -180,148 +198,137 @@ class NeuSRenderer:
         self.rand_fn = None          # tests inject the uniform numbers the reference drew; None = torch.rand on the rays' device
 
     # ---- background model (:140-190) ------------------------------------------------------------------------------
-    def render_core_outside(self, rays_o, rays_d, z_vals, sample_dist, nerf, background_rgb=None):
-        batch_size, n_samples = z_vals.shape
-        dists = z_vals[..., 1:] - z_vals[..., :-1]
-        dists = torch.cat([dists, torch.full_like(dists[..., :1], sample_dist)], -1)
-        mid_z_vals = z_vals + dists * 0.5
-        pts = rays_o[:, None, :] + rays_d[:, None, :] * mid_z_vals[..., :, None]
-        dis_to_center = torch.linalg.norm(pts, ord=2, dim=-1, keepdim=True).clip(1.0, 1e10)
-        pts = torch.cat([pts / dis_to_center, 1.0 / dis_to_center], dim=-1)
-        dirs = rays_d[:, None, :].expand(batch_size, n_samples, 3)
-        pts = pts.reshape(-1, 3 + int(self.n_outside > 0))
-        dirs = dirs.reshape(-1, 3)
+    def _outside(self, rays_o, rays_d, z_vals, sample_dist, nerf):
+        """Raw density [N,n], section lengths [N,n] and colour [N,n,3] of the background model on the given sections."""
+        N, n = z_vals.shape
+        dists, _, pts, dirs = ray_sections(rays_o, rays_d, z_vals, sample_dist, outside=self.n_outside > 0)
         density, sampled_color = nerf(pts, dirs)
-        alpha = 1.0 - torch.exp(-F.softplus(density.reshape(batch_size, n_samples)) * dists)
-        alpha = alpha.reshape(batch_size, n_samples)
-        weights = alpha * torch.cumprod(torch.cat([torch.ones([batch_size, 1], device=alpha.device), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
-        sampled_color = sampled_color.reshape(batch_size, n_samples, 3)
+        return density.reshape(N, n), dists, sampled_color.reshape(N, n, 3)
+
+    def render_core_outside(self, rays_o, rays_d, z_vals, sample_dist, nerf, background_rgb=None):
+        density, dists, sampled_color = self._outside(rays_o, rays_d, z_vals, sample_dist, nerf)
+        alpha = 1.0 - torch.exp(-F.softplus(density) * dists)
+        trans = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+        weights = alpha * trans
         color = (weights[:, :, None] * sampled_color).sum(dim=1)
         if background_rgb is not None:
             color = color + background_rgb * (1.0 - weights.sum(dim=-1, keepdim=True))
         return {"color": color, "sampled_color": sampled_color, "alpha": alpha, "weights": weights}
 
     # ---- hierarchical sampling (:192-246), no gradients -----------------------------------------------------------------
-    def up_sample(self, rays_o, rays_d, z_vals, sdf, n_importance, inv_s):
-        batch_size, n_samples = z_vals.shape
-        pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]
-        radius = torch.linalg.norm(pts, ord=2, dim=-1, keepdim=False)
-        inside_sphere = (radius[:, :-1] < 1.0) | (radius[:, 1:] < 1.0)
-        sdf = sdf.reshape(batch_size, n_samples)
-        prev_sdf, next_sdf = sdf[:, :-1], sdf[:, 1:]
-        prev_z_vals, next_z_vals = z_vals[:, :-1], z_vals[:, 1:]
-        mid_sdf = (prev_sdf + next_sdf) * 0.5
-        cos_val = (next_sdf - prev_sdf) / (next_z_vals - prev_z_vals + 1e-5)
-        prev_cos_val = torch.cat([torch.zeros([batch_size, 1], device=z_vals.device), cos_val[:, :-1]], dim=-1)
-        cos_val = torch.minimum(prev_cos_val, cos_val)
-        cos_val = cos_val.clip(-1e3, 0.0) * inside_sphere
-        dist = next_z_vals - prev_z_vals
-        prev_esti_sdf = mid_sdf - cos_val * dist * 0.5
-        next_esti_sdf = mid_sdf + cos_val * dist * 0.5
-        prev_cdf = torch.sigmoid(prev_esti_sdf * inv_s)
-        next_cdf = torch.sigmoid(next_esti_sdf * inv_s)
-        alpha = (prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)
-        weights = alpha * torch.cumprod(torch.cat([torch.ones([batch_size, 1], device=z_vals.device), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
-        return sample_pdf(z_vals, weights, n_importance, det=True).detach()
+    def _up_sample(self, rays_o, rays_d, z_vals, sdf, n_importance, inv_s, want_pts):
+        N, n = z_vals.shape
+        dev = z_vals.device
+        new_z = torch.empty(N, n_importance, dtype=torch.float32, device=dev)
+        pts = torch.empty(N * n_importance, 3, dtype=torch.float32, device=dev) if want_pts else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().ironb_neus_upsample(_lib.ptr(_cf(rays_o)), _lib.ptr(_cf(rays_d)), _lib.ptr(_cf(z_vals)),
+                                                       _lib.ptr(_cf(sdf.reshape(N, n))), N, n, int(n_importance), float(inv_s),
+                                                       _lib.ptr(new_z), _lib.ptr(pts), _lib.stream()), "neus_upsample")
+        return new_z, pts
 
-    def cat_z_vals(self, rays_o, rays_d, z_vals, new_z_vals, sdf, last=False):
-        batch_size, n_samples = z_vals.shape
-        _, n_importance = new_z_vals.shape
-        pts = rays_o[:, None, :] + rays_d[:, None, :] * new_z_vals[..., :, None]
-        z_vals = torch.cat([z_vals, new_z_vals], dim=-1)
-        z_vals, index = torch.sort(z_vals, dim=-1)
+    def up_sample(self, rays_o, rays_d, z_vals, sdf, n_importance, inv_s):
+        """n_importance new samples per ray at the quantiles of the interval weights under the fixed sharpness inv_s: one
+        launch (`ironb_neus_upsample`) for the reference's alpha / cumprod / sample_pdf(det=True) sequence."""
+        return self._up_sample(rays_o, rays_d, z_vals, sdf, n_importance, inv_s, False)[0]
+
+    def cat_z_vals(self, rays_o, rays_d, z_vals, new_z_vals, sdf, last=False, new_pts=None):
+        """Sorted union of the two ascending sample lists (a per-ray merge, `ironb_neus_merge`); unless `last`, the SDF is
+        evaluated at the new samples and travels with them."""
+        N, n = z_vals.shape
+        m = new_z_vals.shape[1]
+        dev = z_vals.device
+        new_sdf = None
         if not last:
-            new_sdf = self.sdf_network.sdf(pts.reshape(-1, 3)).reshape(batch_size, n_importance)
-            sdf = torch.cat([sdf, new_sdf], dim=-1)
-            sdf = torch.gather(sdf, -1, index)
-        return z_vals, sdf
+            if new_pts is None:
+                new_pts = (rays_o[:, None, :] + rays_d[:, None, :] * new_z_vals[..., :, None]).reshape(-1, 3)
+            new_sdf = _cf(self.sdf_network.sdf(new_pts).reshape(N, m))
+        out_z = torch.empty(N, n + m, dtype=torch.float32, device=dev)
+        out_sdf = torch.empty(N, n + m, dtype=torch.float32, device=dev) if not last else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().ironb_neus_merge(_lib.ptr(_cf(z_vals)), _lib.ptr(None if last else _cf(sdf.reshape(N, n))), n,
+                                                    _lib.ptr(_cf(new_z_vals)), _lib.ptr(new_sdf), m, N, _lib.ptr(out_z),
+                                                    _lib.ptr(out_sdf), _lib.stream()), "neus_merge")
+        return out_z, (sdf if last else out_sdf)
 
     # ---- the differentiable core (:248-351) ---------------------------------------------------------------------------------
-    def render_core(self, rays_o, rays_d, z_vals, sample_dist, sdf_network, deviation_network, color_network,
-                    background_alpha=None, background_sampled_color=None, background_rgb=None, cos_anneal_ratio=0.0):
-        batch_size, n_samples = z_vals.shape
-        dists = z_vals[..., 1:] - z_vals[..., :-1]
-        dists = torch.cat([dists, torch.full_like(dists[..., :1], sample_dist)], -1)
-        mid_z_vals = z_vals + dists * 0.5
-        pts = rays_o[:, None, :] + rays_d[:, None, :] * mid_z_vals[..., :, None]
-        dirs = rays_d[:, None, :].expand(pts.shape)
-        pts = pts.reshape(-1, 3)
-        dirs = dirs.reshape(-1, 3)
+    def _core(self, rays_o, rays_d, z_vals, sample_dist, sdf_network, deviation_network, color_network, bg, background_rgb,
+              cos_anneal_ratio):
+        N, n = z_vals.shape
+        dists, mid_z_vals, pts, dirs = ray_sections(rays_o, rays_d, z_vals, sample_dist)
         # sdf_network(pts) + sdf_network.gradient(pts) of the reference (:270-274) in one evaluation
         sdf, feature_vector, gradients = sdf_network.get_all(pts, is_training=torch.is_grad_enabled())
-        sampled_color = color_network(pts, gradients, dirs, feature_vector).reshape(batch_size, n_samples, 3)
+        sampled_color = color_network(pts, gradients, dirs, feature_vector)
         inv_s = deviation_network(torch.zeros([1, 3], device=pts.device))[:, :1].clip(1e-6, 1e6)     # single parameter
+        bg_density, bg_dists, bg_color = bg if bg is not None else (None, None, None)
         color, weights, cdf, inside_sphere, gradient_error = _NeusComposite.apply(
-            rays_o, rays_d, mid_z_vals, dists, sdf, gradients, sampled_color, inv_s, background_alpha, background_sampled_color,
+            rays_o, rays_d, mid_z_vals, dists, sdf, gradients, sampled_color, inv_s, bg_density, bg_dists, bg_color,
             background_rgb, float(cos_anneal_ratio))
-        return {
-            "color": color,
-            "sdf": sdf,
-            "dists": dists,
-            "gradients": gradients.reshape(batch_size, n_samples, 3),
-            "s_val": 1.0 / inv_s.expand(batch_size * n_samples, 1),
-            "mid_z_vals": mid_z_vals,
-            "weights": weights,
-            "cdf": cdf,
-            "gradient_error": gradient_error,
-            "inside_sphere": inside_sphere,
-        }
+        return {"color": color, "sdf": sdf, "dists": dists, "gradients": gradients.reshape(N, n, 3),
+                "s_val": 1.0 / inv_s.expand(N * n, 1), "mid_z_vals": mid_z_vals, "weights": weights, "cdf": cdf,
+                "gradient_error": gradient_error, "inside_sphere": inside_sphere}
+
+    def render_core(self, rays_o, rays_d, z_vals, sample_dist, sdf_network, deviation_network, color_network,
+                    background_alpha=None, background_sampled_color=None, background_rgb=None, cos_anneal_ratio=0.0):
+        """The reference's signature: `background_alpha` is an ALPHA in [0, 1) (what render_core_outside returns).  The kernel
+        takes a density and a section length, so the alpha is passed as the density that reproduces it with length 1:
+        alpha = 1 - exp(-softplus(x)), x = log(expm1(-log1p(-alpha)))."""
+        bg = None
+        if background_alpha is not None:
+            tau = -torch.log1p(-background_alpha.clamp(max=1.0 - 1e-7))                  # optical depth
+            density = torch.where(tau > 20.0, tau, torch.log(torch.expm1(tau.clamp(min=1e-30))))
+            bg = (density, torch.ones_like(density), background_sampled_color)
+        return self._core(rays_o, rays_d, z_vals, sample_dist, sdf_network, deviation_network, color_network, bg, background_rgb,
+                          cos_anneal_ratio)
 
     def render(self, rays_o, rays_d, near, far, perturb_overwrite=-1, background_rgb=None, cos_anneal_ratio=0.0):
         dev = rays_o.device
-        batch_size = len(rays_o)
-        sample_dist = 2.0 / self.n_samples
-        z_vals = torch.linspace(0.0, 1.0, self.n_samples, device=dev)
-        z_vals = near + (far - near) * z_vals[None, :]
-        z_vals_outside = None
-        if self.n_outside > 0:
-            z_vals_outside = torch.linspace(1e-3, 1.0 - 1.0 / (self.n_outside + 1.0), self.n_outside, device=dev)
-        n_samples = self.n_samples
-        perturb = self.perturb
-        if perturb_overwrite >= 0:
-            perturb = perturb_overwrite
+        N = len(rays_o)
+        ns, n_out = self.n_samples, self.n_outside
+        sample_dist = 2.0 / ns                                  # the region of interest is the unit sphere
         rand = self.rand_fn if self.rand_fn is not None else (lambda shape: torch.rand(shape, device=dev))
+        perturb = perturb_overwrite if perturb_overwrite >= 0 else self.perturb
+        # ---- coarse samples: uniform in [near, far], jittered by one draw per ray (:356-379)
+        z_vals = near + (far - near) * torch.linspace(0.0, 1.0, ns, device=dev)[None, :]
         if perturb > 0:
-            t_rand = rand([batch_size, 1]) - 0.5
-            z_vals = z_vals + t_rand * 2.0 / self.n_samples
-            if self.n_outside > 0:
-                mids = 0.5 * (z_vals_outside[..., 1:] + z_vals_outside[..., :-1])
-                upper = torch.cat([mids, z_vals_outside[..., -1:]], -1)
-                lower = torch.cat([z_vals_outside[..., :1], mids], -1)
-                t_rand = rand([batch_size, z_vals_outside.shape[-1]])
-                z_vals_outside = lower[None, :] + (upper - lower)[None, :] * t_rand
-        if self.n_outside > 0:
-            z_vals_outside = far / torch.flip(z_vals_outside, dims=[-1]) + 1.0 / self.n_samples
-        background_alpha = None
-        background_sampled_color = None
+            z_vals = z_vals + (rand([N, 1]) - 0.5) * (2.0 / ns)
+        # ---- outside samples: uniform in inverse depth beyond `far`, stratified jitter (:361-389)
+        z_out = None
+        if n_out > 0:
+            z_out = torch.linspace(1e-3, 1.0 - 1.0 / (n_out + 1.0), n_out, device=dev)
+            if perturb > 0:
+                mids = 0.5 * (z_out[1:] + z_out[:-1])
+                lower, upper = torch.cat([z_out[:1], mids]), torch.cat([mids, z_out[-1:]])
+                z_out = lower[None, :] + (upper - lower)[None, :] * rand([N, n_out])
+            z_out = far / torch.flip(z_out, dims=[-1]) + 1.0 / ns
+        # ---- hierarchical sampling: up_sample_steps rounds of n_importance / steps new samples at sharpness 64 * 2^i (:394-419)
+        n = ns
         if self.n_importance > 0:
             with torch.no_grad():
-                pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]
-                sdf = self.sdf_network.sdf(pts.reshape(-1, 3)).reshape(batch_size, self.n_samples)
+                # the SDF AT the coarse samples (not at section midpoints: :397-398)
+                sdf = self.sdf_network.sdf((rays_o[:, None, :] + rays_d[:, None, :] * z_vals[..., :, None]).reshape(-1, 3)).reshape(N, ns)
+                per = self.n_importance // self.up_sample_steps
                 for i in range(self.up_sample_steps):
-                    new_z_vals = self.up_sample(rays_o, rays_d, z_vals, sdf, self.n_importance // self.up_sample_steps, 64 * 2 ** i)
-                    z_vals, sdf = self.cat_z_vals(rays_o, rays_d, z_vals, new_z_vals, sdf, last=(i + 1 == self.up_sample_steps))
-            n_samples = self.n_samples + self.n_importance
-        if self.n_outside > 0:
-            z_vals_feed = torch.cat([z_vals, z_vals_outside], dim=-1)
-            z_vals_feed, _ = torch.sort(z_vals_feed, dim=-1)
-            ret_outside = self.render_core_outside(rays_o, rays_d, z_vals_feed, sample_dist, self.nerf)
-            background_sampled_color = ret_outside["sampled_color"]
-            background_alpha = ret_outside["alpha"]
-        ret_fine = self.render_core(rays_o, rays_d, z_vals, sample_dist, self.sdf_network, self.deviation_network,
-                                    self.color_network, background_rgb=background_rgb, background_alpha=background_alpha,
-                                    background_sampled_color=background_sampled_color, cos_anneal_ratio=cos_anneal_ratio)
-        weights = ret_fine["weights"]
-        # s_val over the sections the reference averages over: (n_samples) of them, all equal to 1 / inv_s
-        s_val = ret_fine["s_val"].reshape(batch_size, n_samples).mean(dim=-1, keepdim=True)
+                    last = i + 1 == self.up_sample_steps
+                    new_z, new_pts = self._up_sample(rays_o, rays_d, z_vals, sdf, per, 64 * 2 ** i, not last)
+                    z_vals, sdf = self.cat_z_vals(rays_o, rays_d, z_vals, new_z, sdf, last=last, new_pts=new_pts)
+            n = ns + self.n_importance
+        # ---- background model on the union of all samples (:422-428), then the core
+        bg = None
+        if n_out > 0:
+            z_feed, _ = torch.sort(torch.cat([z_vals, z_out], dim=-1), dim=-1)
+            bg = self._outside(rays_o, rays_d, z_feed, sample_dist, self.nerf)
+        fine = self._core(rays_o, rays_d, z_vals, sample_dist, self.sdf_network, self.deviation_network, self.color_network, bg,
+                          background_rgb, cos_anneal_ratio)
+        weights = fine["weights"]
         return {
-            "color_fine": ret_fine["color"],
-            "s_val": s_val,
-            "cdf_fine": ret_fine["cdf"],
+            "color_fine": fine["color"],
+            "s_val": fine["s_val"].reshape(N, n).mean(dim=-1, keepdim=True),
+            "cdf_fine": fine["cdf"],
             "weight_sum": weights.sum(dim=-1, keepdim=True),
             "weight_max": torch.max(weights, dim=-1, keepdim=True)[0],
-            "gradients": ret_fine["gradients"],
+            "gradients": fine["gradients"],
             "weights": weights,
-            "gradient_error": ret_fine["gradient_error"],
-            "inside_sphere": ret_fine["inside_sphere"],
+            "gradient_error": fine["gradient_error"],
+            "inside_sphere": fine["inside_sphere"],
         }
