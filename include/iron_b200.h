@@ -318,6 +318,18 @@ int ironb_neus_upsample(const float* ray_o, const float* ray_d, const float* z, 
  * (sdf [N][n], new_sdf [N][m]) travel with their samples. */
 int ironb_neus_merge(const float* z, const float* sdf, int n, const float* new_z, const float* new_sdf, int m, int64_t N,
                      float* out_z, float* out_sdf, void* stream);
+/* ---------------------------------------------------------------- plain nn.Linear layers on the tensor cores
+ * The stage-1 background model (NeRF, models/fields.py:241-322) is plain Linear + ReLU layers:
+ *   ironb_linear_fwd    y[M][ldc] = act(x[M][lda] W[N][ldb]^T + b)           (relu != 0: ReLU; bias may be NULL)
+ *   ironb_relu_mask     out = dy where y > 0 else 0                            (n elements, 16-byte aligned buffers)
+ *   ironb_linear_wgrad  dW[N][ldc] += dy[M][lda]^T x[M][ldb], db[N] += column sums of dy (zero both first; db may be NULL;
+ *                       scratch: ironb_gemm_tn_scratch_bytes(M, N, K))
+ * the input gradient is ironb_gemm_nt(dy, W^T).  N, K and the pitches multiples of 4; fp32-grade (3xTF32) arithmetic. */
+int ironb_linear_fwd(const float* x, int lda, const float* W, int ldb, const float* bias, int M, int N, int K, int relu, float* y,
+                     int ldc, void* stream);
+int ironb_relu_mask(const float* dy, const float* y, int64_t n, float* out, void* stream);
+int ironb_linear_wgrad(const float* dy, int lda, const float* x, int ldb, int M, int N, int K, float* dW, int ldc, float* db,
+                       void* scratch, void* stream);
 /* Gradient bucket of the data-parallel step (the reference is single-GPU, no interface replaced):
  * flat[off[t] .. off[t] + off[n + t]) = scale * src[t][:] for t < n, zeros where src[t] is NULL.  src_dev (n pointers) and
  * off_dev (n element offsets followed by n element counts) are DEVICE arrays, so the launch can be a CUDA-graph node.  max_numel sizes the grid. */

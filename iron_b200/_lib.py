@@ -95,6 +95,9 @@ _PROTOS = {
     "ironb_neus_sections": (_INT, [_P, _P, _P, _I64, _INT, _F, _INT, _P, _P, _P, _P, _P]),
     "ironb_neus_upsample": (_INT, [_P, _P, _P, _P, _I64, _INT, _INT, _F, _P, _P, _P]),
     "ironb_neus_merge": (_INT, [_P, _P, _INT, _P, _P, _INT, _I64, _P, _P, _P]),
+    "ironb_linear_fwd": (_INT, [_P, _INT, _P, _INT, _P, _INT, _INT, _INT, _INT, _P, _INT, _P]),
+    "ironb_relu_mask": (_INT, [_P, _P, _I64, _P, _P]),
+    "ironb_linear_wgrad": (_INT, [_P, _INT, _P, _INT, _INT, _INT, _INT, _P, _INT, _P, _P, _P]),
     "ironb_pack_tensors": (_INT, [_P, _P, _INT, _I64, _P, _F, _P]),
     "ironb_patch_loss_workspace_bytes": (_I64, [_INT, _INT, _INT]),
     "ironb_pyramid_l2": (_INT, [_P, _PI64, _P, _PI64, _INT, _INT, _INT, _P, _P, _PI64, _P, _I64, _P]),

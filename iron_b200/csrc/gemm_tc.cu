@@ -123,6 +123,33 @@ struct EpiStore {
     *reinterpret_cast<float4*>(C + (int64_t)m * ldc + n0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
 };
+// y = act(x W^T + b): a plain nn.Linear (+ ReLU) -- the background NeRF's layers (models/fields.py:281-322)
+struct EpiBiasAct {
+  const float* bias;     // [N] or null
+  float* C;
+  int ldc, relu;
+  __device__ __forceinline__ void operator()(int m, int n0, const float (&acc)[4]) const {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = acc[j] + (bias ? __ldg(bias + n0 + j) : 0.f);
+      if (relu) v[j] = fmaxf(v[j], 0.f);
+    }
+    *reinterpret_cast<float4*>(C + (int64_t)m * ldc + n0) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+// dx = (dy masked by the ReLU of the SAME layer's output y) W: the mask is applied to the A operand beforehand (relu_mask_kernel)
+__global__ void __launch_bounds__(256) relu_mask_kernel(const float* __restrict__ dy, const float* __restrict__ y, int64_t n,
+                                                        float* __restrict__ out) {
+  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 g = *reinterpret_cast<const float4*>(dy + i), a = *reinterpret_cast<const float4*>(y + i);
+    *reinterpret_cast<float4*>(out + i) = make_float4(a.x > 0.f ? g.x : 0.f, a.y > 0.f ? g.y : 0.f, a.z > 0.f ? g.z : 0.f,
+                                                      a.w > 0.f ? g.w : 0.f);
+  } else {
+    for (int64_t k = i; k < n; ++k) out[k] = y[k] > 0.f ? dy[k] : 0.f;
+  }
+}
 }  // namespace
 }  // namespace ironb
 
@@ -166,6 +193,37 @@ extern "C" int ironb_gemm_tn(const float* A, int lda, const float* B, int ldb, i
     return launch_wgrad_tc(A, lda, B, ldb, M, Nd, Kd, C, ldc, reinterpret_cast<float*>(scratch), as_stream(stream), "gemm_tn (tcgen05)");
   }
   return launch_gemm_tn(A, lda, B, ldb, M, Nd, Kd, C, ldc, as_stream(stream), "gemm_tn (simt)");
+}
+
+// ---- plain nn.Linear layers on the tensor cores (the stage-1 background NeRF: models/fields.py:241-322) -------------------
+// y[M][ldc] = act(x[M][lda] W[N][ldb]^T + b): N, K and the pitches multiples of 4.
+extern "C" int ironb_linear_fwd(const float* x, int lda, const float* W, int ldb, const float* bias, int M, int N, int K, int relu,
+                                float* y, int ldc, void* stream) {
+  IRONB_REQUIRE(x && W && y, "linear_fwd: null pointer");
+  IRONB_REQUIRE((N & 3) == 0 && (K & 3) == 0 && (lda & 3) == 0 && (ldb & 3) == 0 && (ldc & 3) == 0,
+                "linear_fwd: N, K and the row pitches must be multiples of 4");
+  EpiBiasAct ep{bias, y, ldc, relu};
+  if (tc::tc_enabled()) return tc::launch_gemm_nt_tc(x, lda, W, ldb, M, N, K, ep, as_stream(stream), "linear_fwd (tcgen05)", 0);
+  return launch_gemm_nt(x, lda, W, ldb, M, N, K, ep, as_stream(stream), "linear_fwd (simt)");
+}
+// out = dy where y > 0 else 0 (n elements): the ReLU backward of a layer, applied before its dgrad / wgrad products.
+extern "C" int ironb_relu_mask(const float* dy, const float* y, int64_t n, float* out, void* stream) {
+  IRONB_REQUIRE(dy && y && out && n >= 0, "relu_mask: bad arguments");
+  IRONB_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0,
+                "relu_mask: 16-byte aligned buffers");
+  if (n == 0) return IRONB_OK;
+  relu_mask_kernel<<<(unsigned)ceil_div64(ceil_div64(n, 4), 256), 256, 0, as_stream(stream)>>>(dy, y, n, out);
+  IRONB_CHECK_LAUNCH("relu_mask_kernel");
+  return IRONB_OK;
+}
+// dW[N][ldc] += dy[M][lda]^T x[M][ldb], db[N] += column sums of dy (db may be NULL): zero both first.  scratch:
+// ironb_gemm_tn_scratch_bytes(M, N, K).
+extern "C" int ironb_linear_wgrad(const float* dy, int lda, const float* x, int ldb, int M, int N, int K, float* dW, int ldc,
+                                  float* db, void* scratch, void* stream) {
+  IRONB_REQUIRE(dy && x && dW, "linear_wgrad: null pointer");
+  IRONB_REQUIRE((N & 3) == 0 && (K & 3) == 0 && (ldc & 3) == 0, "linear_wgrad: N, K, ldc must be multiples of 4");
+  return launch_wgrad_auto(dy, lda, x, ldb, M, N, K, dW, ldc, reinterpret_cast<float*>(scratch), as_stream(stream),
+                           "linear_wgrad", db, db ? N : 0, 1.f);
 }
 
 namespace ironb {

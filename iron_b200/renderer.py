@@ -39,9 +39,74 @@ class SingleVarianceNetwork(nn.Module):
         return torch.ones([len(x), 1], device=self.variance.device) * torch.exp(self.variance * 10.0)
 
 
+class _TCLinear(torch.autograd.Function):
+    """y = act(x W^T + b) for a plain nn.Linear on the tcgen05 GEMMs (3xTF32, fp32-grade): `ironb_linear_fwd`; backward =
+    ReLU mask (`ironb_relu_mask`), input gradient `ironb_gemm_nt(dy, W^T)`, weight + bias gradient `ironb_linear_wgrad`."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, relu):
+        lib = _lib.load()
+        x, Wc = _lib.f32c(x), _lib.f32c(W)
+        M, K = x.shape
+        N = Wc.shape[0]
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.ironb_linear_fwd(_lib.ptr(x), K, _lib.ptr(Wc), K, _lib.ptr(None if b is None else _lib.f32c(b)), M, N, K,
+                                            int(relu), _lib.ptr(y), N, _lib.stream()), "linear_fwd")
+        ctx.relu = bool(relu)
+        ctx.save_for_backward(x, Wc, y if relu else None)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, W, y = ctx.saved_tensors
+        M, K = x.shape
+        N = W.shape[0]
+        dev = x.device
+        dy = _lib.f32c(dy)
+        with torch.cuda.device(dev):
+            if ctx.relu:
+                dym = torch.empty_like(dy)
+                _lib.check(lib.ironb_relu_mask(_lib.ptr(dy), _lib.ptr(y), M * N, _lib.ptr(dym), _lib.stream()), "relu_mask")
+            else:
+                dym = dy
+            dx = None
+            if ctx.needs_input_grad[0]:
+                Wt = W.t().contiguous()
+                dx = torch.empty(M, K, dtype=torch.float32, device=dev)
+                _lib.check(lib.ironb_gemm_nt(_lib.ptr(dym), N, _lib.ptr(Wt), N, M, K, N, _lib.ptr(dx), K, _gemm_nt_mode(lib),
+                                             _lib.stream()), "linear dgrad")
+            dW = torch.zeros(N, K, dtype=torch.float32, device=dev)
+            db = torch.zeros(N, dtype=torch.float32, device=dev) if ctx.needs_input_grad[2] else None
+            scratch = torch.empty(max(int(lib.ironb_gemm_tn_scratch_bytes(M, N, K)), 16), dtype=torch.uint8, device=dev)
+            _lib.check(lib.ironb_linear_wgrad(_lib.ptr(dym), N, _lib.ptr(x), K, M, N, K, _lib.ptr(dW), K, _lib.ptr(db),
+                                              _lib.ptr(scratch), _lib.stream()), "linear_wgrad")
+        return dx, dW, db, None
+
+
+def _gemm_nt_mode(lib):
+    """ironb_gemm_nt's mode argument for the library's current GEMM arithmetic: 0 = FFMA, 2 = 3xTF32 on tcgen05."""
+    cur = lib.ironb_set_gemm_mode(2)
+    lib.ironb_set_gemm_mode(cur)
+    return 0 if cur == 0 else 2
+
+
+def _linear(layer, h, relu):
+    """A plain nn.Linear (+ ReLU): on this library's GEMMs when the shapes allow (fan-in and fan-out multiples of 4), else ATen
+    (the 1- and 3-wide heads and the 283-wide view layer of the NeRF: < 3 % of its FLOPs)."""
+    W = layer.weight
+    if h.is_cuda and W.shape[0] % 4 == 0 and W.shape[1] % 4 == 0 and h.dim() == 2:
+        return _TCLinear.apply(h, W, layer.bias, relu)
+    out = layer(h)
+    return F.relu(out) if relu else out
+
+
 class NeRF(nn.Module):
     """The background model, models/fields.py:241-322 (use_viewdirs=True): plain Linear layers, ReLU, one skip; same module
-    names and state-dict keys (`pts_linears.{i}`, `views_linears.0`, `feature_linear`, `alpha_linear`, `rgb_linear`)."""
+    names and state-dict keys (`pts_linears.{i}`, `views_linears.0`, `feature_linear`, `alpha_linear`, `rgb_linear`).  The
+    256-wide layers run on the tensor cores (`_TCLinear`)."""
 
     def __init__(self, D=8, W=256, d_in=3, d_in_view=3, multires=0, multires_view=0, output_ch=4, skips=(4,), use_viewdirs=False):
         super().__init__()
@@ -72,15 +137,15 @@ class NeRF(nn.Module):
             input_views = self.embed_fn_view(input_views)
         h = input_pts
         for i in range(len(self.pts_linears)):
-            h = F.relu(self.pts_linears[i](h))
+            h = _linear(self.pts_linears[i], h, True)
             if i in self.skips:
                 h = torch.cat([input_pts, h], -1)
         assert self.use_viewdirs, "NeRF: use_viewdirs=False has no forward in the reference either (fields.py:321)"
-        alpha = self.alpha_linear(h)
-        h = torch.cat([self.feature_linear(h), input_views], -1)
+        alpha = _linear(self.alpha_linear, h, False)
+        h = torch.cat([_linear(self.feature_linear, h, False), input_views], -1)
         for i in range(len(self.views_linears)):
-            h = F.relu(self.views_linears[i](h))
-        return alpha, self.rgb_linear(h)
+            h = _linear(self.views_linears[i], h, True)
+        return alpha, _linear(self.rgb_linear, h, False)
 
 
 def sample_pdf(bins, weights, n_samples, det=False):
