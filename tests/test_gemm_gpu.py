@@ -102,3 +102,44 @@ def test_gemm_tn(M, Nd, Kd, mode):
     rel = ((C.double() - ref).abs() / scale).max().item()
     print(f"tn mode {mode} M={M} Nd={Nd} Kd={Kd}: max |err| / scale = {rel:.2e}")
     assert torch.isfinite(C).all() and rel < 2e-6, rel
+
+
+def test_gemm_tc_two_streams_bitwise():
+    """Regression test of round 1's multi-stream fault (profiles/r2j_multistream_fault_rootcause.md): two streams of 3xTF32 GEMM
+    grids next to a copy stream, every output compared BITWISE with a quiet single-stream run of the same (deterministic)
+    kernel.  With the old splitter protocol (IRONB_SPLIT_STRICT=0) this shape died with 'unspecified launch failure' within
+    ~9,000 launches (3 s); the fixed kernel ran 190 k launches clean.  Here: ~4 s of it."""
+    import time
+    from iron_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    M, N, K = 16384, 512, 2048
+    A = [torch.randn(M, K, generator=g).to(DEV) for _ in range(2)]
+    B = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    hog_src = torch.empty(64 << 20, dtype=torch.float32, device=DEV).normal_()
+    hog_dst = torch.empty_like(hog_src)
+    streams = [torch.cuda.Stream() for _ in range(3)]
+
+    def gemm(a, c, st):
+        _lib.check(lib.ironb_gemm_nt(_lib.ptr(a), K, _lib.ptr(B), K, M, N, K, _lib.ptr(c), N, 2, st.cuda_stream), "gemm_nt")
+
+    ref = [torch.empty(M, N, device=DEV) for _ in range(2)]
+    for i in range(2):
+        gemm(A[i], ref[i], torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    out = [torch.empty(M, N, device=DEV) for _ in range(2)]
+    bad = torch.zeros(2, dtype=torch.int64, device=DEV)
+    launches, t0 = 0, time.time()
+    while time.time() - t0 < 4.0:
+        for _ in range(10):
+            with torch.cuda.stream(streams[2]):
+                hog_dst.copy_(hog_src, non_blocking=True)
+            for i in range(2):
+                with torch.cuda.stream(streams[i]):
+                    for _ in range(4):
+                        gemm(A[i], out[i], streams[i])
+                        bad[i] += (out[i] != ref[i]).any().to(torch.int64)
+            launches += 8
+        torch.cuda.synchronize()
+    assert bad.tolist() == [0, 0], f"{bad.tolist()} mismatching launches of {launches}"
+    print(f"two-stream 3xTF32 GEMM: {launches} launches bit-identical to the quiet run")
