@@ -371,7 +371,10 @@ BWs carve_b(const ironb_mlp_layout* lay, int64_t N, unsigned char* base) {
   memset(&w, 0, sizeof(w));
   int64_t off = 0;
   auto take = [&](int64_t bytes) { unsigned char* p = base ? base + off : nullptr; off += (bytes + 255) / 256 * 256; return p; };
-  int64_t cap = 16 * N;                     // sampler items per pass: 50 % unfinished rays fit in one pass
+  // sampler items per pass.  Small calls (the training patch) take every ray in ONE pass: a second pass is 9 launches that
+  // find nothing to do whenever at most half of the rays reach the sampler, and 32 N rows are only ~1 GB of workspace there.
+  // Large calls keep 16 N (50 % unfinished rays fit in one pass): the workspace grows with 8.5 KB per row at H = 512.
+  int64_t cap = (N <= 8192 ? 32 : 16) * N;
   if (cap < 4096) cap = 4096;
   if (cap > (1 << 21)) cap = (1 << 21);
   if (cap < N) cap = N;
