@@ -21,8 +21,16 @@
  *   ironb_camera_rays                    Camera.get_rays + intersect_sphere   models/raytracer.py:254-286, 223-237
  *   ironb_trace                          RayTracer.forward (sphere_tracing, ray_sampler, rootfind)
  *                                                                             models/raytracer.py:45-220
- *   ironb_depth_closing                  kornia.morphology.closing in raytrace_camera (fill_holes)
- *                                                                             models/raytracer.py:554-557
+ *   ironb_depth_closing / ironb_sobel_depth  kornia closing / sobel in raytrace_camera (fill_holes, edge detection)
+ *                                                                             models/raytracer.py:554-557, 569
+ *   ironb_composite_fwd / _bwd           CompositeRenderer.forward            models/renderer_ggx.py:781-858 (+ autograd)
+ *   ironb_pyramid_l2 / ironb_ssim_loss   PyramidL2Loss, ssim_loss_fn          models/image_losses.py:13-158 (+ autograd)
+ *   ironb_adam_step                      six torch.optim.Adam instances       render_surface.py:112-113, 651-653
+ *   ironb_neus_composite_fwd / _bwd, ironb_neus_upsample, ironb_neus_merge, ironb_neus_sections
+ *                                        NeuSRenderer.render_core / up_sample / cat_z_vals / sample_pdf
+ *                                                                             models/renderer.py:43-73, 192-351 (+ autograd)
+ *   ironb_linear_fwd / _wgrad, ironb_relu_mask  the nn.Linear layers of the background NeRF  models/fields.py:241-322
+ *   ironb_pack_tensors                   (new: the gradient bucket of the data-parallel step; the reference is single-GPU)
  */
 #ifndef IRON_B200_H
 #define IRON_B200_H
