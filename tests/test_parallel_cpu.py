@@ -93,3 +93,28 @@ def test_shard_range_partitions_exactly():
     assert all(0 <= x <= 448 and 0 <= y <= 448 for x, y in corners)
     near = {crop_for_rank(r, 64, stride=8) for r in range(8)}                  # the bench's equal-work windows
     assert len(near) == 8 and all(abs(x - 224) <= 8 and abs(y - 224) <= 8 for x, y in near)
+
+
+def test_bench_view_sharding_orbits_the_fixture_camera(monkeypatch):
+    """bench.py's default weak-scaling inputs: rank r renders the centre crop of the fixture view orbited by r x 45 degrees
+    about the y-axis -- same distance and elevation, rank 0 = the canonical view; 'windows' keeps one view."""
+    import numpy as np
+    import bench
+    from oracle import iron_oracle as O
+    monkeypatch.delenv("IRONB_BENCH_SHARD", raising=False)
+    monkeypatch.delenv("IRONB_BENCH_CROP_STRIDE", raising=False)
+    W0 = np.array(O.FIXTURE_W2C, dtype=np.float64).reshape(4, 4)
+    assert np.array_equal(bench.view_w2c(0), W0)
+    c0 = np.linalg.inv(W0)[:3, 3]
+    centres = []
+    for r in range(8):
+        W = bench.view_w2c(r)
+        c = np.linalg.inv(W)[:3, 3]
+        centres.append(c)
+        assert abs(np.linalg.norm(c) - np.linalg.norm(c0)) < 1e-9 and abs(c[1] - c0[1]) < 1e-9      # same distance, same height
+        assert np.allclose(W[:3, :3] @ W[:3, :3].T, np.eye(3), atol=1e-12)                            # still a rotation
+        assert bench.crop_corner(r, 64) == (224, 224)
+    assert min(np.linalg.norm(centres[i] - centres[j]) for i in range(8) for j in range(i)) > 1.0     # eight distinct views
+    monkeypatch.setenv("IRONB_BENCH_SHARD", "windows")
+    assert np.array_equal(bench.view_w2c(3), W0)
+    assert len({bench.crop_corner(r, 64) for r in range(8)}) == 8
